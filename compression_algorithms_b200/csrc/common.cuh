@@ -1,0 +1,116 @@
+// Shared device/host helpers for the sm_100a kernels of libb200comp.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define B200_OK 0
+#define B200_ERR_CUDA 1
+#define B200_ERR_ARG 2
+#define B200_ERR_CAPACITY 3
+#define B200_ERR_DOMAIN 4   /* the reference would exit(1) on this input */
+#define B200_ERR_FORMAT 5   /* corrupt stream */
+
+extern thread_local char g_b200_err[512];
+
+#define B200_SET_ERR(...) snprintf(g_b200_err, sizeof(g_b200_err), __VA_ARGS__)
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (expr);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            B200_SET_ERR("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+            return B200_ERR_CUDA;                                                        \
+        }                                                                                \
+    } while (0)
+
+#define B200_TRY(expr)                 \
+    do {                               \
+        int rc_ = (expr);              \
+        if (rc_ != B200_OK) return rc_; \
+    } while (0)
+
+// One growable device scratch arena + the stream every kernel of a context runs on.
+struct b200_ctx {
+    int          device;
+    cudaStream_t stream;
+    bool         own_stream;
+    int          sm_count;
+    // named scratch buffers, grown on demand and kept
+    static const int kSlots = 16;
+    void*        buf[kSlots];
+    size_t       cap[kSlots];
+    // pinned host staging for small results
+    void*        pinned;
+    size_t       pinned_cap;
+    uint64_t     launches;  // kernels launched through this context (bench "gpu_launches")
+    uint32_t     lz_epoch;  // last epoch tag used in this context's LZ77 table arena
+};
+
+int b200_scratch(b200_ctx* ctx, int slot, size_t bytes, void** out);
+int b200_pinned(b200_ctx* ctx, size_t bytes, void** out);
+
+static inline unsigned ceil_div_u64(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= (unsigned)d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= (unsigned)d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// One step of a 1024-thread CTA-wide scan: returns the exclusive prefix of v inside
+// the tile and the tile total. warp_tot: 33 u64 of shared memory. Must be called
+// by all 1024 threads.
+__device__ __forceinline__ uint64_t cta_scan_step(uint64_t v, uint64_t* warp_tot, uint64_t* tile_total) {
+    const uint64_t incl = warp_incl_scan_u64(v);
+    const unsigned w = threadIdx.x >> 5;
+    __syncthreads();  // protect warp_tot from the previous step
+    if (lane_id() == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        const uint64_t t = warp_tot[lane_id()];
+        const uint64_t ti = warp_incl_scan_u64(t);
+        warp_tot[lane_id()] = ti - t;
+        if (lane_id() == 31) warp_tot[32] = ti;
+    }
+    __syncthreads();
+    *tile_total = warp_tot[32];
+    return warp_tot[w] + incl - v;
+}
+
+// murmur3-style hash of one u32 key, seed 0, no length xor, masked to 2^20 slots
+// (reference: algorithms/lz77/lz77.c:13-41, algorithms/deflate/lz77.c:14-42).
+__host__ __device__ __forceinline__ uint32_t lz_hash(uint32_t k) {
+    k *= 0xcc9e2d51u;
+    k = (k << 15) | (k >> 17);
+    k *= 0x1b873593u;
+    uint32_t h = k;
+    h = ((h << 13) | (h >> 19)) * 5u + 0xe6546b64u;
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h & 0xFFFFFu;
+}
+#endif

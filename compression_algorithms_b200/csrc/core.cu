@@ -1,0 +1,91 @@
+// Context, scratch memory and copy helpers of libb200comp.so.
+#include "common.cuh"
+#include "../../include/b200comp.h"
+
+thread_local char g_b200_err[512] = "";
+
+extern "C" const char* b200_last_error(void) { return g_b200_err; }
+
+extern "C" int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int b200_ctx_create(b200_ctx** out, int device, void* cuda_stream) {
+    if (!out) { B200_SET_ERR("b200_ctx_create: out is NULL"); return B200_ERR_ARG; }
+    int n = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n));
+    if (n <= 0 || device < 0 || device >= n) {
+        B200_SET_ERR("b200_ctx_create: no CUDA device %d (found %d); there is no CPU fallback", device, n);
+        return B200_ERR_CUDA;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    b200_ctx* c = new b200_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+    else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return B200_OK;
+}
+
+extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < b200_ctx::kSlots; ++i) if (ctx->buf[i]) cudaFree(ctx->buf[i]);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int b200_ctx_sync(b200_ctx* ctx) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+extern "C" uint64_t b200_ctx_launches(b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b200_scratch(b200_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (slot < 0 || slot >= b200_ctx::kSlots) { B200_SET_ERR("bad scratch slot %d", slot); return B200_ERR_ARG; }
+    if (ctx->cap[slot] < bytes) {
+        if (ctx->buf[slot]) {
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(cudaFree(ctx->buf[slot]));
+            ctx->buf[slot] = nullptr; ctx->cap[slot] = 0;
+        }
+        size_t want = bytes + (bytes >> 3) + 256;
+        CUDA_TRY(cudaMalloc(&ctx->buf[slot], want));
+        ctx->cap[slot] = want;
+    }
+    *out = ctx->buf[slot];
+    return B200_OK;
+}
+
+int b200_pinned(b200_ctx* ctx, size_t bytes, void** out) {
+    if (ctx->pinned_cap < bytes) {
+        if (ctx->pinned) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); CUDA_TRY(cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; }
+        CUDA_TRY(cudaMallocHost(&ctx->pinned, bytes + 256));
+        ctx->pinned_cap = bytes + 256;
+    }
+    *out = ctx->pinned;
+    return B200_OK;
+}
+
+extern "C" int b200_dev_alloc(void** d_ptr, uint64_t bytes) { CUDA_TRY(cudaMalloc(d_ptr, bytes ? bytes : 1)); return B200_OK; }
+extern "C" int b200_dev_free(void* d_ptr) { CUDA_TRY(cudaFree(d_ptr)); return B200_OK; }
+extern "C" int b200_host_alloc(void** h_ptr, uint64_t bytes) { CUDA_TRY(cudaMallocHost(h_ptr, bytes ? bytes : 1)); return B200_OK; }
+extern "C" int b200_host_free(void* h_ptr) { CUDA_TRY(cudaFreeHost(h_ptr)); return B200_OK; }
+extern "C" int b200_copy_h2d(b200_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes) {
+    CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream)); return B200_OK;
+}
+extern "C" int b200_copy_d2h(b200_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes) {
+    CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); return B200_OK;
+}
+extern "C" int b200_memset(b200_ctx* ctx, void* d_dst, int value, uint64_t bytes) {
+    CUDA_TRY(cudaMemsetAsync(d_dst, value, bytes, ctx->stream)); return B200_OK;
+}

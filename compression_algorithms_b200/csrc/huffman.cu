@@ -1,0 +1,595 @@
+// Huffman: histogram, exact heap-order table build, scan-based MSB-first bit packing
+// and table-lookup decoding for sm_100a.
+//
+// Reference being replaced (bit-exact): /root/reference/algorithms/huffman/huffman.c
+//   histogram :184-187, heap :100-159, tree :189-211, codes :217-250,
+//   write_bits :18-48, sizes :318-320, decoder :330-364.
+//
+// Data layout in HBM: input bytes; output = host-endian u32 words, MSB-first, each
+// table scope ("block") starting on a word boundary; a side buffer (b200_huff_layout)
+// with per-block tables and the chunk/sub-chunk bit index used for parallel decode.
+#include "common.cuh"
+#include "../../include/b200comp.h"
+
+namespace {
+
+constexpr uint32_t CHUNK = B200_HUFF_CHUNK;  // symbols per encode CTA
+constexpr uint32_t SUB = B200_HUFF_SUB;      // symbols per decode thread
+constexpr uint32_t SUBS_PER_CHUNK = CHUNK / SUB;
+constexpr uint32_t TILE_CHUNKS = 16;         // chunks per histogram / decode-lut tile
+constexpr uint32_t LUT_BITS = 12;
+
+inline uint64_t eff_block(uint64_t n, uint64_t bs) {
+    if (bs == 0 || bs >= n) return ((n ? n : 1) + CHUNK - 1) / CHUNK * CHUNK;
+    return bs;
+}
+
+// ---------------------------------------------------------------- K1 histogram
+// One CTA per 64 KiB tile of one block; 16-byte loads; one private 256-bin
+// histogram per warp in shared memory, merged into the block's global histogram.
+__global__ void __launch_bounds__(256) huff_hist_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t bs,
+                                                        uint32_t tiles_per_block, uint32_t* __restrict__ freq) {
+    __shared__ uint32_t h[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t b = blockIdx.x / tiles_per_block, k = blockIdx.x % tiles_per_block;
+    const uint64_t start = b * bs + k * (uint64_t)(TILE_CHUNKS * CHUNK);
+    uint64_t end = start + TILE_CHUNKS * CHUNK;
+    if (end > (b + 1) * bs) end = (b + 1) * bs;
+    if (end > n) end = n;
+    uint32_t* my = h[threadIdx.x >> 5];
+    for (uint64_t i = start + (uint64_t)threadIdx.x * 16; i < end; i += 256 * 16) {
+        if (i + 16 <= end) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                atomicAdd(&my[w[q] & 0xFF], 1u);
+                atomicAdd(&my[(w[q] >> 8) & 0xFF], 1u);
+                atomicAdd(&my[(w[q] >> 16) & 0xFF], 1u);
+                atomicAdd(&my[w[q] >> 24], 1u);
+            }
+        } else {
+            for (uint64_t j = i; j < end; ++j) atomicAdd(&my[in[j]], 1u);
+        }
+    }
+    __syncthreads();
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += h[w][threadIdx.x];
+    if (s) atomicAdd(&freq[b * 256 + threadIdx.x], s);
+}
+
+// ---------------------------------------------------------------- K2 table build
+// One warp per block. Lane 0 replays the reference's binary min-heap exactly
+// (enqueue in symbol order, strict '<' sift-up, left-then-right sift-down, dequeue
+// moves the last element to the root); afterwards the 32 lanes walk leaf->root in
+// parallel to produce codes and lengths.
+__global__ void __launch_bounds__(32) huff_build_kernel(const uint32_t* __restrict__ freq, uint32_t* __restrict__ codes,
+                                                       uint8_t* __restrict__ lens, int16_t* __restrict__ tree,
+                                                       uint32_t* __restrict__ meta) {
+    __shared__ uint32_t fr[256];
+    __shared__ uint32_t nfreq[511];
+    __shared__ int16_t  left[511], right[511], parent[511];
+    __shared__ uint8_t  isright[511];
+    __shared__ uint32_t hf[256];
+    __shared__ uint16_t hn[256];
+    __shared__ int s_nn, s_root, s_distinct;
+    const uint64_t b = blockIdx.x;
+    const unsigned lane = threadIdx.x;
+    for (int s = lane; s < 256; s += 32) fr[s] = freq[b * 256 + s];
+    __syncwarp();
+    if (lane == 0) {
+        int size = 0, nn = 0;
+        for (int s = 0; s < 256; ++s) {
+            const uint32_t f = fr[s];
+            if (!f) continue;
+            nfreq[nn] = f; left[nn] = -1; right[nn] = (int16_t)s; parent[nn] = -1; isright[nn] = 0;
+            int idx = size++;
+            hf[idx] = f; hn[idx] = (uint16_t)nn; ++nn;
+            while (idx > 0) {
+                const int p = (idx - 1) >> 1;
+                if (!(hf[idx] < hf[p])) break;
+                const uint32_t tf = hf[idx]; hf[idx] = hf[p]; hf[p] = tf;
+                const uint16_t tn = hn[idx]; hn[idx] = hn[p]; hn[p] = tn;
+                idx = p;
+            }
+        }
+        const int distinct = nn;
+        while (size > 1) {
+            int pick[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                pick[q] = hn[0];
+                --size;
+                hf[0] = hf[size]; hn[0] = hn[size];
+                int idx = 0;
+                for (;;) {
+                    const int l = 2 * idx + 1, r = l + 1;
+                    int sm = idx; uint32_t fs = hf[idx];
+                    if (l < size && hf[l] < fs) { sm = l; fs = hf[l]; }
+                    if (r < size && hf[r] < fs) { sm = r; }
+                    if (sm == idx) break;
+                    const uint32_t tf = hf[idx]; hf[idx] = hf[sm]; hf[sm] = tf;
+                    const uint16_t tn = hn[idx]; hn[idx] = hn[sm]; hn[sm] = tn;
+                    idx = sm;
+                }
+            }
+            const uint32_t f = nfreq[pick[0]] + nfreq[pick[1]];  // u32 wrap like init_node(uint32_t)
+            nfreq[nn] = f; left[nn] = (int16_t)pick[0]; right[nn] = (int16_t)pick[1]; parent[nn] = -1; isright[nn] = 0;
+            parent[pick[0]] = (int16_t)nn; isright[pick[0]] = 0;
+            parent[pick[1]] = (int16_t)nn; isright[pick[1]] = 1;
+            int idx = size++;
+            hf[idx] = f; hn[idx] = (uint16_t)nn; ++nn;
+            while (idx > 0) {
+                const int p = (idx - 1) >> 1;
+                if (!(hf[idx] < hf[p])) break;
+                const uint32_t tf = hf[idx]; hf[idx] = hf[p]; hf[p] = tf;
+                const uint16_t tn = hn[idx]; hn[idx] = hn[p]; hn[p] = tn;
+                idx = p;
+            }
+        }
+        s_nn = nn; s_distinct = distinct; s_root = distinct ? hn[0] : 0;
+    }
+    __syncwarp();
+    const int nn = s_nn, distinct = s_distinct, root = s_root;
+    uint32_t maxlen = 0;
+    for (int v = lane; v < distinct; v += 32) {
+        uint32_t code = 0, len = 0;
+        int u = v;
+        while (u != root) {
+            if (len < 32) code |= (uint32_t)isright[u] << len;
+            ++len;
+            u = parent[u];
+        }
+        const int sym = right[v];
+        codes[b * 256 + sym] = code;
+        lens[b * 256 + sym] = (uint8_t)(len > 255 ? 255 : len);
+        maxlen = max(maxlen, len);
+    }
+    for (int v = lane; v < nn; v += 32) {
+        tree[(b * 511 + v) * 2 + 0] = left[v];
+        tree[(b * 511 + v) * 2 + 1] = right[v];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, d));
+    if (lane == 0) {
+        uint32_t status = 0;
+        if (distinct < 2) status = 1;       // reference: exit(1), huffman.c:278-281 / :149-152
+        else if (maxlen > 32) status = 2;   // reference: silent corruption (uint32_t code, BIT_MASK[33])
+        meta[b * 4 + 0] = status; meta[b * 4 + 1] = (uint32_t)distinct; meta[b * 4 + 2] = (uint32_t)root; meta[b * 4 + 3] = maxlen;
+    }
+}
+
+// ---------------------------------------------------------------- K3 chunk bit counts
+__global__ void __launch_bounds__(256) huff_chunkbits_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t cpb,
+                                                             const uint8_t* __restrict__ lens, uint32_t* __restrict__ chunk_bits) {
+    __shared__ uint8_t sl[256];
+    __shared__ uint32_t wsum[8];
+    const uint64_t c = blockIdx.x, b = c / cpb;
+    sl[threadIdx.x] = lens[b * 256 + threadIdx.x];
+    __syncthreads();
+    const uint64_t i = c * CHUNK + (uint64_t)threadIdx.x * 16;
+    uint32_t bits = 0;
+    if (i + 16 <= n) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bits += sl[w[q] & 0xFF] + sl[(w[q] >> 8) & 0xFF] + sl[(w[q] >> 16) & 0xFF] + sl[w[q] >> 24];
+    } else {
+        for (uint64_t j = i; j < n && j < i + 16; ++j) bits += sl[in[j]];
+    }
+    bits = warp_sum_u32(bits);
+    if (lane_id() == 0) wsum[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        chunk_bits[c] = t;
+    }
+}
+
+// ---------------------------------------------------------------- K4 offsets (single CTA)
+// Exclusive scans that place every chunk: P = scan(chunk_bits); per block
+// bits -> ceil/32 words -> scan -> first word; absolute bit offset per chunk.
+// Also zeroes the words shared by two chunks so the encoder can OR into them.
+__global__ void __launch_bounds__(1024) huff_offsets_kernel(const uint32_t* __restrict__ chunk_bits, uint64_t nchunks,
+                                                            uint32_t cpb, uint64_t nblocks, uint64_t* __restrict__ P,
+                                                            uint64_t* __restrict__ block_bits, uint64_t* __restrict__ block_word,
+                                                            uint64_t* __restrict__ chunk_off, uint32_t* __restrict__ words,
+                                                            uint64_t words_capacity, uint64_t* __restrict__ info) {
+    __shared__ uint64_t warp_tot[33];
+    uint64_t carry = 0, tot;
+    for (uint64_t base = 0; base < nchunks; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t v = i < nchunks ? chunk_bits[i] : 0;
+        const uint64_t ex = cta_scan_step(v, warp_tot, &tot);
+        if (i < nchunks) P[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) P[nchunks] = carry;
+    __syncthreads();
+    carry = 0;
+    for (uint64_t base = 0; base < nblocks; base += 1024) {
+        const uint64_t b = base + threadIdx.x;
+        uint64_t wds = 0;
+        if (b < nblocks) {
+            const uint64_t first = b * cpb;
+            uint64_t last = first + cpb; if (last > nchunks) last = nchunks;
+            const uint64_t bits = P[last] - P[first];
+            block_bits[b] = bits;
+            wds = (bits + 31) >> 5;
+        }
+        const uint64_t ex = cta_scan_step(wds, warp_tot, &tot);
+        if (b < nblocks) block_word[b] = carry + ex;
+        carry += tot;
+    }
+    const uint64_t total_words = carry;
+    if (threadIdx.x == 0) {
+        block_word[nblocks] = total_words;
+        info[0] = total_words;
+        info[1] = total_words > words_capacity ? 1 : 0;
+    }
+    __syncthreads();
+    const bool fits = total_words <= words_capacity;
+    for (uint64_t c = threadIdx.x; c < nchunks; c += 1024) {
+        const uint64_t b = c / cpb;
+        const uint64_t off = block_word[b] * 32 + (P[c] - P[b * cpb]);
+        chunk_off[c] = off;
+        if (fits && (off & 31)) words[off >> 5] = 0;
+    }
+}
+
+// ---------------------------------------------------------------- K5 encode
+// One CTA per chunk of 4096 symbols; thread t owns 16 consecutive symbols. A block
+// exclusive scan of the code lengths gives each thread its bit offset; codes are
+// packed MSB-first into a shared-memory image of the output words (OR only on the
+// words a thread shares with its neighbours), then stored coalesced.
+__global__ void __launch_bounds__(256) huff_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t cpb,
+                                                          const uint32_t* __restrict__ codes, const uint8_t* __restrict__ lens,
+                                                          const uint32_t* __restrict__ meta, const uint32_t* __restrict__ chunk_bits,
+                                                          const uint64_t* __restrict__ chunk_off, uint32_t* __restrict__ sub_off,
+                                                          uint32_t* __restrict__ words, const uint64_t* __restrict__ info) {
+    __shared__ uint32_t sc[256];
+    __shared__ uint8_t  sl[256];
+    __shared__ uint32_t stage[CHUNK + 2];
+    __shared__ uint32_t wtot[8];
+    if (info[1]) return;  // output does not fit
+    const uint64_t c = blockIdx.x, b = c / cpb;
+    if (meta[b * 4 + 0]) return;  // block the reference would not encode
+    sc[threadIdx.x] = codes[b * 256 + threadIdx.x];
+    sl[threadIdx.x] = lens[b * 256 + threadIdx.x];
+    const uint64_t A = chunk_off[c];
+    const uint32_t T = chunk_bits[c];
+    const uint32_t r = (uint32_t)(A & 31);
+    const uint32_t nw = (r + T + 31) >> 5;
+    for (uint32_t j = threadIdx.x; j < nw; j += 256) stage[j] = 0;
+    __syncthreads();
+
+    const uint64_t i0 = c * CHUNK + (uint64_t)threadIdx.x * 16;
+    uint8_t sym[16];
+    uint32_t cnt = 0;
+    if (i0 + 16 <= n) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i0));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            sym[4 * q + 0] = w[q] & 0xFF; sym[4 * q + 1] = (w[q] >> 8) & 0xFF;
+            sym[4 * q + 2] = (w[q] >> 16) & 0xFF; sym[4 * q + 3] = w[q] >> 24;
+        }
+        cnt = 16;
+    } else if (i0 < n) {
+        cnt = (uint32_t)(n - i0);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sym[q] = (uint32_t)q < cnt ? in[i0 + q] : 0;
+    }
+    uint32_t mybits = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) if ((uint32_t)q < cnt) mybits += sl[sym[q]];
+    // block exclusive scan of mybits
+    const uint32_t incl = warp_incl_scan_u32(mybits);
+    if (lane_id() == 31) wtot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) if ((uint32_t)w < (threadIdx.x >> 5)) wbase += wtot[w];
+    const uint32_t ex = wbase + incl - mybits;
+    if ((threadIdx.x & 15) == 0) sub_off[c * SUBS_PER_CHUNK + (threadIdx.x >> 4)] = ex;
+
+    if (mybits) {
+        uint32_t pos = r + ex;
+        uint32_t wi = pos >> 5;
+        uint32_t fill = pos & 31;       // bits of word wi that belong to earlier threads
+        uint64_t acc = 0;               // left-aligned: top `have` bits are meaningful
+        uint32_t have = fill;
+        bool first = fill != 0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            if ((uint32_t)q < cnt) {
+                const uint32_t L = sl[sym[q]];
+                const uint64_t code = sc[sym[q]];
+                if (L) acc |= code << (64 - have - L);
+                have += L;
+                if (have >= 32) {
+                    const uint32_t wv = (uint32_t)(acc >> 32);
+                    if (first) { atomicOr(&stage[wi], wv); first = false; }
+                    else stage[wi] = wv;
+                    ++wi; acc <<= 32; have -= 32;
+                }
+            }
+        }
+        if (have) atomicOr(&stage[wi], (uint32_t)(acc >> 32));
+    }
+    __syncthreads();
+    uint32_t* dst = words + (A >> 5);
+    // the last word is shared only if another chunk of the same block follows
+    const bool tail_shared = ((r + T) & 31) != 0 && (c + 1) % cpb != 0 && c + 1 < gridDim.x;
+    for (uint32_t j = threadIdx.x; j < nw; j += 256) {
+        const uint32_t v = stage[j];
+        if ((j == 0 && r != 0) || (j == nw - 1 && tail_shared)) atomicOr(&dst[j], v);
+        else dst[j] = v;
+    }
+}
+
+// ---------------------------------------------------------------- K6 decode
+// One CTA per tile of 16 chunks of one block (256 threads, one 256-symbol sub-chunk
+// each). A 12-bit primary table in shared memory resolves codes up to 12 bits in
+// one lookup; longer (rare) codes are matched against the short list of long codes.
+__global__ void __launch_bounds__(256) huff_decode_kernel(const uint32_t* __restrict__ words, uint64_t total_words,
+                                                          uint64_t n, uint64_t bs, uint32_t cpb, uint32_t tiles_per_block,
+                                                          const uint32_t* __restrict__ codes, const uint8_t* __restrict__ lens,
+                                                          const uint64_t* __restrict__ chunk_off, const uint32_t* __restrict__ sub_off,
+                                                          uint8_t* __restrict__ out) {
+    __shared__ uint16_t lut[1u << LUT_BITS];
+    __shared__ uint32_t sc[256];
+    __shared__ uint8_t  sl[256];
+    __shared__ uint8_t  long_sym[256];
+    __shared__ uint32_t n_long;
+    const uint64_t b = blockIdx.x / tiles_per_block, k = blockIdx.x % tiles_per_block;
+    if (threadIdx.x == 0) n_long = 0;
+    sc[threadIdx.x] = codes[b * 256 + threadIdx.x];
+    sl[threadIdx.x] = lens[b * 256 + threadIdx.x];
+    __syncthreads();
+    {
+        const uint32_t s = threadIdx.x;
+        const uint32_t L = sl[s];
+        if (L > LUT_BITS) {
+            const uint32_t slot = atomicAdd(&n_long, 1u);
+            long_sym[slot] = (uint8_t)s;
+            lut[sc[s] >> (L - LUT_BITS)] = 0;
+        }
+    }
+    const unsigned warp = threadIdx.x >> 5;
+    for (uint32_t s = warp; s < 256; s += 8) {
+        const uint32_t L = sl[s];
+        if (L == 0 || L > LUT_BITS) continue;
+        const uint32_t base = sc[s] << (LUT_BITS - L), count = 1u << (LUT_BITS - L);
+        const uint16_t e = (uint16_t)(0x8000u | (L << 8) | s);
+        for (uint32_t i = lane_id(); i < count; i += 32) lut[base + i] = e;
+    }
+    __syncthreads();
+
+    const uint64_t chunk = b * cpb + (uint64_t)k * TILE_CHUNKS + (threadIdx.x >> 4);
+    const uint64_t sub = chunk * SUBS_PER_CHUNK + (threadIdx.x & 15);
+    const uint64_t sym0 = sub * SUB;
+    uint64_t blk_end = (b + 1) * bs; if (blk_end > n) blk_end = n;
+    if ((threadIdx.x >> 4) + k * TILE_CHUNKS >= cpb || sym0 >= blk_end) return;
+    const uint32_t count = (uint32_t)(blk_end - sym0 < SUB ? blk_end - sym0 : SUB);
+    const uint64_t bitpos = chunk_off[chunk] + sub_off[sub];
+    uint64_t wi = bitpos >> 5;
+    // window: top `avail` bits of win are the next stream bits
+    uint64_t win = 0; uint32_t avail = 0;
+    {
+        const uint32_t sh = (uint32_t)(bitpos & 31);
+        const uint64_t w0 = wi < total_words ? __ldg(&words[wi]) : 0; ++wi;
+        win = w0 << (32 + sh); avail = 32 - sh;
+        const uint64_t w1 = wi < total_words ? __ldg(&words[wi]) : 0; ++wi;
+        win |= w1 << (32 - avail); avail += 32;
+    }
+    uint8_t* o = out + sym0;
+    const uint32_t nl = n_long;
+    uint32_t done = 0;
+    while (done < count) {
+        uint32_t pack[4] = {0, 0, 0, 0};
+        const uint32_t batch = count - done < 16 ? count - done : 16;
+#pragma unroll
+        for (uint32_t q = 0; q < 16; ++q) {
+            if (q < batch) {
+                if (avail <= 32) {
+                    const uint64_t w = wi < total_words ? __ldg(&words[wi]) : 0; ++wi;
+                    win |= w << (32 - avail); avail += 32;
+                }
+                const uint32_t e = lut[(uint32_t)(win >> (64 - LUT_BITS))];
+                uint32_t s, L;
+                if (e & 0x8000u) { s = e & 0xFF; L = (e >> 8) & 0x7F; }
+                else {
+                    const uint32_t top = (uint32_t)(win >> 32);
+                    s = 0; L = 1;
+                    for (uint32_t j = 0; j < nl; ++j) {
+                        const uint32_t cs = long_sym[j], cl = sl[cs];
+                        if ((top >> (32 - cl)) == sc[cs]) { s = cs; L = cl; break; }
+                    }
+                }
+                win <<= L; avail -= L;
+                pack[q >> 2] |= s << (8 * (q & 3));
+            }
+        }
+        if (batch == 16 && ((reinterpret_cast<uintptr_t>(o + done) & 15) == 0)) {
+            *reinterpret_cast<uint4*>(o + done) = make_uint4(pack[0], pack[1], pack[2], pack[3]);
+        } else {
+            for (uint32_t q = 0; q < batch; ++q) o[done + q] = (uint8_t)(pack[q >> 2] >> (8 * (q & 3)));
+        }
+        done += batch;
+    }
+}
+
+// ---------------------------------------------------------------- serial decoder
+// Generic path for a stream without a side index: one thread, tree walk, the
+// reference's "consumed bytes >= buffer_size" termination (huffman.c:344-361).
+__global__ void huff_decode_serial_kernel(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t buffer_size,
+                                          const uint32_t* __restrict__ codes, const uint8_t* __restrict__ lens,
+                                          uint8_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ count) {
+    __shared__ int16_t left[512], right[512];
+    __shared__ uint8_t symv[512];
+    if (threadIdx.x != 0) return;
+    int nn = 1; left[0] = right[0] = -1; symv[0] = 0;
+    for (int s = 0; s < 256; ++s) {
+        const int L = lens[s]; if (!L) continue;
+        int cur = 0;
+        for (int bit = L - 1; bit >= 0; --bit) {
+            int16_t* nx = ((codes[s] >> bit) & 1) ? &right[cur] : &left[cur];
+            if (*nx < 0) { *nx = (int16_t)nn; left[nn] = right[nn] = -1; symv[nn] = 0; ++nn; }
+            cur = *nx;
+        }
+        symv[cur] = (uint8_t)s;
+    }
+    uint64_t consumed = 0, o = 0;
+    do {
+        int v = 0;
+        while (left[v] >= 0 && right[v] >= 0) {
+            const uint64_t w = consumed >> 5;
+            const uint32_t word = w < nwords ? words[w] : 0;
+            v = ((word >> (31 - (consumed & 31))) & 1) ? right[v] : left[v];
+            ++consumed;
+        }
+        if (o < out_cap) out[o] = symv[v];
+        ++o;
+    } while ((consumed >> 3) < buffer_size);
+    *count = o;
+}
+
+inline uint64_t align8(uint64_t x) { return (x + 7) & ~(uint64_t)7; }
+
+}  // namespace
+
+extern "C" int b200_huffman_layout(uint64_t n, uint64_t block_size, b200_huff_layout* L) {
+    if (!L) { B200_SET_ERR("b200_huffman_layout: NULL"); return B200_ERR_ARG; }
+    if (block_size && block_size < n && (block_size % CHUNK)) {
+        B200_SET_ERR("huffman block_size %llu must be a multiple of %u", (unsigned long long)block_size, CHUNK);
+        return B200_ERR_ARG;
+    }
+    const uint64_t bs = eff_block(n, block_size);
+    L->nblocks = n ? (n + bs - 1) / bs : 1;
+    L->nchunks = n ? (n + CHUNK - 1) / CHUNK : 1;
+    L->chunks_per_block = bs / CHUNK;
+    uint64_t o = 64;  // info[8] u64 lives at offset 0
+    L->off_freq = o;       o += align8(L->nblocks * 256 * 4);
+    L->off_codes = o;      o += align8(L->nblocks * 256 * 4);
+    L->off_lens = o;       o += align8(L->nblocks * 256);
+    L->off_tree = o;       o += align8(L->nblocks * 511 * 2 * 2);
+    L->off_meta = o;       o += align8(L->nblocks * 4 * 4);
+    L->off_block_bits = o; o += align8(L->nblocks * 8);
+    L->off_block_word = o; o += align8((L->nblocks + 1) * 8);
+    L->off_chunk_bits = o; o += align8(L->nchunks * 4);
+    L->off_chunk_off = o;  o += align8((L->nchunks + 1) * 8);
+    L->off_sub_off = o;    o += align8(L->nchunks * SUBS_PER_CHUNK * 4);
+    o += align8((L->nchunks + 1) * 8);  // private prefix array P behind the public part
+    L->bytes = o;
+    return B200_OK;
+}
+
+extern "C" uint64_t b200_huffman_max_words(uint64_t n, uint64_t block_size) {
+    // A Huffman code never beats a fixed 8-bit code on average, but per block the
+    // reference only guarantees <= 32 bits/symbol; size for 8 bits/symbol + rounding
+    // like init_bitwriter(size) (huffman.c:293) plus one word per block.
+    const uint64_t bs = eff_block(n, block_size);
+    const uint64_t nblocks = n ? (n + bs - 1) / bs : 1;
+    return n / 4 + nblocks + 4;
+}
+
+static int huff_tables(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size, uint8_t* d_side,
+                       uint64_t side_bytes, b200_huff_layout* L, uint64_t* bs_out) {
+    if (n == 0) { B200_SET_ERR("huffman: empty input (the reference exits: queue is empty, huffman.c:149-152)"); return B200_ERR_DOMAIN; }
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_side) & 7)) {
+        B200_SET_ERR("huffman: d_in must be 16-byte and d_side 8-byte aligned"); return B200_ERR_ARG;
+    }
+    B200_TRY(b200_huffman_layout(n, block_size, L));
+    if (side_bytes < L->bytes) { B200_SET_ERR("huffman: side buffer %llu < %llu", (unsigned long long)side_bytes, (unsigned long long)L->bytes); return B200_ERR_CAPACITY; }
+    const uint64_t bs = eff_block(n, block_size);
+    *bs_out = bs;
+    // zero info + freq + codes + lens (contiguous at the front of the side buffer)
+    CUDA_TRY(cudaMemsetAsync(d_side, 0, L->off_tree, ctx->stream));
+    const uint32_t tpb = (uint32_t)((L->chunks_per_block + TILE_CHUNKS - 1) / TILE_CHUNKS);
+    const uint64_t grid = L->nblocks * tpb;
+    huff_hist_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(d_in, n, bs, tpb, reinterpret_cast<uint32_t*>(d_side + L->off_freq));
+    huff_build_kernel<<<(unsigned)L->nblocks, 32, 0, ctx->stream>>>(
+        reinterpret_cast<const uint32_t*>(d_side + L->off_freq), reinterpret_cast<uint32_t*>(d_side + L->off_codes),
+        d_side + L->off_lens, reinterpret_cast<int16_t*>(d_side + L->off_tree), reinterpret_cast<uint32_t*>(d_side + L->off_meta));
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_huffman_tables_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                                       uint8_t* d_side, uint64_t side_bytes) {
+    b200_huff_layout L; uint64_t bs;
+    return huff_tables(ctx, d_in, n, block_size, d_side, side_bytes, &L, &bs);
+}
+
+extern "C" int b200_huffman_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                                       uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
+                                       uint64_t* h_total_words, uint32_t* h_worst_status) {
+    b200_huff_layout L; uint64_t bs;
+    B200_TRY(huff_tables(ctx, d_in, n, block_size, d_side, side_bytes, &L, &bs));
+    const uint32_t cpb = (uint32_t)L.chunks_per_block;
+    uint64_t* info = reinterpret_cast<uint64_t*>(d_side);
+    uint64_t* P = reinterpret_cast<uint64_t*>(d_side + L.off_sub_off + align8(L.nchunks * SUBS_PER_CHUNK * 4));
+    huff_chunkbits_kernel<<<(unsigned)L.nchunks, 256, 0, ctx->stream>>>(d_in, n, cpb, d_side + L.off_lens,
+                                                                         reinterpret_cast<uint32_t*>(d_side + L.off_chunk_bits));
+    huff_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_side + L.off_chunk_bits), L.nchunks, cpb,
+                                                     L.nblocks, P, reinterpret_cast<uint64_t*>(d_side + L.off_block_bits),
+                                                     reinterpret_cast<uint64_t*>(d_side + L.off_block_word),
+                                                     reinterpret_cast<uint64_t*>(d_side + L.off_chunk_off), d_words, words_capacity, info);
+    huff_encode_kernel<<<(unsigned)L.nchunks, 256, 0, ctx->stream>>>(
+        d_in, n, cpb, reinterpret_cast<const uint32_t*>(d_side + L.off_codes), d_side + L.off_lens,
+        reinterpret_cast<const uint32_t*>(d_side + L.off_meta), reinterpret_cast<const uint32_t*>(d_side + L.off_chunk_bits),
+        reinterpret_cast<const uint64_t*>(d_side + L.off_chunk_off), reinterpret_cast<uint32_t*>(d_side + L.off_sub_off), d_words, info);
+    ctx->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    if (h_total_words || h_worst_status) {
+        uint64_t* pin; B200_TRY(b200_pinned(ctx, 16 + L.nblocks * 16, reinterpret_cast<void**>(&pin)));
+        CUDA_TRY(cudaMemcpyAsync(pin, info, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(pin + 2, d_side + L.off_meta, L.nblocks * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (h_total_words) *h_total_words = pin[0];
+        uint32_t worst = 0;
+        const uint32_t* m = reinterpret_cast<const uint32_t*>(pin + 2);
+        for (uint64_t b = 0; b < L.nblocks; ++b) if (m[4 * b] > worst) worst = m[4 * b];
+        if (h_worst_status) *h_worst_status = worst;
+        if (pin[1]) { B200_SET_ERR("huffman: stream needs %llu words, capacity %llu", (unsigned long long)pin[0], (unsigned long long)words_capacity); return B200_ERR_CAPACITY; }
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_huffman_decode_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words, const uint8_t* d_side,
+                                       uint64_t side_bytes, uint64_t n, uint64_t block_size, uint8_t* d_out) {
+    if (n == 0) return B200_OK;
+    b200_huff_layout L;
+    B200_TRY(b200_huffman_layout(n, block_size, &L));
+    if (side_bytes < L.bytes) { B200_SET_ERR("huffman decode: side buffer too small"); return B200_ERR_CAPACITY; }
+    const uint64_t bs = eff_block(n, block_size);
+    const uint32_t cpb = (uint32_t)L.chunks_per_block;
+    const uint32_t tpb = (cpb + TILE_CHUNKS - 1) / TILE_CHUNKS;
+    huff_decode_kernel<<<(unsigned)(L.nblocks * tpb), 256, 0, ctx->stream>>>(
+        d_words, total_words, n, bs, cpb, tpb, reinterpret_cast<const uint32_t*>(d_side + L.off_codes), d_side + L.off_lens,
+        reinterpret_cast<const uint64_t*>(d_side + L.off_chunk_off), reinterpret_cast<const uint32_t*>(d_side + L.off_sub_off), d_out);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_huffman_decode_serial_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t nwords, uint64_t buffer_size,
+                                              const uint32_t* d_codes, const uint8_t* d_lens, uint8_t* d_out,
+                                              uint64_t out_capacity, uint64_t* h_count) {
+    uint64_t* d_cnt;
+    B200_TRY(b200_scratch(ctx, 0, 64, reinterpret_cast<void**>(&d_cnt)));
+    huff_decode_serial_kernel<<<1, 32, 0, ctx->stream>>>(d_words, nwords, buffer_size, d_codes, d_lens, d_out, out_capacity, d_cnt);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    uint64_t* pin; B200_TRY(b200_pinned(ctx, 64, reinterpret_cast<void**>(&pin)));
+    CUDA_TRY(cudaMemcpyAsync(pin, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_count) *h_count = pin[0];
+    return B200_OK;
+}

@@ -1,0 +1,408 @@
+// LZ77 match finder + greedy parse + token emission + decoders for sm_100a.
+//
+// Reference being replaced (bit-exact on the same block segmentation):
+//   algorithms/lz77/lz77.c      hash :13-41, insert :55-86, find :94-108,
+//                               greedy parse :264-345, decoder :347-377
+//   algorithms/deflate/lz77.c   insert :77-145, find :147-174, byte tokens :176-197,
+//                               greedy parse :199-280
+//
+// The reference's 2^20-slot open-addressed table is emulated slot-exactly with the
+// "lazy expiry" rule: an entry placed for position i is
+// live at time P iff i >= P - W, plus the slot-0 exception caused by the reference's
+// early is_full flip. No eviction stores, no clearing between blocks (epoch tags).
+//
+// v1 layout: one warp owns one 2^20(+guard)-slot table of 8-byte slots
+// {pattern, epoch<<22 | index} in HBM and walks its blocks sequentially; the 32
+// lanes read 32 consecutive slots of a probe chain per step (256 B, coalesced) and
+// pick the first non-live / first matching slot with ballot + ffs.
+#include "common.cuh"
+#include "../../include/b200comp.h"
+#include <stdlib.h>
+
+namespace {
+
+constexpr uint32_t TABLE_SLOTS = 1u << 20;
+constexpr uint32_t GUARD = 65536u + 64u;
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t IDX_BITS = 22;               // blocks up to 4 MiB
+constexpr uint32_t IDX_MASK = (1u << IDX_BITS) - 1;
+constexpr uint32_t MAX_EPOCH = (1u << (32 - IDX_BITS)) - 1;
+constexpr uint32_t CLRQ = 1024;                 // pending slot-0 clear times per warp
+constexpr uint64_t MAX_BLOCK = 1ull << IDX_BITS;
+
+template <int V> struct Cfg;
+template <> struct Cfg<0> { static constexpr uint32_t W = 1u << 14, MAXLEN = 15; };
+template <> struct Cfg<1> { static constexpr uint32_t W = 1u << 15, MAXLEN = 31; };
+
+__device__ __forceinline__ uint32_t byte_at(const uint8_t* __restrict__ d, uint32_t len, uint32_t p) {
+    return p < len ? (uint32_t)__ldg(d + p) : 0u;  // bytes past the block read as 0 (U1)
+}
+__device__ __forceinline__ uint32_t word_at(const uint8_t* __restrict__ d, uint32_t len, uint32_t p) {
+    return byte_at(d, len, p) | (byte_at(d, len, p + 1) << 8) | (byte_at(d, len, p + 2) << 16) | (byte_at(d, len, p + 3) << 24);
+}
+
+// ------------------------------------------------------------------ parse (v1)
+template <int V>
+__global__ void __launch_bounds__(128) lz77_parse_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t bs, uint64_t nblocks,
+                                                        uint2* __restrict__ tables, uint32_t* __restrict__ clrq, uint32_t epoch0,
+                                                        uint8_t* __restrict__ scratch, uint64_t stride,
+                                                        uint64_t* __restrict__ block_sizes, uint64_t* __restrict__ block_bytes,
+                                                        uint32_t* __restrict__ err) {
+    constexpr uint32_t W = Cfg<V>::W, MAXLEN = Cfg<V>::MAXLEN;
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint2* T = tables + gw * (uint64_t)(TABLE_SLOTS + GUARD);
+    uint32_t* Q = clrq + gw * CLRQ;
+    uint32_t epoch = epoch0;
+
+    for (uint64_t b = gw; b < nblocks; b += nwarps) {
+        ++epoch;
+        const uint8_t* d = in + b * bs;
+        const uint32_t len = (uint32_t)(n - b * bs < bs ? n - b * bs : bs);
+        uint8_t* out = scratch + b * stride;
+        // FIFO of times at which slot 0 must be cleared (after that insert). The
+        // reference reads the never-written ring cell at insert W-1 (lz77.c:70-76).
+        uint32_t qh = 0, qt = 1, next_clear = W - 1;
+        if (lane == 0) Q[0] = W - 1;
+        uint32_t p = 0, pf = 0;
+        uint64_t acc = 0; uint32_t accbits = 0; uint32_t opos = 0;  // V==0: word index; V==1: byte index
+
+        while (p < len) {
+            // warm L2 with the home slot of the next positions (each position once)
+            if (p + 32 > pf) {
+                const uint32_t q = pf + lane;
+                if (q < len) {
+                    const uint2* a = &T[lz_hash(word_at(d, len, q))];
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                }
+                pf += 32;
+            }
+            const uint32_t pat = word_at(d, len, p);
+            const uint32_t h = lz_hash(pat);
+            // ---- find(pat): first slot from h that is non-live or holds pat (no wrap)
+            uint32_t m = NONE, s = h, stop_slot = 0;
+            bool stop_dead = false;
+            for (;;) {
+                const uint2 e = __ldcg(&T[s + lane]);
+                const bool live = (e.y >> IDX_BITS) == epoch && (e.y & IDX_MASK) + W >= p;
+                const bool stop = !live || e.x == pat;
+                const unsigned mask = __ballot_sync(0xffffffffu, stop);
+                if (mask) {
+                    const int k = __ffs(mask) - 1;
+                    const uint32_t idx = __shfl_sync(0xffffffffu, e.y & IDX_MASK, k);
+                    const bool lv = __shfl_sync(0xffffffffu, (int)live, k) != 0;
+                    m = lv ? idx : NONE;
+                    stop_slot = s + k; stop_dead = !lv;
+                    break;
+                }
+                s += 32;
+            }
+            const bool reject = (m == NONE) || (V ? (p - m >= W - 1) : (p - m == W));
+            uint32_t mlen = 1;
+            if (!reject) {
+                bool neq = true;
+                if (lane < MAXLEN - 4) neq = byte_at(d, len, m + 4 + lane) != byte_at(d, len, p + 4 + lane);
+                const unsigned mask = __ballot_sync(0xffffffffu, neq);
+                mlen = 4 + (uint32_t)(__ffs(mask) - 1);
+            }
+            // ---- emit token
+            if (lane == 0) {
+                if (V == 0) {
+                    if (reject) { acc |= (uint64_t)(byte_at(d, len, p) << 1) << accbits; accbits += 9; }
+                    else { acc |= (uint64_t)(1u | ((p - m) << 1) | (mlen << 15)) << accbits; accbits += 19; }
+                    if (accbits >= 32) {
+                        reinterpret_cast<uint32_t*>(out)[opos++] = (uint32_t)acc;
+                        acc >>= 32; accbits -= 32;
+                    }
+                } else {
+                    if (reject) { *reinterpret_cast<uint16_t*>(out + opos) = (uint16_t)(byte_at(d, len, p) << 8); opos += 2; }
+                    else {
+                        const uint32_t off = p - m;
+                        *reinterpret_cast<uint16_t*>(out + opos) = (uint16_t)(1u | ((off & 0xFF) << 8));
+                        *reinterpret_cast<uint16_t*>(out + opos + 2) = (uint16_t)((off >> 8) | (mlen << 8));
+                        opos += 4;
+                    }
+                }
+            }
+            // ---- insert every covered position, in order
+            for (uint32_t q = p; q < p + mlen; ++q) {
+                const uint32_t pq = (q == p) ? pat : word_at(d, len, q);
+                uint32_t slot = 0, t;
+                bool have = false;
+                if (q == p && (V == 0 || stop_slot < TABLE_SLOTS)) {
+                    // the find walk already proved every slot before stop_slot live
+                    if (stop_dead) { slot = stop_slot; have = true; }
+                    t = stop_slot;
+                } else {
+                    t = lz_hash(pq);
+                }
+                while (!have) {
+                    const uint32_t at = V ? ((t + lane) & (TABLE_SLOTS - 1)) : (t + lane);  // deflate insert wraps (deflate/lz77.c:99-101)
+                    const uint2 e = __ldcg(&T[at]);
+                    const bool live = (e.y >> IDX_BITS) == epoch && (e.y & IDX_MASK) + W >= q;
+                    const unsigned mask = __ballot_sync(0xffffffffu, !live);
+                    if (mask) {
+                        const uint32_t k = (uint32_t)(__ffs(mask) - 1);
+                        slot = V ? ((t + k) & (TABLE_SLOTS - 1)) : (t + k);
+                        have = true;
+                    }
+                    t += 32;
+                }
+                if (lane == 0) __stcg(&T[slot], make_uint2(pq, (epoch << IDX_BITS) | q));
+                if (slot == 0) {
+                    if (qt - qh < CLRQ) { if (lane == 0) Q[qt % CLRQ] = q + W; }
+                    else if (lane == 0) atomicOr(err, 2u);
+                    if (qt == qh) next_clear = q + W;
+                    ++qt;
+                }
+                if (q == next_clear) {
+                    if (lane == 0) __stcg(&T[0], make_uint2(0u, 0u));  // kills even an entry placed just now
+                    ++qh;
+                    __syncwarp();
+                    next_clear = (qh != qt) ? __ldcg(&Q[qh % CLRQ]) : NONE;
+                }
+                __syncwarp();
+            }
+            p += mlen;
+        }
+        if (lane == 0) {
+            if (V == 0) {
+                const uint64_t bits = (uint64_t)opos * 32 + accbits;
+                reinterpret_cast<uint32_t*>(out)[opos] = (uint32_t)acc;        // tail bits, zero padded
+                reinterpret_cast<uint32_t*>(out)[opos + 1] = 0;                // covers the bit_index/8+1 byte (lz77.c:341)
+                block_sizes[b] = bits;
+                block_bytes[b] = bits / 8 + 1;
+            } else {
+                block_sizes[b] = opos;
+                block_bytes[b] = opos;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ offsets (single CTA)
+__global__ void __launch_bounds__(1024) lz77_offsets_kernel(const uint64_t* __restrict__ block_bytes, uint64_t nblocks,
+                                                            uint64_t* __restrict__ block_off, uint64_t capacity,
+                                                            uint64_t* __restrict__ info) {
+    __shared__ uint64_t warp_tot[33];
+    uint64_t carry = 0, tot;
+    for (uint64_t base = 0; base < nblocks; base += 1024) {
+        const uint64_t b = base + threadIdx.x;
+        const uint64_t v = b < nblocks ? block_bytes[b] : 0;
+        const uint64_t ex = cta_scan_step(v, warp_tot, &tot);
+        if (b < nblocks) block_off[b] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) { block_off[nblocks] = carry; info[0] = carry; info[1] = carry > capacity ? 1 : 0; }
+}
+
+// ------------------------------------------------------------------ compaction
+// Copies each block's tokens from its fixed-stride scratch slot to its final,
+// arbitrarily aligned offset. One CTA per (block, 32 KiB piece). 16-byte aligned
+// destination stores assembled from aligned source words with funnel shifts.
+__global__ void __launch_bounds__(256) lz77_gather_kernel(const uint8_t* __restrict__ scratch, uint64_t stride,
+                                                          const uint64_t* __restrict__ block_bytes, const uint64_t* __restrict__ block_off,
+                                                          uint32_t pieces, uint8_t* __restrict__ out, const uint64_t* __restrict__ info) {
+    if (info[1]) return;
+    const uint64_t b = blockIdx.x / pieces, piece = blockIdx.x % pieces;
+    const uint64_t nb = block_bytes[b];
+    const uint64_t PIECE = 32768;
+    const uint64_t lo = piece * PIECE;
+    if (lo >= nb) return;
+    const uint64_t hi = lo + PIECE < nb ? lo + PIECE : nb;
+    const uint8_t* src = scratch + b * stride + lo;   // 16-byte aligned (stride and PIECE are)
+    uint8_t* dst = out + block_off[b] + lo;
+    const uint64_t cnt = hi - lo;
+    // head: bytes until dst is 16-byte aligned
+    uint64_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    if (head > cnt) head = cnt;
+    if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+    const uint64_t body = (cnt - head) / 16;
+    const uint32_t sh = (uint32_t)(head & 3) * 8;           // src misalignment of the body in bits
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + (head & ~(uint64_t)3));
+    uint4* d128 = reinterpret_cast<uint4*>(dst + head);
+    for (uint64_t i = threadIdx.x; i < body; i += 256) {
+        const uint32_t* a = s32 + i * 4;
+        const uint32_t w0 = a[0], w1 = a[1], w2 = a[2], w3 = a[3];
+        const uint32_t w4 = sh ? a[4] : 0;
+        uint4 v;
+        v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+        v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+        d128[i] = v;
+    }
+    const uint64_t done = head + body * 16;
+    if (threadIdx.x < cnt - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
+}
+
+// ------------------------------------------------------------------ decoders (v1)
+// One warp per block. The last 64 KiB of output live in a shared-memory ring
+// (offsets are < 32768), flushed to HBM in 16 KiB coalesced pieces. All lanes
+// parse the token stream redundantly; copies are done one byte per lane, with
+// overlapping matches (offset < length) resolved by the period rule
+// out[o+k] = out[o - off + k % off].
+constexpr uint32_t RING = 65536, FLUSH = 16384;
+
+__device__ __forceinline__ void ring_flush(const uint8_t* ring, uint8_t* gout, uint32_t from, uint32_t to, unsigned lane) {
+    // [from, to) with from % FLUSH == 0; to may be ragged at the end of the block
+    const uint32_t full = (to - from) / 16;
+    for (uint32_t i = lane; i < full; i += 32) {
+        const uint4 v = *reinterpret_cast<const uint4*>(ring + ((from + i * 16) & (RING - 1)));
+        uint8_t* g = gout + from + i * 16;
+        if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) *reinterpret_cast<uint4*>(g) = v;
+        else { const uint8_t* pv = reinterpret_cast<const uint8_t*>(&v); for (int k = 0; k < 16; ++k) g[k] = pv[k]; }
+    }
+    for (uint32_t i = from + full * 16 + lane; i < to; i += 32) gout[i] = ring[i & (RING - 1)];
+}
+
+template <int V>
+__global__ void __launch_bounds__(32) lz77_decode_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ block_off,
+                                                        const uint64_t* __restrict__ block_sizes, uint64_t n, uint64_t bs,
+                                                        uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t ring[];
+    const unsigned lane = threadIdx.x;
+    const uint64_t b = blockIdx.x;
+    const uint32_t len = (uint32_t)(n - b * bs < bs ? n - b * bs : bs);
+    const uint8_t* tk = stream + block_off[b];
+    uint8_t* gout = out + b * bs;
+    uint32_t o = 0, flushed = 0;
+    if (V == 0) {
+        // LSB-first bit tokens: 0 + 8-bit literal | 1 + 14-bit offset + 4-bit length (lz77.c:358-372)
+        uint64_t win = 0; uint32_t avail = 0; uint64_t rp = 0;
+        const uint64_t nbytes = block_sizes[b] / 8 + 1;
+        while (o < len) {
+            while (avail <= 56) { const uint64_t by = rp < nbytes ? (uint64_t)__ldg(tk + rp) : 0; ++rp; win |= by << avail; avail += 8; }
+            if (win & 1) {
+                const uint32_t off = (uint32_t)(win >> 1) & 0x3FFF, ml = (uint32_t)(win >> 15) & 0xF;
+                win >>= 19; avail -= 19;
+                if (lane < ml) {
+                    const uint32_t src = off ? o - off + (lane % off) : o;
+                    ring[(o + lane) & (RING - 1)] = ring[src & (RING - 1)];
+                }
+                o += ml;
+                if (ml == 0 && off == 0) break;  // corrupt stream guard: no progress
+            } else {
+                if (lane == 0) ring[o & (RING - 1)] = (uint8_t)(win >> 1);
+                win >>= 9; avail -= 9;
+                ++o;
+            }
+            __syncwarp();
+            while (o >= flushed + FLUSH + 64) { ring_flush(ring, gout, flushed, flushed + FLUSH, lane); flushed += FLUSH; }
+        }
+    } else {
+        // byte tokens: 00 cc | 01 dist_lo dist_hi len (deflate/lz77.c:176-197)
+        const uint64_t ntok = block_sizes[b];
+        uint64_t i = 0;
+        while (i < ntok) {
+            const uint32_t flag = __ldg(tk + i);
+            if (flag == 0) {
+                // batch a run of literals: lane k looks at the token 2k bytes ahead
+                const uint64_t at = i + 2 * (uint64_t)lane;
+                const bool lit = at < ntok && __ldg(tk + at) == 0;
+                const unsigned mask = __ballot_sync(0xffffffffu, !lit);
+                const uint32_t run = mask ? (uint32_t)(__ffs(mask) - 1) : 32u;
+                if (lane < run) ring[(o + lane) & (RING - 1)] = __ldg(tk + at + 1);
+                o += run; i += 2 * (uint64_t)run;
+            } else {
+                const uint32_t off = (uint32_t)__ldg(tk + i + 1) | ((uint32_t)__ldg(tk + i + 2) << 8);
+                const uint32_t ml = __ldg(tk + i + 3);
+                if (lane < ml) {
+                    const uint32_t src = off ? o - off + (lane % off) : o;
+                    ring[(o + lane) & (RING - 1)] = ring[src & (RING - 1)];
+                }
+                o += ml; i += 4;
+            }
+            __syncwarp();
+            while (o >= flushed + FLUSH + 64) { ring_flush(ring, gout, flushed, flushed + FLUSH, lane); flushed += FLUSH; }
+        }
+    }
+    __syncwarp();
+    const uint32_t end = o < len ? o : len;   // a final match may overshoot the block (U1)
+    if (end > flushed) ring_flush(ring, gout, flushed, end, lane);
+}
+
+inline uint64_t round16(uint64_t x) { return (x + 15) & ~(uint64_t)15; }
+
+}  // namespace
+
+extern "C" uint64_t b200_lz77_block_stride(uint64_t block_size) { return round16(2 * block_size + 16); }
+
+// scratch slots used: 1 tables, 2 clear queues, 3 token scratch, 4 block_bytes/info/err
+extern "C" int b200_lz77_encode_dev(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                                    uint8_t* d_out, uint64_t out_capacity, uint64_t* d_block_sizes, uint64_t* d_block_off,
+                                    uint64_t* h_total_bytes) {
+    if (variant != 0 && variant != 1) { B200_SET_ERR("lz77: variant must be 0 or 1"); return B200_ERR_ARG; }
+    if (n == 0) {
+        CUDA_TRY(cudaMemsetAsync(d_block_off, 0, 2 * sizeof(uint64_t), ctx->stream));
+        if (h_total_bytes) *h_total_bytes = 0;
+        return B200_OK;
+    }
+    const uint64_t bs = (block_size == 0 || block_size > n) ? n : block_size;
+    if (bs > MAX_BLOCK) { B200_SET_ERR("lz77: block of %llu bytes exceeds the %llu-byte limit of this build", (unsigned long long)bs, (unsigned long long)MAX_BLOCK); return B200_ERR_ARG; }
+    const uint64_t nblocks = (n + bs - 1) / bs;
+    const uint64_t stride = b200_lz77_block_stride(bs);
+
+    int wps = 32;
+    if (const char* e = getenv("B200_LZ_WARPS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 64) wps = v; }
+    uint64_t nwarps = (uint64_t)ctx->sm_count * wps;
+    if (nwarps > nblocks) nwarps = nblocks;
+    nwarps = (nwarps + 3) / 4 * 4;  // 4 warps per CTA
+    const uint64_t per_warp = (nblocks + nwarps - 1) / nwarps;
+
+    const size_t table_bytes = (size_t)nwarps * (TABLE_SLOTS + GUARD) * sizeof(uint2);
+    uint2* tables; uint32_t* clrq; uint8_t* scratch; uint64_t* misc;
+    const bool fresh = ctx->cap[1] < table_bytes;
+    B200_TRY(b200_scratch(ctx, 1, table_bytes, reinterpret_cast<void**>(&tables)));
+    B200_TRY(b200_scratch(ctx, 2, (size_t)nwarps * CLRQ * 4, reinterpret_cast<void**>(&clrq)));
+    B200_TRY(b200_scratch(ctx, 3, (size_t)(nblocks * stride + 64), reinterpret_cast<void**>(&scratch)));
+    B200_TRY(b200_scratch(ctx, 4, (size_t)(nblocks * 8 + 64), reinterpret_cast<void**>(&misc)));
+    uint32_t& ep = ctx->lz_epoch;
+    if (fresh || ep + per_warp > MAX_EPOCH) {
+        CUDA_TRY(cudaMemsetAsync(tables, 0, ctx->cap[1], ctx->stream));
+        ep = 0;
+    }
+    uint64_t* info = misc;                       // [0] total, [1] overflow
+    uint32_t* err = reinterpret_cast<uint32_t*>(misc + 2);
+    uint64_t* block_bytes = misc + 4;
+    CUDA_TRY(cudaMemsetAsync(misc, 0, 32, ctx->stream));
+    const unsigned grid = (unsigned)(nwarps / 4);
+    if (variant == 0)
+        lz77_parse_kernel<0><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
+    else
+        lz77_parse_kernel<1><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
+    ep += (uint32_t)per_warp;
+    lz77_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(block_bytes, nblocks, d_block_off, out_capacity, info);
+    const uint32_t pieces = (uint32_t)((stride + 32767) / 32768);
+    lz77_gather_kernel<<<(unsigned)(nblocks * pieces), 256, 0, ctx->stream>>>(scratch, stride, block_bytes, d_block_off, pieces, d_out, info);
+    ctx->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    if (h_total_bytes) {
+        uint64_t* pin; B200_TRY(b200_pinned(ctx, 64, reinterpret_cast<void**>(&pin)));
+        CUDA_TRY(cudaMemcpyAsync(pin, misc, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        *h_total_bytes = pin[0];
+        if (pin[1]) { B200_SET_ERR("lz77: stream needs %llu bytes, capacity %llu", (unsigned long long)pin[0], (unsigned long long)out_capacity); return B200_ERR_CAPACITY; }
+        if (reinterpret_cast<uint32_t*>(pin + 2)[0]) { B200_SET_ERR("lz77: slot-0 clear queue overflow"); return B200_ERR_DOMAIN; }
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d_stream, const uint64_t* d_block_off,
+                                    const uint64_t* d_block_sizes, uint64_t n, uint64_t block_size, uint8_t* d_out) {
+    if (variant != 0 && variant != 1) { B200_SET_ERR("lz77: variant must be 0 or 1"); return B200_ERR_ARG; }
+    if (n == 0) return B200_OK;
+    const uint64_t bs = (block_size == 0 || block_size > n) ? n : block_size;
+    const uint64_t nblocks = (n + bs - 1) / bs;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[variant]) {
+        if (variant == 0) CUDA_TRY(cudaFuncSetAttribute(lz77_decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RING));
+        else CUDA_TRY(cudaFuncSetAttribute(lz77_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RING));
+        attr_done[variant] = true;
+    }
+    if (variant == 0) lz77_decode_kernel<0><<<(unsigned)nblocks, 32, RING, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, d_out);
+    else lz77_decode_kernel<1><<<(unsigned)nblocks, 32, RING, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, d_out);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}

@@ -1,0 +1,158 @@
+/*
+ * libb200comp.so -- C-ABI of the B200 (sm_100a) block-parallel codecs.
+ *
+ * This is the boundary the reference's four directories bind to. The reference
+ * has no FFI/plugin registry: its "interface" is the set of global C functions
+ * each driver links. Those exact prototypes are provided by the
+ * thin per-directory shims (include/b200_lz77.h, b200_huffman.h, b200_deflate.h,
+ * b200_fse.h -> libb200_{lz77,huffman,deflate,fse}.so, one per directory because
+ * the reference's symbols collide). The shims are host wrappers around the
+ * device-resident entry points declared here:  H2D -> *_dev -> D2H.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `d_` = device pointer, `h_` = host pointer;
+ *   - every call returns 0 on success, else a B200_ERR_* code; the text is in
+ *     b200_last_error();
+ *   - all kernels of a context run on that context's CUDA stream; `*_dev` calls
+ *     are asynchronous unless they have an `h_` result parameter, in which case
+ *     they synchronise the stream before returning;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef B200COMP_H
+#define B200COMP_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_CUDA 1
+#define B200_ERR_ARG 2
+#define B200_ERR_CAPACITY 3
+#define B200_ERR_DOMAIN 4
+#define B200_ERR_FORMAT 5
+
+typedef struct b200_ctx b200_ctx;
+
+/* ---- context / memory ------------------------------------------------------ */
+int         b200_device_count(void);
+/* cuda_stream: a cudaStream_t to launch on (cudaStreamLegacy / cudaStreamPerThread are
+ * accepted), or NULL to create a private non-blocking stream. */
+int         b200_ctx_create(b200_ctx** out, int device, void* cuda_stream);
+void        b200_ctx_destroy(b200_ctx* ctx);
+int         b200_ctx_sync(b200_ctx* ctx);
+uint64_t    b200_ctx_launches(b200_ctx* ctx); /* kernels launched so far */
+const char* b200_last_error(void);
+int         b200_dev_alloc(void** d_ptr, uint64_t bytes);
+int         b200_dev_free(void* d_ptr);
+int         b200_host_alloc(void** h_ptr, uint64_t bytes); /* pinned */
+int         b200_host_free(void* h_ptr);
+int         b200_copy_h2d(b200_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes); /* async */
+int         b200_copy_d2h(b200_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes); /* async */
+int         b200_memset(b200_ctx* ctx, void* d_dst, int value, uint64_t bytes);           /* async */
+
+/* ---- Huffman (replaces algorithms/huffman/huffman.c:179-364) --------------- */
+#define B200_HUFF_CHUNK 4096u /* symbols per encode chunk (one CTA)              */
+#define B200_HUFF_SUB   256u  /* symbols per decode sub-chunk (one thread)       */
+
+/* Layout of the caller-allocated device "side" buffer: code tables plus the index
+ * that makes the stream parallel-decodable. It is NOT part of the compressed words
+ * the reference compares. All offsets are in bytes. */
+typedef struct {
+    uint64_t bytes;          /* total size to allocate                                   */
+    uint64_t nblocks;        /* table scopes: ceil(n / block_size)                       */
+    uint64_t nchunks;        /* ceil over blocks of len/4096                             */
+    uint64_t chunks_per_block;
+    uint64_t off_freq;       /* u32[nblocks][256]  histogram (huffman.c:184-187)         */
+    uint64_t off_codes;      /* u32[nblocks][256]  codes, right-aligned (huffman.c:225)  */
+    uint64_t off_lens;       /* u8 [nblocks][256]  code lengths (huffman.c:226)          */
+    uint64_t off_tree;       /* i16[nblocks][511][2] children; leaf = {-1, symbol}       */
+    uint64_t off_meta;       /* u32[nblocks][4] = {status, distinct, root, max_len}      */
+    uint64_t off_block_bits; /* u64[nblocks]   bits of each block's stream               */
+    uint64_t off_block_word; /* u64[nblocks+1] first u32 word of each block; [nblocks]=total */
+    uint64_t off_chunk_bits; /* u32[nchunks]   bits of each chunk                        */
+    uint64_t off_chunk_off;  /* u64[nchunks+1] scratch prefix, then absolute bit offset  */
+    uint64_t off_sub_off;    /* u32[nchunks*16] bit offset of each sub-chunk in its chunk*/
+} b200_huff_layout;
+
+/* block_size = table scope in bytes; 0 means one table for the whole buffer
+ * (what huffman_compress does). Otherwise it must be a multiple of 4096. */
+int b200_huffman_layout(uint64_t n, uint64_t block_size, b200_huff_layout* out);
+/* upper bound of the stream size in u32 words for (n, block_size) */
+uint64_t b200_huffman_max_words(uint64_t n, uint64_t block_size);
+
+/* histogram -> tables -> MSB-first u32 word stream (bit-exact with
+ * build_huffman_tree + gather_codes + _huffman_compress per block). meta.status
+ * != 0 marks a block the reference would not encode (1: fewer than 2 distinct
+ * symbols, exit(1) at huffman.c:278-281; 2: a code longer than 32 bits, which the
+ * reference silently corrupts). h_total_words may be NULL (then no sync). */
+int b200_huffman_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                            uint32_t* d_words, uint64_t words_capacity,
+                            uint8_t* d_side, uint64_t side_bytes,
+                            uint64_t* h_total_words, uint32_t* h_worst_status);
+/* only the histogram + table build (build_huffman_tree + gather_codes) */
+int b200_huffman_tables_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                            uint8_t* d_side, uint64_t side_bytes);
+/* table-lookup decoder driven by the side index written by the encoder */
+int b200_huffman_decode_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words,
+                            const uint8_t* d_side, uint64_t side_bytes,
+                            uint64_t n, uint64_t block_size, uint8_t* d_out);
+/* Index-free decoder for one foreign stream (e.g. produced by the reference):
+ * one GPU thread walks the stream with the reference's termination rule
+ * (huffman.c:344-361) and reports the symbol count the reference would report.
+ * d_codes/d_lens: 256 entries each. */
+int b200_huffman_decode_serial_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t nwords,
+                                   uint64_t buffer_size, const uint32_t* d_codes, const uint8_t* d_lens,
+                                   uint8_t* d_out, uint64_t out_capacity, uint64_t* h_count);
+
+/* ---- LZ77 (replaces algorithms/lz77/lz77.c:55-108,264-377 and
+ *            algorithms/deflate/lz77.c:77-280) -------------------------------- */
+#define B200_LZ_STANDALONE 0 /* W=2^14, MAX_LEN 15, LSB-first 9/19-bit tokens   */
+#define B200_LZ_DEFLATE    1 /* W=2^15, MAX_LEN 31, 2/4-byte tokens             */
+
+/* worst-case bytes of one block's token stream (the reference allocates 2*size) */
+uint64_t b200_lz77_block_stride(uint64_t block_size);
+/* Greedy parse of every block with a fresh table (the parity contract of SURVEY.md
+ * §8a), tokens compacted back to back into d_out:
+ *   variant 0: block b occupies bits/8+1 bytes (lz77.c:341), d_block_sizes[b] = bit_index
+ *   variant 1: block b occupies d_block_sizes[b] bytes (deflate/lz77.c:277)
+ * d_block_off[nblocks+1] = byte offset of each block in d_out (exclusive scan;
+ * last entry = total). This is deflate.c:47-63's raw concatenation plus the index
+ * the reference lacks. block_size 0 = whole buffer as one block. */
+int b200_lz77_encode_dev(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                         uint8_t* d_out, uint64_t out_capacity,
+                         uint64_t* d_block_sizes, uint64_t* d_block_off, uint64_t* h_total_bytes);
+int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d_stream,
+                         const uint64_t* d_block_off, const uint64_t* d_block_sizes,
+                         uint64_t n, uint64_t block_size, uint8_t* d_out);
+
+/* ---- FSE (C mirror of algorithms/fse/src/main.zig:50-189) ------------------- */
+#define B200_FSE_TABLE_LOG 8u
+typedef struct {
+    uint64_t bytes;
+    uint64_t nblocks;       /* table scopes                                             */
+    uint64_t nsegs;         /* independent single-state streams                         */
+    uint64_t segs_per_block;
+    uint64_t off_freq;      /* u32[nblocks][256] histogram (main.zig:88-96)             */
+    uint64_t off_norm;      /* u16[nblocks][256] normalised counts (main.zig:106-149)   */
+    uint64_t off_tt;        /* u32[nblocks][256] TT_Entry {symbol,next_state,num_bits}  */
+    uint64_t off_seg_bits;  /* u32[nsegs] exact bits of each segment stream             */
+    uint64_t off_seg_word;  /* u64[nsegs+1] first u64 word of each segment; last=total  */
+} b200_fse_layout;
+int b200_fse_layout_for(uint64_t n, uint64_t block_size, uint64_t seg_size, b200_fse_layout* out);
+uint64_t b200_fse_max_words(uint64_t n, uint64_t seg_size);
+int b200_fse_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size, uint64_t seg_size,
+                        uint64_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
+                        uint64_t* h_total_words);
+int b200_fse_decode_dev(b200_ctx* ctx, const uint64_t* d_words, const uint8_t* d_side, uint64_t side_bytes,
+                        uint64_t n, uint64_t block_size, uint64_t seg_size, uint8_t* d_out, uint32_t* h_bad_segments);
+/* histogram + normalisation only (the part of FSE whose parity is pinned) */
+int b200_fse_normalize_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                           uint8_t* d_side, uint64_t side_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200COMP_H */

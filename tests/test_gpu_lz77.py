@@ -1,0 +1,158 @@
+"""GPU parity: CUDA LZ77 (both reference variants) vs the oracle, through the C-ABI.
+
+Token streams must be bit-exact with the reference's lz77_compress run per block
+on a fresh table (SURVEY.md §8a parity contracts), and decode must give the input back.
+"""
+import binascii
+
+import numpy as np
+import pytest
+
+from helpers import first_diff, fnv1a64, lcg_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def _to_dev(ctx, a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+
+
+def _corpus(n, kind=0, seed=20261018):
+    from compression_algorithms_b200 import corpus
+    return corpus.generate(n, kind, seed)
+
+
+def _as_np(data):
+    return np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data
+
+
+def _encode_check(ctx, ob, data, variant, block):
+    """returns (stream, per-block list of token bytes from the GPU)"""
+    from compression_algorithms_b200 import device as dv
+    data = _as_np(data)
+    n = data.size
+    st = dv.lz77_encode(ctx, _to_dev(ctx, data), variant, block)
+    bs = n if (block == 0 or block > n) else block
+    nblocks = (n + bs - 1) // bs
+    exp_out, exp_sizes = ob.port_lz77_compress_blocks(data, bs, variant)
+    sizes = st.block_sizes.cpu().numpy().astype(np.uint64)
+    off = st.block_off.cpu().numpy()
+    out = st.out[: st.total_bytes].cpu().numpy()
+    bad = np.nonzero(sizes != exp_sizes)[0]
+    assert bad.size == 0, "block sizes differ first at block %d: got %d want %d" % (bad[0], sizes[bad[0]], exp_sizes[bad[0]])
+    for b in range(nblocks):
+        nbytes = int(exp_sizes[b]) // 8 + 1 if variant == 0 else int(exp_sizes[b])
+        assert int(off[b + 1] - off[b]) == nbytes
+        got = out[int(off[b]): int(off[b]) + nbytes]
+        want = exp_out[b, :nbytes].copy()
+        if variant == 0 and exp_sizes[b] % 8 == 0:
+            got = got[:-1]; want = want[:-1]   # the extra byte of bit_index/8+1 is undefined in the reference (U3)
+        d = first_diff(got, want)
+        assert d == -1, "block %d differs at byte %d" % (b, d)
+    assert int(off[nblocks]) == st.total_bytes
+    dec = dv.lz77_decode(ctx, st).cpu().numpy()
+    d = first_diff(dec, data)
+    assert d == -1, "decode differs at byte %d" % d
+    return st
+
+
+def test_kat_standalone(ctx, ob):
+    """SURVEY.md §4.3 known answer produced by the compiled reference."""
+    from compression_algorithms_b200 import device as dv
+    inp = b"abc" * 10 + b"_the quick brown fox the quick brown fox!"
+    st = _encode_check(ctx, ob, inp, 0, 0)
+    assert int(st.block_sizes[0].item()) == 301
+    got = bytes(st.out[:38].cpu().numpy())
+    want = binascii.unhexlify("c288193b007c09807da183a60c883875d28c5903428c9c3777dc8030f3060f480ae053002404")
+    assert got[:37] == want[:37] and (got[37] & 0x1F) == (want[37] & 0x1F)
+
+
+def test_kat_deflate(ctx, ob):
+    inp = b"abc" * 16 + b"_the quick brown fox the quick brown fox!"
+    st = _encode_check(ctx, ob, inp, 1, 0)
+    want = binascii.unhexlify(
+        "0061006200630103001f0121000e005f00740068006500200071007500690063006b002000620072006f0077006e00200066006f00780020011400130021")
+    assert bytes(st.out[: st.total_bytes].cpu().numpy()) == want
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_golden_checksums(ctx, ob, variant):
+    """ring wrap / eviction vectors of SURVEY.md §4.3 (200 000 bytes, one block)"""
+    want = {0: {"A": (881309, 0x4ECEC64A28BFCA73), "B": (1697723, 0xEFC63237F46EA7C1)},
+            1: {"A": (185176, 0xE62329D39182A5B3), "B": (359204, 0x80E2EA207690B525)}}[variant]
+    for mode, (size, h) in want.items():
+        data = np.frombuffer(lcg_bytes(mode), dtype=np.uint8)
+        st = _encode_check(ctx, ob, data, variant, 0)
+        assert int(st.block_sizes[0].item()) == size
+        if variant == 1:
+            assert fnv1a64(st.out[:size].cpu().numpy().tobytes()) == h
+        else:
+            raw = bytearray(st.out[: size // 8 + 1].cpu().numpy().tobytes())
+            raw[-1] &= (1 << (size % 8)) - 1
+            assert fnv1a64(bytes(raw)) == h
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("kind", [0, 1, 3])
+@pytest.mark.parametrize("block", [65536, 262144])
+def test_block_parity(ctx, ob, variant, kind, block):
+    _encode_check(ctx, ob, _corpus(1_000_003, kind, 11), variant, block)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 32, 33, 1000])
+def test_tiny_and_ragged(ctx, ob, variant, n):
+    _encode_check(ctx, ob, _corpus(n, 0, 3), variant, 0)
+    if n >= 33:
+        _encode_check(ctx, ob, _corpus(n, 1, 3), variant, 16)   # many ragged 16-byte blocks
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_skewed_long_chains(ctx, ob, variant):
+    """2-symbol skewed input: probe chains thousands of slots long"""
+    _encode_check(ctx, ob, _corpus(40_000, 2, 5), variant, 0)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_zero_bytes_and_overshoot(ctx, ob, variant):
+    """U1: data containing 0x00 lets a match run past the end of the block"""
+    rng = np.random.default_rng(9)
+    data = rng.integers(0, 3, size=70000, dtype=np.uint8)
+    data[-40:] = 0
+    _encode_check(ctx, ob, data, variant, 65536)
+    _encode_check(ctx, ob, data[:5000], variant, 0)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_slot0_exception(ctx, ob, variant):
+    """U10: pattern 0x01021578 hashes to slot 0; the reference clears slot 0 early at
+    insert W-1 and keeps evicting its occupants early afterwards."""
+    assert ob.port_lz77_hash(0x01021578) == 0
+    rng = np.random.default_rng(4)
+    n = 200_000
+    data = rng.integers(97, 123, size=n, dtype=np.uint8)
+    pat = np.array([0x78, 0x15, 0x02, 0x01], dtype=np.uint8)
+    pos = 0
+    while pos + 4 < n:
+        data[pos: pos + 4] = pat
+        pos += int(rng.integers(800, 3000))
+    _encode_check(ctx, ob, data, variant, 0)
+    _encode_check(ctx, ob, data, variant, 65536)
+
+
+def test_full_size_roundtrip(ctx):
+    """BASELINE.json configs[2] size (100 MB, 64 KiB blocks): round trip + size bookkeeping."""
+    import torch
+    from compression_algorithms_b200 import device as dv
+    n = 100_000_000
+    data = torch.from_numpy(_corpus(n, 0)).to(ctx.device)
+    for variant in (1, 0):
+        st = dv.lz77_encode(ctx, data, variant, 65536)
+        off = st.block_off
+        sizes = st.block_sizes
+        per = sizes // 8 + 1 if variant == 0 else sizes
+        assert torch.equal(off[1:] - off[:-1], per)
+        assert int(off[-1].item()) == st.total_bytes
+        dec = dv.lz77_decode(ctx, st)
+        assert torch.equal(dec, data)
