@@ -56,6 +56,16 @@ def core():
         lib.b200_lz77_block_stride.argtypes = [C.c_uint64]
         lib.b200_lz77_encode_dev.argtypes = [vp, C.c_int, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp, u64p]
         lib.b200_lz77_decode_dev.argtypes = [vp, C.c_int, vp, vp, vp, C.c_uint64, C.c_uint64, vp]
+        lib.b200_ctx_set_timing.argtypes = [vp, C.c_int]
+        lib.b200_ctx_timing_count.argtypes = [vp]
+        lib.b200_ctx_timing_get.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        lib.b200_lz77_max_bytes.restype = C.c_uint64
+        lib.b200_lz77_max_bytes.argtypes = [C.c_int, C.c_uint64, C.c_uint64]
+        lib.b200_lz77_compress_host.argtypes = [vp, C.c_int, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp, u64p]
+        lib.b200_lz77_decompress_host.argtypes = [vp, C.c_int, vp, C.c_uint64, vp, vp, C.c_uint64, C.c_uint64, vp]
+        lib.b200_huffman_compress_host.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, u64p, u32p]
+        lib.b200_huffman_decompress_host.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
+        lib.b200_huffman_decompress_serial_host.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_uint64, u64p]
         if hasattr(lib, "b200_fse_layout_for"):
             lib.b200_fse_layout_for.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(FseLayout)]
             lib.b200_fse_max_words.restype = C.c_uint64

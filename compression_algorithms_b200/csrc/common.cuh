@@ -46,10 +46,29 @@ struct b200_ctx {
     size_t       pinned_cap;
     uint64_t     launches;  // kernels launched through this context (bench "gpu_launches")
     uint32_t     lz_epoch;  // last epoch tag used in this context's LZ77 table arena
+    // optional timing of the dominant kernel of every codec call (bench.py roofline):
+    // a pool of event pairs recorded in-stream, read back after the timed region
+    bool         timing;
+    static const int kTimed = 512;
+    cudaEvent_t  ev_a[kTimed], ev_b[kTimed];
+    int          ev_kind[kTimed];
+    int          ev_created, ev_used;
 };
 
 int b200_scratch(b200_ctx* ctx, int slot, size_t bytes, void** out);
 int b200_pinned(b200_ctx* ctx, size_t bytes, void** out);
+
+// bracket the dominant kernel of an API call with events when timing is enabled
+#define B200_K_LZ_PARSE 0
+#define B200_K_LZ_DECODE 1
+#define B200_K_HUFF_ENCODE 2
+#define B200_K_HUFF_DECODE 3
+#define B200_K_FSE_ENCODE 4
+#define B200_K_FSE_DECODE 5
+void b200_timed_begin(b200_ctx* ctx, int kind);
+void b200_timed_end(b200_ctx* ctx);
+#define B200_TIMED_BEGIN(ctx, kind) do { if ((ctx)->timing) b200_timed_begin((ctx), (kind)); } while (0)
+#define B200_TIMED_END(ctx) do { if ((ctx)->timing) b200_timed_end((ctx)); } while (0)
 
 static inline unsigned ceil_div_u64(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 

@@ -39,12 +39,45 @@ extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < b200_ctx::kSlots; ++i) if (ctx->buf[i]) cudaFree(ctx->buf[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < ctx->ev_created; ++i) { cudaEventDestroy(ctx->ev_a[i]); cudaEventDestroy(ctx->ev_b[i]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 extern "C" int b200_ctx_sync(b200_ctx* ctx) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+void b200_timed_begin(b200_ctx* ctx, int kind) {
+    if (ctx->ev_used >= b200_ctx::kTimed) return;
+    const int i = ctx->ev_used;
+    if (i >= ctx->ev_created) {
+        if (cudaEventCreate(&ctx->ev_a[i]) != cudaSuccess || cudaEventCreate(&ctx->ev_b[i]) != cudaSuccess) return;
+        ctx->ev_created = i + 1;
+    }
+    ctx->ev_kind[i] = kind;
+    cudaEventRecord(ctx->ev_a[i], ctx->stream);
+}
+void b200_timed_end(b200_ctx* ctx) {
+    if (ctx->ev_used >= ctx->ev_created) return;
+    cudaEventRecord(ctx->ev_b[ctx->ev_used], ctx->stream);
+    ++ctx->ev_used;
+}
+
+extern "C" int b200_ctx_set_timing(b200_ctx* ctx, int enable) {
+    ctx->timing = enable != 0;
+    ctx->ev_used = 0;   // (re)start collecting
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_timing_count(b200_ctx* ctx) { return ctx->ev_used; }
+
+extern "C" int b200_ctx_timing_get(b200_ctx* ctx, int i, int* kind, float* ms) {
+    if (i < 0 || i >= ctx->ev_used) { B200_SET_ERR("timing entry %d out of range", i); return B200_ERR_ARG; }
+    CUDA_TRY(cudaEventSynchronize(ctx->ev_b[i]));
+    CUDA_TRY(cudaEventElapsedTime(ms, ctx->ev_a[i], ctx->ev_b[i]));
+    *kind = ctx->ev_kind[i];
     return B200_OK;
 }
 

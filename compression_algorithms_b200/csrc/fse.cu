@@ -1,0 +1,372 @@
+// FSE (tANS, TABLE_LOG = 8): histogram, f64 normalisation, table build, encode and
+// decode for sm_100a.
+//
+// Reference: /root/reference/algorithms/fse/src/main.zig (Zig, does not compile).
+//   PINNED  : buildFrequencyTable :88-96 and normalizeFrequencyTable :106-149 --
+//             reproduced bit for bit (IEEE f64 divide + multiply, truncation).
+//   UNPINNED: everything after (table :151-189 is defective, encoder :42-68 is
+//             unfinished, no decoder). Kept from the reference: TABLE_LOG 8, 256-state
+//             table of {symbol u8, next_state u16, num_bits u8} (:73-82), single state
+//             starting at 0 (:52), last byte raw in the first 8 bits (:55-56), symbols
+//             visited from the end of the input (:59-62), final state flushed in 8 bits
+//             (:65), LSB-first u64 words (:28-39). Chosen here: spread step 163 and the
+//             standard tANS transition; oracle/port/fse_port.c is the written spec.
+//
+// Parallel layout: a "block" shares one table; it is cut into independent
+// "segments", each one single-state stream in exactly the reference's stream shape
+// and starting on a u64 word. One thread encodes/decodes one segment.
+#include "common.cuh"
+#include "hist.cuh"
+#include "../../include/b200comp.h"
+
+namespace {
+
+constexpr uint32_t TSIZE = 256, TLOG = 8, SEG_TILE = 128;
+
+inline uint64_t align8(uint64_t x) { return (x + 7) & ~(uint64_t)7; }
+inline uint64_t eff_block(uint64_t n, uint64_t bs, uint64_t seg) {
+    if (bs == 0 || bs >= n) { const uint64_t m = n ? n : 1; return (m + seg - 1) / seg * seg; }
+    return bs;
+}
+inline uint64_t seg_stride_words(uint64_t seg) { return seg / 8 + 2; }  // 8 bits/symbol worst case + 16 bits
+
+// ------------------------------------------------------------ normalise + tables
+// One warp per block; lane l owns symbols 8l..8l+7.
+__global__ void __launch_bounds__(32) fse_tables_kernel(const uint32_t* __restrict__ freq, uint16_t* __restrict__ norm_out,
+                                                       uint32_t* __restrict__ tt_out) {
+    __shared__ uint8_t  sym_at[TSIZE];
+    __shared__ uint16_t next[256];
+    const uint64_t b = blockIdx.x;
+    const unsigned lane = threadIdx.x;
+    uint64_t f[8];
+    uint64_t total = 0; uint32_t present = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { f[k] = freq[b * 256 + lane * 8 + k]; total += f[k]; present += f[k] != 0; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { total += __shfl_xor_sync(0xffffffffu, total, d); present += __shfl_xor_sync(0xffffffffu, present, d); }
+    if (total == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { norm_out[b * 256 + lane * 8 + k] = 0; tt_out[b * 256 + lane * 8 + k] = 0; }
+        return;
+    }
+    // main.zig:118-133 -- the only floating-point step: one divide, one multiply per symbol, truncation
+    const double scale = __ddiv_rn((double)(TSIZE - present), __ull2double_rn(total));
+    uint32_t nf[8]; uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t v = 0;
+        if (f[k]) { v = (uint32_t)__double2ull_rz(__dmul_rn(__ull2double_rn(f[k]), scale)); if (v == 0) v = 1; }
+        nf[k] = v; sum += v;
+    }
+    const uint32_t lane_sum = sum;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    // main.zig:135-148 -- the remainder goes, one at a time, to the first strict maximum;
+    // after the first increment that entry stays the maximum, so it receives all of it
+    uint32_t best = 0, besti = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (nf[k] > best) { best = nf[k]; besti = lane * 8 + k; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, d), oi = __shfl_xor_sync(0xffffffffu, besti, d);
+        if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    const uint32_t remaining = TSIZE - sum;
+    uint32_t my_sum = lane_sum;
+    if (best > 0 && (besti >> 3) == lane) { nf[besti & 7] += remaining; my_sum += remaining; }
+    // cumulative counts
+    const uint32_t incl = warp_incl_scan_u32(my_sum);
+    uint32_t cum = incl - my_sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t s = lane * 8 + k;
+        norm_out[b * 256 + s] = (uint16_t)nf[k];
+        next[s] = (uint16_t)nf[k];
+        for (uint32_t j = cum; j < cum + nf[k]; ++j) sym_at[(j * 163u) & (TSIZE - 1)] = (uint8_t)s;
+        cum += nf[k];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (uint32_t u = 0; u < TSIZE; ++u) {
+            const uint32_t s = sym_at[u];
+            const uint32_t x = next[s]; next[s] = (uint16_t)(x + 1);
+            const uint32_t nb = TLOG - (31u - (uint32_t)__clz(x));
+            const uint32_t base = (x << nb) - TSIZE;
+            tt_out[b * 256 + u] = s | (base << 8) | (nb << 24);
+        }
+    }
+}
+
+// ------------------------------------------------------------ encode
+// One thread per segment; tables of the block in shared memory.
+__global__ void __launch_bounds__(SEG_TILE) fse_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t bs, uint32_t seg,
+                                                              uint32_t spb, uint32_t tiles_per_block,
+                                                              const uint16_t* __restrict__ norm, const uint32_t* __restrict__ tt,
+                                                              uint64_t* __restrict__ scratch, uint32_t stride_words,
+                                                              uint32_t* __restrict__ seg_bits) {
+    __shared__ uint16_t s_norm[256], s_cum[256];
+    __shared__ uint8_t  s_enc[256];
+    const uint64_t b = blockIdx.x / tiles_per_block, tile = blockIdx.x % tiles_per_block;
+    for (uint32_t s = threadIdx.x; s < 256; s += blockDim.x) s_norm[s] = norm[b * 256 + s];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v[8], t = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[k] = s_norm[threadIdx.x * 8 + k]; t += v[k]; }
+        uint32_t c = warp_incl_scan_u32(t) - t;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s_cum[threadIdx.x * 8 + k] = (uint16_t)c; c += v[k]; }
+    }
+    __syncthreads();
+    for (uint32_t u = threadIdx.x; u < TSIZE; u += blockDim.x) {
+        const uint32_t e = tt[b * 256 + u];
+        const uint32_t s = e & 0xFF, nb = e >> 24, base = (e >> 8) & 0xFFFF;
+        const uint32_t x = (base + TSIZE) >> nb;
+        if (s_norm[s]) s_enc[s_cum[s] + x - s_norm[s]] = (uint8_t)u;
+    }
+    __syncthreads();
+    const uint32_t g = (uint32_t)tile * SEG_TILE + threadIdx.x;   // segment inside the block
+    if (g >= spb) return;
+    const uint64_t start = b * bs + (uint64_t)g * seg;
+    uint64_t blk_end = (b + 1) * bs; if (blk_end > n) blk_end = n;
+    if (start >= blk_end) return;
+    const uint32_t len = (uint32_t)(blk_end - start < seg ? blk_end - start : seg);
+    const uint64_t gseg = b * spb + g;
+    uint64_t* out = scratch + gseg * stride_words;
+    const uint8_t* src = in + start;
+
+    uint64_t acc = src[len - 1];   // last byte raw in the first 8 bits (main.zig:55-56)
+    uint32_t accbits = 8, w = 0;
+    uint32_t X = TSIZE;            // state value 0 (main.zig:52)
+    uint4 cache = make_uint4(0, 0, 0, 0);
+    uint32_t cache_base = 0xFFFFFFFFu;
+    for (int i = (int)len - 2; i >= 0; --i) {
+        const uint32_t cb = (uint32_t)i & ~15u;
+        if (cb != cache_base) {
+            cache_base = cb;
+            if (start + cb + 16 <= n) cache = __ldg(reinterpret_cast<const uint4*>(src + cb));
+            else {
+                uint32_t t[4] = {0, 0, 0, 0};
+                for (uint32_t k = 0; k < 16 && start + cb + k < n; ++k) t[k >> 2] |= (uint32_t)src[cb + k] << (8 * (k & 3));
+                cache = make_uint4(t[0], t[1], t[2], t[3]);
+            }
+        }
+        const uint32_t q = (uint32_t)i & 15u;
+        const uint32_t word = q < 8 ? (q < 4 ? cache.x : cache.y) : (q < 12 ? cache.z : cache.w);
+        const uint32_t s = (word >> (8 * (q & 3))) & 0xFF;
+        const uint32_t f = s_norm[s];
+        uint32_t nb = TLOG - (31u - (uint32_t)__clz(f));
+        if ((X >> nb) < f) --nb;
+        const uint64_t bits = X & ((1u << nb) - 1);
+        acc |= bits << accbits;
+        accbits += nb;
+        if (accbits >= 64) { out[w++] = acc; accbits -= 64; acc = accbits ? bits >> (nb - accbits) : 0; }
+        X = TSIZE + s_enc[s_cum[s] + (X >> nb) - f];
+    }
+    {
+        const uint64_t bits = X - TSIZE;   // final state in TABLE_LOG bits (main.zig:65)
+        acc |= bits << accbits;
+        accbits += TLOG;
+        if (accbits >= 64) { out[w++] = acc; accbits -= 64; acc = accbits ? bits >> (TLOG - accbits) : 0; }
+    }
+    if (accbits) out[w] = acc;
+    seg_bits[gseg] = w * 64 + accbits;
+}
+
+// ------------------------------------------------------------ offsets (single CTA) + gather
+__global__ void __launch_bounds__(1024) fse_offsets_kernel(const uint32_t* __restrict__ seg_bits, uint64_t nsegs,
+                                                           uint64_t* __restrict__ seg_word, uint64_t capacity,
+                                                           uint64_t* __restrict__ info) {
+    __shared__ uint64_t warp_tot[33];
+    uint64_t carry = 0, tot;
+    for (uint64_t base = 0; base < nsegs; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t v = i < nsegs ? ((uint64_t)seg_bits[i] + 63) >> 6 : 0;
+        const uint64_t ex = cta_scan_step(v, warp_tot, &tot);
+        if (i < nsegs) seg_word[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) { seg_word[nsegs] = carry; info[0] = carry; info[1] = carry > capacity ? 1 : 0; }
+}
+
+__global__ void __launch_bounds__(256) fse_gather_kernel(const uint64_t* __restrict__ scratch, uint32_t stride_words,
+                                                         const uint32_t* __restrict__ seg_bits, const uint64_t* __restrict__ seg_word,
+                                                         uint64_t nsegs, uint64_t* __restrict__ out, const uint64_t* __restrict__ info) {
+    if (info[1]) return;
+    const uint64_t g = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= nsegs) return;
+    const uint32_t nw = (seg_bits[g] + 63) >> 6;
+    const uint64_t* src = scratch + g * stride_words;
+    uint64_t* dst = out + seg_word[g];
+    for (uint32_t i = lane_id(); i < nw; i += 32) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------ decode
+__device__ __forceinline__ uint32_t get_bits(const uint64_t* __restrict__ w, uint64_t pos, uint32_t nb) {
+    if (!nb) return 0;
+    const uint64_t i = pos >> 6; const uint32_t o = (uint32_t)(pos & 63);
+    uint64_t v = __ldg(w + i) >> o;
+    if (o + nb > 64) v |= __ldg(w + i + 1) << (64 - o);
+    return (uint32_t)(v & ((1ull << nb) - 1));
+}
+
+__global__ void __launch_bounds__(SEG_TILE) fse_decode_kernel(const uint64_t* __restrict__ words, uint64_t n, uint64_t bs, uint32_t seg,
+                                                              uint32_t spb, uint32_t tiles_per_block, const uint32_t* __restrict__ tt,
+                                                              const uint32_t* __restrict__ seg_bits, const uint64_t* __restrict__ seg_word,
+                                                              uint8_t* __restrict__ out, uint32_t* __restrict__ bad) {
+    __shared__ uint32_t s_tt[TSIZE];
+    const uint64_t b = blockIdx.x / tiles_per_block, tile = blockIdx.x % tiles_per_block;
+    for (uint32_t u = threadIdx.x; u < TSIZE; u += blockDim.x) s_tt[u] = tt[b * 256 + u];
+    __syncthreads();
+    const uint32_t g = (uint32_t)tile * SEG_TILE + threadIdx.x;
+    if (g >= spb) return;
+    const uint64_t start = b * bs + (uint64_t)g * seg;
+    uint64_t blk_end = (b + 1) * bs; if (blk_end > n) blk_end = n;
+    if (start >= blk_end) return;
+    const uint32_t len = (uint32_t)(blk_end - start < seg ? blk_end - start : seg);
+    const uint64_t gseg = b * spb + g;
+    const uint64_t* w = words + seg_word[gseg];
+    const uint32_t T = seg_bits[gseg];
+    uint8_t* o = out + start;
+    if (T < 16) { atomicAdd(bad, 1u); return; }
+    uint64_t pos = T - TLOG;
+    uint32_t u = get_bits(w, pos, TLOG);
+    uint32_t i = 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
+    while (i + 1 < len) {
+        uint32_t pack[4] = {0, 0, 0, 0};
+        const uint32_t batch = len - 1 - i < 16 ? len - 1 - i : 16;
+        for (uint32_t q = 0; q < batch; ++q) {
+            const uint32_t e = s_tt[u & 0xFF];
+            const uint32_t nb = e >> 24;
+            pack[q >> 2] |= (e & 0xFF) << (8 * (q & 3));
+            if (pos < 8 + nb) { pos = 0; u = 0x100; break; }  // corrupt stream: would read below the raw byte
+            pos -= nb;
+            u = ((e >> 8) & 0xFFFF) + get_bits(w, pos, nb);
+        }
+        if (batch == 16 && aligned) *reinterpret_cast<uint4*>(o + i) = make_uint4(pack[0], pack[1], pack[2], pack[3]);
+        else for (uint32_t q = 0; q < batch; ++q) o[i + q] = (uint8_t)(pack[q >> 2] >> (8 * (q & 3)));
+        i += batch;
+        if (u == 0x100) break;
+    }
+    o[len - 1] = (uint8_t)(__ldg(w) & 0xFF);
+    if (!(pos == 8 && u == 0)) atomicAdd(bad, 1u);   // a valid stream lands back on state 0 at bit 8
+}
+
+int fse_args(uint64_t n, uint64_t block_size, uint64_t seg, uint64_t* bs_out) {
+    if (seg < 64 || seg > 65536 || (seg & (seg - 1))) { B200_SET_ERR("fse: seg_size must be a power of two in [64, 65536]"); return B200_ERR_ARG; }
+    if (block_size && block_size < n && (block_size % seg || block_size % 4096)) {
+        B200_SET_ERR("fse: block_size must be a multiple of seg_size and of 4096"); return B200_ERR_ARG;
+    }
+    *bs_out = eff_block(n, block_size, seg);
+    return B200_OK;
+}
+
+}  // namespace
+
+extern "C" int b200_fse_layout_for(uint64_t n, uint64_t block_size, uint64_t seg_size, b200_fse_layout* L) {
+    uint64_t bs;
+    B200_TRY(fse_args(n, block_size, seg_size, &bs));
+    L->nblocks = n ? (n + bs - 1) / bs : 1;
+    L->segs_per_block = bs / seg_size;
+    L->nsegs = L->nblocks * L->segs_per_block;
+    uint64_t o = 64;
+    L->off_freq = o;     o += align8(L->nblocks * 256 * 4);
+    L->off_norm = o;     o += align8(L->nblocks * 256 * 2);
+    L->off_tt = o;       o += align8(L->nblocks * 256 * 4);
+    L->off_seg_bits = o; o += align8(L->nsegs * 4);
+    L->off_seg_word = o; o += align8((L->nsegs + 1) * 8);
+    L->bytes = o;
+    return B200_OK;
+}
+
+extern "C" uint64_t b200_fse_max_words(uint64_t n, uint64_t seg_size) {
+    const uint64_t nsegs = (n + seg_size - 1) / seg_size + 1;
+    return n / 8 + nsegs * 2 + 4;
+}
+
+static int fse_front(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size, uint64_t seg_size, uint8_t* d_side,
+                     uint64_t side_bytes, b200_fse_layout* L, uint64_t* bs) {
+    if (n == 0) { B200_SET_ERR("fse: empty input"); return B200_ERR_DOMAIN; }
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_side) & 7)) { B200_SET_ERR("fse: d_in must be 16-byte and d_side 8-byte aligned"); return B200_ERR_ARG; }
+    B200_TRY(b200_fse_layout_for(n, block_size, seg_size, L));
+    if (side_bytes < L->bytes) { B200_SET_ERR("fse: side buffer too small"); return B200_ERR_CAPACITY; }
+    B200_TRY(fse_args(n, block_size, seg_size, bs));
+    CUDA_TRY(cudaMemsetAsync(d_side, 0, L->off_norm, ctx->stream));  // info + histogram
+    const uint32_t tpb = (uint32_t)((*bs + HIST_TILE - 1) / HIST_TILE);
+    byte_hist_kernel<<<(unsigned)(L->nblocks * tpb), 256, 0, ctx->stream>>>(d_in, n, *bs, tpb, reinterpret_cast<uint32_t*>(d_side + L->off_freq));
+    fse_tables_kernel<<<(unsigned)L->nblocks, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_side + L->off_freq),
+                                                                   reinterpret_cast<uint16_t*>(d_side + L->off_norm),
+                                                                   reinterpret_cast<uint32_t*>(d_side + L->off_tt));
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_fse_normalize_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size, uint8_t* d_side, uint64_t side_bytes) {
+    b200_fse_layout L; uint64_t bs;
+    return fse_front(ctx, d_in, n, block_size, 1024, d_side, side_bytes, &L, &bs);
+}
+
+extern "C" int b200_fse_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size, uint64_t seg_size,
+                                   uint64_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
+                                   uint64_t* h_total_words) {
+    b200_fse_layout L; uint64_t bs;
+    B200_TRY(fse_front(ctx, d_in, n, block_size, seg_size, d_side, side_bytes, &L, &bs));
+    const uint32_t spb = (uint32_t)L.segs_per_block;
+    const uint32_t tpb = (spb + SEG_TILE - 1) / SEG_TILE;
+    const uint32_t threads = spb < SEG_TILE ? ((spb + 31) / 32 * 32) : SEG_TILE;
+    const uint32_t stride = (uint32_t)seg_stride_words(seg_size);
+    uint64_t* scratch;
+    B200_TRY(b200_scratch(ctx, 5, (size_t)L.nsegs * stride * 8 + 64, reinterpret_cast<void**>(&scratch)));
+    uint32_t* seg_bits = reinterpret_cast<uint32_t*>(d_side + L.off_seg_bits);
+    uint64_t* seg_word = reinterpret_cast<uint64_t*>(d_side + L.off_seg_word);
+    uint64_t* info = reinterpret_cast<uint64_t*>(d_side);
+    CUDA_TRY(cudaMemsetAsync(seg_bits, 0, L.nsegs * 4, ctx->stream));
+    B200_TIMED_BEGIN(ctx, B200_K_FSE_ENCODE);
+    fse_encode_kernel<<<(unsigned)(L.nblocks * tpb), threads, 0, ctx->stream>>>(
+        d_in, n, bs, (uint32_t)seg_size, spb, tpb, reinterpret_cast<const uint16_t*>(d_side + L.off_norm),
+        reinterpret_cast<const uint32_t*>(d_side + L.off_tt), scratch, stride, seg_bits);
+    B200_TIMED_END(ctx);
+    fse_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(seg_bits, L.nsegs, seg_word, words_capacity, info);
+    fse_gather_kernel<<<(unsigned)((L.nsegs + 7) / 8), 256, 0, ctx->stream>>>(scratch, stride, seg_bits, seg_word, L.nsegs, d_words, info);
+    ctx->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    if (h_total_words) {
+        uint64_t* pin; B200_TRY(b200_pinned(ctx, 64, reinterpret_cast<void**>(&pin)));
+        CUDA_TRY(cudaMemcpyAsync(pin, info, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        *h_total_words = pin[0];
+        if (pin[1]) { B200_SET_ERR("fse: stream needs %llu words, capacity %llu", (unsigned long long)pin[0], (unsigned long long)words_capacity); return B200_ERR_CAPACITY; }
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_fse_decode_dev(b200_ctx* ctx, const uint64_t* d_words, const uint8_t* d_side, uint64_t side_bytes,
+                                   uint64_t n, uint64_t block_size, uint64_t seg_size, uint8_t* d_out, uint32_t* h_bad_segments) {
+    if (n == 0) { if (h_bad_segments) *h_bad_segments = 0; return B200_OK; }
+    b200_fse_layout L; uint64_t bs;
+    B200_TRY(b200_fse_layout_for(n, block_size, seg_size, &L));
+    B200_TRY(fse_args(n, block_size, seg_size, &bs));
+    if (side_bytes < L.bytes) { B200_SET_ERR("fse decode: side buffer too small"); return B200_ERR_CAPACITY; }
+    const uint32_t spb = (uint32_t)L.segs_per_block;
+    const uint32_t tpb = (spb + SEG_TILE - 1) / SEG_TILE;
+    const uint32_t threads = spb < SEG_TILE ? ((spb + 31) / 32 * 32) : SEG_TILE;
+    uint32_t* d_bad;
+    B200_TRY(b200_scratch(ctx, 6, 64, reinterpret_cast<void**>(&d_bad)));
+    CUDA_TRY(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    B200_TIMED_BEGIN(ctx, B200_K_FSE_DECODE);
+    fse_decode_kernel<<<(unsigned)(L.nblocks * tpb), threads, 0, ctx->stream>>>(
+        d_words, n, bs, (uint32_t)seg_size, spb, tpb, reinterpret_cast<const uint32_t*>(d_side + L.off_tt),
+        reinterpret_cast<const uint32_t*>(d_side + L.off_seg_bits), reinterpret_cast<const uint64_t*>(d_side + L.off_seg_word), d_out, d_bad);
+    B200_TIMED_END(ctx);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    if (h_bad_segments) {
+        uint32_t* pin; B200_TRY(b200_pinned(ctx, 64, reinterpret_cast<void**>(&pin)));
+        CUDA_TRY(cudaMemcpyAsync(pin, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        *h_bad_segments = pin[0];
+    }
+    return B200_OK;
+}

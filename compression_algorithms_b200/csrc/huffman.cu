@@ -9,6 +9,7 @@
 // table scope ("block") starting on a word boundary; a side buffer (b200_huff_layout)
 // with per-block tables and the chunk/sub-chunk bit index used for parallel decode.
 #include "common.cuh"
+#include "hist.cuh"
 #include "../../include/b200comp.h"
 
 namespace {
@@ -24,41 +25,7 @@ inline uint64_t eff_block(uint64_t n, uint64_t bs) {
     return bs;
 }
 
-// ---------------------------------------------------------------- K1 histogram
-// One CTA per 64 KiB tile of one block; 16-byte loads; one private 256-bin
-// histogram per warp in shared memory, merged into the block's global histogram.
-__global__ void __launch_bounds__(256) huff_hist_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t bs,
-                                                        uint32_t tiles_per_block, uint32_t* __restrict__ freq) {
-    __shared__ uint32_t h[8][256];
-    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
-    __syncthreads();
-    const uint64_t b = blockIdx.x / tiles_per_block, k = blockIdx.x % tiles_per_block;
-    const uint64_t start = b * bs + k * (uint64_t)(TILE_CHUNKS * CHUNK);
-    uint64_t end = start + TILE_CHUNKS * CHUNK;
-    if (end > (b + 1) * bs) end = (b + 1) * bs;
-    if (end > n) end = n;
-    uint32_t* my = h[threadIdx.x >> 5];
-    for (uint64_t i = start + (uint64_t)threadIdx.x * 16; i < end; i += 256 * 16) {
-        if (i + 16 <= end) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i));
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                atomicAdd(&my[w[q] & 0xFF], 1u);
-                atomicAdd(&my[(w[q] >> 8) & 0xFF], 1u);
-                atomicAdd(&my[(w[q] >> 16) & 0xFF], 1u);
-                atomicAdd(&my[w[q] >> 24], 1u);
-            }
-        } else {
-            for (uint64_t j = i; j < end; ++j) atomicAdd(&my[in[j]], 1u);
-        }
-    }
-    __syncthreads();
-    uint32_t s = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) s += h[w][threadIdx.x];
-    if (s) atomicAdd(&freq[b * 256 + threadIdx.x], s);
-}
+// K1 histogram: byte_hist_kernel in hist.cuh (shared with FSE)
 
 // ---------------------------------------------------------------- K2 table build
 // One warp per block. Lane 0 replays the reference's binary min-heap exactly
@@ -512,7 +479,7 @@ static int huff_tables(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t 
     CUDA_TRY(cudaMemsetAsync(d_side, 0, L->off_tree, ctx->stream));
     const uint32_t tpb = (uint32_t)((L->chunks_per_block + TILE_CHUNKS - 1) / TILE_CHUNKS);
     const uint64_t grid = L->nblocks * tpb;
-    huff_hist_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(d_in, n, bs, tpb, reinterpret_cast<uint32_t*>(d_side + L->off_freq));
+    byte_hist_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(d_in, n, bs, tpb, reinterpret_cast<uint32_t*>(d_side + L->off_freq));
     huff_build_kernel<<<(unsigned)L->nblocks, 32, 0, ctx->stream>>>(
         reinterpret_cast<const uint32_t*>(d_side + L->off_freq), reinterpret_cast<uint32_t*>(d_side + L->off_codes),
         d_side + L->off_lens, reinterpret_cast<int16_t*>(d_side + L->off_tree), reinterpret_cast<uint32_t*>(d_side + L->off_meta));
@@ -541,10 +508,12 @@ extern "C" int b200_huffman_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint6
                                                      L.nblocks, P, reinterpret_cast<uint64_t*>(d_side + L.off_block_bits),
                                                      reinterpret_cast<uint64_t*>(d_side + L.off_block_word),
                                                      reinterpret_cast<uint64_t*>(d_side + L.off_chunk_off), d_words, words_capacity, info);
+    B200_TIMED_BEGIN(ctx, B200_K_HUFF_ENCODE);
     huff_encode_kernel<<<(unsigned)L.nchunks, 256, 0, ctx->stream>>>(
         d_in, n, cpb, reinterpret_cast<const uint32_t*>(d_side + L.off_codes), d_side + L.off_lens,
         reinterpret_cast<const uint32_t*>(d_side + L.off_meta), reinterpret_cast<const uint32_t*>(d_side + L.off_chunk_bits),
         reinterpret_cast<const uint64_t*>(d_side + L.off_chunk_off), reinterpret_cast<uint32_t*>(d_side + L.off_sub_off), d_words, info);
+    B200_TIMED_END(ctx);
     ctx->launches += 3;
     CUDA_TRY(cudaGetLastError());
     if (h_total_words || h_worst_status) {
@@ -571,9 +540,11 @@ extern "C" int b200_huffman_decode_dev(b200_ctx* ctx, const uint32_t* d_words, u
     const uint64_t bs = eff_block(n, block_size);
     const uint32_t cpb = (uint32_t)L.chunks_per_block;
     const uint32_t tpb = (cpb + TILE_CHUNKS - 1) / TILE_CHUNKS;
+    B200_TIMED_BEGIN(ctx, B200_K_HUFF_DECODE);
     huff_decode_kernel<<<(unsigned)(L.nblocks * tpb), 256, 0, ctx->stream>>>(
         d_words, total_words, n, bs, cpb, tpb, reinterpret_cast<const uint32_t*>(d_side + L.off_codes), d_side + L.off_lens,
         reinterpret_cast<const uint64_t*>(d_side + L.off_chunk_off), reinterpret_cast<const uint32_t*>(d_side + L.off_sub_off), d_out);
+    B200_TIMED_END(ctx);
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return B200_OK;

@@ -367,10 +367,12 @@ extern "C" int b200_lz77_encode_dev(b200_ctx* ctx, int variant, const uint8_t* d
     uint64_t* block_bytes = misc + 4;
     CUDA_TRY(cudaMemsetAsync(misc, 0, 32, ctx->stream));
     const unsigned grid = (unsigned)(nwarps / 4);
+    B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
     if (variant == 0)
         lz77_parse_kernel<0><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
     else
         lz77_parse_kernel<1><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
+    B200_TIMED_END(ctx);
     ep += (uint32_t)per_warp;
     lz77_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(block_bytes, nblocks, d_block_off, out_capacity, info);
     const uint32_t pieces = (uint32_t)((stride + 32767) / 32768);
@@ -400,8 +402,10 @@ extern "C" int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d
         else CUDA_TRY(cudaFuncSetAttribute(lz77_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RING));
         attr_done[variant] = true;
     }
+    B200_TIMED_BEGIN(ctx, B200_K_LZ_DECODE);
     if (variant == 0) lz77_decode_kernel<0><<<(unsigned)nblocks, 32, RING, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, d_out);
     else lz77_decode_kernel<1><<<(unsigned)nblocks, 32, RING, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, d_out);
+    B200_TIMED_END(ctx);
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return B200_OK;

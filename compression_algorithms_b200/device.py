@@ -38,6 +38,19 @@ class Context:
     def sync(self):
         _lib.check(_lib.core().b200_ctx_sync(self._h))
 
+    def set_timing(self, enable=True):
+        _lib.check(_lib.core().b200_ctx_set_timing(self._h, 1 if enable else 0))
+
+    def timings(self):
+        """[(kind, ms)] of the dominant kernels launched since set_timing(); kinds:
+        0 LZ77 parse, 1 LZ77 decode, 2 Huffman encode, 3 Huffman decode, 4 FSE encode, 5 FSE decode"""
+        out = []
+        for i in range(_lib.core().b200_ctx_timing_count(self._h)):
+            k, ms = C.c_int(0), C.c_float(0)
+            _lib.check(_lib.core().b200_ctx_timing_get(self._h, i, C.byref(k), C.byref(ms)))
+            out.append((k.value, ms.value))
+        return out
+
     @property
     def launches(self):
         return int(_lib.core().b200_ctx_launches(self._h))
@@ -200,4 +213,88 @@ def lz77_decode(ctx, st, out=None):
         out = torch.empty(st.n, dtype=torch.uint8, device=ctx.device)
     _lib.check(_lib.core().b200_lz77_decode_dev(
         ctx.handle, st.variant, _ptr(st.out), _ptr(st.block_off), _ptr(st.block_sizes), st.n, st.block_size, _ptr(out)))
+    return out
+
+
+# ------------------------------------------------------------------ FSE
+DEFAULT_FSE_SEG = 1024
+
+
+@dataclass
+class FseStream:
+    words: torch.Tensor        # int64 storage of the u64 word stream
+    side: torch.Tensor         # uint8: histogram, normalised counts, TT, segment index
+    layout: _lib.FseLayout
+    n: int
+    block_size: int
+    seg_size: int
+    total_words: int = -1
+
+    def _view(self, off, count, dtype):
+        nbytes = count * torch.empty((), dtype=dtype).element_size()
+        return self.side[off: off + nbytes].view(dtype)
+
+    def freq(self):
+        return self._view(self.layout.off_freq, self.layout.nblocks * 256, torch.int32).view(-1, 256)
+
+    def norm(self):
+        return self._view(self.layout.off_norm, self.layout.nblocks * 256, torch.int16).view(-1, 256)
+
+    def tt(self):
+        return self._view(self.layout.off_tt, self.layout.nblocks * 256, torch.int32).view(-1, 256)
+
+    def seg_bits(self):
+        return self._view(self.layout.off_seg_bits, self.layout.nsegs, torch.int32)
+
+    def seg_word(self):
+        return self._view(self.layout.off_seg_word, self.layout.nsegs + 1, torch.int64)
+
+
+def fse_layout(n, block_size, seg_size):
+    L = _lib.FseLayout()
+    _lib.check(_lib.core().b200_fse_layout_for(n, block_size, seg_size, C.byref(L)))
+    return L
+
+
+def fse_alloc(ctx, n, block_size, seg_size):
+    L = fse_layout(n, block_size, seg_size)
+    cap = int(_lib.core().b200_fse_max_words(n, seg_size))
+    return FseStream(words=torch.empty(cap, dtype=torch.int64, device=ctx.device),
+                     side=torch.empty(L.bytes, dtype=torch.uint8, device=ctx.device),
+                     layout=L, n=n, block_size=block_size, seg_size=seg_size)
+
+
+def fse_encode(ctx, data, block_size=DEFAULT_BLOCK, seg_size=DEFAULT_FSE_SEG, stream=None, sync=True):
+    """C mirror of compress() (/root/reference/algorithms/fse/src/main.zig:50-68) per segment,
+    one table per block."""
+    _check_u8(data)
+    n = data.numel()
+    st = stream if stream is not None else fse_alloc(ctx, n, block_size, seg_size)
+    tw = C.c_uint64(0)
+    _lib.check(_lib.core().b200_fse_encode_dev(
+        ctx.handle, _ptr(data), n, block_size, seg_size, _ptr(st.words), st.words.numel(), _ptr(st.side), st.side.numel(),
+        C.byref(tw) if sync else None))
+    if sync:
+        st.total_words = tw.value
+    return st
+
+
+def fse_normalize(ctx, data, block_size=DEFAULT_BLOCK):
+    """buildFrequencyTable + normalizeFrequencyTable (main.zig:88-149) per block."""
+    _check_u8(data)
+    n = data.numel()
+    st = fse_alloc(ctx, n, block_size, DEFAULT_FSE_SEG)
+    _lib.check(_lib.core().b200_fse_normalize_dev(ctx.handle, _ptr(data), n, block_size, _ptr(st.side), st.side.numel()))
+    return st
+
+
+def fse_decode(ctx, st, out=None, sync=True):
+    if out is None:
+        out = torch.empty(st.n, dtype=torch.uint8, device=ctx.device)
+    bad = C.c_uint32(0)
+    _lib.check(_lib.core().b200_fse_decode_dev(
+        ctx.handle, _ptr(st.words), _ptr(st.side), st.side.numel(), st.n, st.block_size, st.seg_size, _ptr(out),
+        C.byref(bad) if sync else None))
+    if sync and bad.value:
+        raise RuntimeError("fse_decode: %d corrupt segment(s)" % bad.value)
     return out

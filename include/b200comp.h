@@ -44,6 +44,13 @@ int         b200_ctx_create(b200_ctx** out, int device, void* cuda_stream);
 void        b200_ctx_destroy(b200_ctx* ctx);
 int         b200_ctx_sync(b200_ctx* ctx);
 uint64_t    b200_ctx_launches(b200_ctx* ctx); /* kernels launched so far */
+/* When enabled, every codec call brackets its dominant kernel with CUDA events on
+ * the context's stream (kind: 0 LZ77 parse, 1 LZ77 decode, 2 Huffman encode,
+ * 3 Huffman decode, 4 FSE encode, 5 FSE decode). Up to 512 entries are kept since the
+ * last b200_ctx_set_timing call; b200_ctx_timing_get waits for entry i. */
+int         b200_ctx_set_timing(b200_ctx* ctx, int enable);
+int         b200_ctx_timing_count(b200_ctx* ctx);
+int         b200_ctx_timing_get(b200_ctx* ctx, int i, int* kind, float* ms);
 const char* b200_last_error(void);
 int         b200_dev_alloc(void** d_ptr, uint64_t bytes);
 int         b200_dev_free(void* d_ptr);
@@ -151,6 +158,27 @@ int b200_fse_decode_dev(b200_ctx* ctx, const uint64_t* d_words, const uint8_t* d
 /* histogram + normalisation only (the part of FSE whose parity is pinned) */
 int b200_fse_normalize_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
                            uint8_t* d_side, uint64_t side_bytes);
+
+/* ---- host-buffer wrappers: H2D -> *_dev -> D2H, synchronous ------------------
+ * These are what the reference-named shims call; bench.py's "e2e" number is
+ * measured through them with the copies inside the timed region. Host buffers may
+ * be pageable; pinned ones (b200_host_alloc) copy faster. */
+uint64_t b200_lz77_max_bytes(int variant, uint64_t n, uint64_t block_size);
+int b200_lz77_compress_host(b200_ctx* ctx, int variant, const uint8_t* h_in, uint64_t n, uint64_t block_size,
+                            uint8_t* h_out, uint64_t out_capacity, uint64_t* h_block_sizes,
+                            uint64_t* h_block_off, uint64_t* h_total_bytes);
+int b200_lz77_decompress_host(b200_ctx* ctx, int variant, const uint8_t* h_stream, uint64_t stream_bytes,
+                              const uint64_t* h_block_off, const uint64_t* h_block_sizes,
+                              uint64_t n, uint64_t block_size, uint8_t* h_out);
+int b200_huffman_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
+                               uint32_t* h_words, uint64_t words_capacity, uint8_t* h_side, uint64_t side_bytes,
+                               uint64_t* h_total_words, uint32_t* h_worst_status);
+int b200_huffman_decompress_host(b200_ctx* ctx, const uint32_t* h_words, uint64_t total_words,
+                                 const uint8_t* h_side, uint64_t side_bytes, uint64_t n, uint64_t block_size,
+                                 uint8_t* h_out);
+int b200_huffman_decompress_serial_host(b200_ctx* ctx, const uint32_t* h_words, uint64_t nwords,
+                                        uint64_t buffer_size, const uint32_t* h_codes, const uint8_t* h_lens,
+                                        uint8_t* h_out, uint64_t out_capacity, uint64_t* h_count);
 
 #ifdef __cplusplus
 }

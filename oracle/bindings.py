@@ -329,3 +329,19 @@ def port_fse_decompress(words, total_bits, n, norm):
     out = np.zeros(max(n, 1), dtype=np.uint8)
     rc = _lib("oracle_port").port_fse_decompress(_p(w, _u64p), C.c_uint64(total_bits), C.c_uint64(n), _p(nm, _u64p), _p(out, _u8p))
     return out[:n].copy(), rc
+
+
+def port_lz77_decompress_blocks(stream, off, block, n, variant, threads=0):
+    s = np.concatenate([_as_u8(stream), np.zeros(64, dtype=np.uint8)])
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    out = np.zeros(n + 64, dtype=np.uint8)
+    f = _lib("oracle_port").port_lz77_decompress_blocks
+    f.restype = C.c_uint64
+    bad = f(_p(s, _u8p), _p(off, _u64p), C.c_uint64(off.size - 1), C.c_uint64(block), C.c_uint64(n), C.c_int(variant),
+            _p(out, _u8p), C.c_int(threads))
+    return out[:n], int(bad)
+
+
+def port_threads():
+    import os
+    return os.cpu_count() or 1

@@ -253,3 +253,29 @@ uint64_t port_deflate_lz77_decompress(const uint8_t* tok, uint64_t ntokbytes, ui
     }
     return o;
 }
+
+/* Block-parallel decode (OpenMP over blocks) for the timed CPU baseline: stream is
+ * the concatenation of the per-block token streams, off[b] their byte offsets
+ * (off[nblocks] = total). variant as in port_lz77_compress_blocks. Each block
+ * decodes into out + b*block; scratch of block+64 bytes per thread absorbs the
+ * overshoot of a final match (U1). Returns the number of mismatching block sizes. */
+uint64_t port_lz77_decompress_blocks(const uint8_t* stream, const uint64_t* off, uint64_t nblocks, uint64_t block,
+                                     uint64_t n, int variant, uint8_t* out, int threads) {
+    uint64_t bad = 0;
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel num_threads(threads) reduction(+ : bad)
+    {
+        uint8_t* tmp = (uint8_t*)malloc(block + 64);
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t b = 0; b < (int64_t)nblocks; ++b) {
+            uint64_t o0 = (uint64_t)b * block;
+            uint64_t len = n - o0 < block ? n - o0 : block;
+            uint64_t got = variant ? port_deflate_lz77_decompress(stream + off[b], off[b + 1] - off[b], tmp)
+                                   : port_lz77_decompress(stream + off[b], len, tmp);
+            if (got < len) ++bad;
+            memcpy(out + o0, tmp, len);
+        }
+        free(tmp);
+    }
+    return bad;
+}

@@ -26,3 +26,5 @@ uint64_t port_fse_encode_stream(const uint8_t* in, uint64_t n, const uint64_t* n
 int port_fse_decode_stream(const uint64_t* words, uint64_t total_bits, uint64_t n, const uint32_t* tt, uint8_t* out);
 uint64_t port_fse_compress(const uint8_t* in, uint64_t n, uint64_t* words, uint64_t* norm_out, uint64_t* total_bits);
 int port_fse_decompress(const uint64_t* words, uint64_t total_bits, uint64_t n, const uint64_t* norm, uint8_t* out);
+uint64_t port_lz77_decompress_blocks(const uint8_t* stream, const uint64_t* off, uint64_t nblocks, uint64_t block,
+                                     uint64_t n, int variant, uint8_t* out, int threads);
