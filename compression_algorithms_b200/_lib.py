@@ -56,6 +56,7 @@ def core():
         lib.b200_lz77_block_stride.argtypes = [C.c_uint64]
         lib.b200_lz77_encode_dev.argtypes = [vp, C.c_int, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp, u64p]
         lib.b200_lz77_decode_dev.argtypes = [vp, C.c_int, vp, vp, vp, C.c_uint64, C.c_uint64, vp]
+        lib.b200_lz77_encode_debug_dev.argtypes = [vp, C.c_int, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp, u64p, vp]
         lib.b200_ctx_set_timing.argtypes = [vp, C.c_int]
         lib.b200_ctx_timing_count.argtypes = [vp]
         lib.b200_ctx_timing_get.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]

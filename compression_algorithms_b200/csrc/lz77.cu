@@ -326,12 +326,16 @@ inline uint64_t round16(uint64_t x) { return (x + 15) & ~(uint64_t)15; }
 
 }  // namespace
 
+bool lz77_v2_supported(uint64_t bs);
+int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
+                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok);
+
 extern "C" uint64_t b200_lz77_block_stride(uint64_t block_size) { return round16(2 * block_size + 16); }
 
 // scratch slots used: 1 tables, 2 clear queues, 3 token scratch, 4 block_bytes/info/err
-extern "C" int b200_lz77_encode_dev(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t block_size,
-                                    uint8_t* d_out, uint64_t out_capacity, uint64_t* d_block_sizes, uint64_t* d_block_off,
-                                    uint64_t* h_total_bytes) {
+static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                            uint8_t* d_out, uint64_t out_capacity, uint64_t* d_block_sizes, uint64_t* d_block_off,
+                            uint64_t* h_total_bytes, uint32_t* dbg_tok) {
     if (variant != 0 && variant != 1) { B200_SET_ERR("lz77: variant must be 0 or 1"); return B200_ERR_ARG; }
     if (n == 0) {
         CUDA_TRY(cudaMemsetAsync(d_block_off, 0, 2 * sizeof(uint64_t), ctx->stream));
@@ -343,37 +347,46 @@ extern "C" int b200_lz77_encode_dev(b200_ctx* ctx, int variant, const uint8_t* d
     const uint64_t nblocks = (n + bs - 1) / bs;
     const uint64_t stride = b200_lz77_block_stride(bs);
 
-    int wps = 32;
-    if (const char* e = getenv("B200_LZ_WARPS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 64) wps = v; }
-    uint64_t nwarps = (uint64_t)ctx->sm_count * wps;
-    if (nwarps > nblocks) nwarps = nblocks;
-    nwarps = (nwarps + 3) / 4 * 4;  // 4 warps per CTA
-    const uint64_t per_warp = (nblocks + nwarps - 1) / nwarps;
-
-    const size_t table_bytes = (size_t)nwarps * (TABLE_SLOTS + GUARD) * sizeof(uint2);
-    uint2* tables; uint32_t* clrq; uint8_t* scratch; uint64_t* misc;
-    const bool fresh = ctx->cap[1] < table_bytes;
-    B200_TRY(b200_scratch(ctx, 1, table_bytes, reinterpret_cast<void**>(&tables)));
-    B200_TRY(b200_scratch(ctx, 2, (size_t)nwarps * CLRQ * 4, reinterpret_cast<void**>(&clrq)));
+    // v2: whole table in one SM's shared memory (blocks <= 64 KiB); v1: table in HBM (any block <= 4 MiB)
+    const bool use_v2 = lz77_v2_supported(bs) && !getenv("B200_LZ_FORCE_V1");
+    uint8_t* scratch; uint64_t* misc;
     B200_TRY(b200_scratch(ctx, 3, (size_t)(nblocks * stride + 64), reinterpret_cast<void**>(&scratch)));
     B200_TRY(b200_scratch(ctx, 4, (size_t)(nblocks * 8 + 64), reinterpret_cast<void**>(&misc)));
-    uint32_t& ep = ctx->lz_epoch;
-    if (fresh || ep + per_warp > MAX_EPOCH) {
-        CUDA_TRY(cudaMemsetAsync(tables, 0, ctx->cap[1], ctx->stream));
-        ep = 0;
-    }
     uint64_t* info = misc;                       // [0] total, [1] overflow
     uint32_t* err = reinterpret_cast<uint32_t*>(misc + 2);
     uint64_t* block_bytes = misc + 4;
     CUDA_TRY(cudaMemsetAsync(misc, 0, 32, ctx->stream));
-    const unsigned grid = (unsigned)(nwarps / 4);
-    B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
-    if (variant == 0)
-        lz77_parse_kernel<0><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
-    else
-        lz77_parse_kernel<1><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
-    B200_TIMED_END(ctx);
-    ep += (uint32_t)per_warp;
+    if (use_v2) {
+        B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
+        B200_TRY(lz77_v2_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
+        B200_TIMED_END(ctx);
+    } else {
+        if (dbg_tok) { B200_SET_ERR("lz77: token dump needs the shared-memory path (block <= 65536)"); return B200_ERR_ARG; }
+        int wps = 32;
+        if (const char* e = getenv("B200_LZ_WARPS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 64) wps = v; }
+        uint64_t nwarps = (uint64_t)ctx->sm_count * wps;
+        if (nwarps > nblocks) nwarps = nblocks;
+        nwarps = (nwarps + 3) / 4 * 4;  // 4 warps per CTA
+        const uint64_t per_warp = (nblocks + nwarps - 1) / nwarps;
+        const size_t table_bytes = (size_t)nwarps * (TABLE_SLOTS + GUARD) * sizeof(uint2);
+        uint2* tables; uint32_t* clrq;
+        const bool fresh = ctx->cap[1] < table_bytes;
+        B200_TRY(b200_scratch(ctx, 1, table_bytes, reinterpret_cast<void**>(&tables)));
+        B200_TRY(b200_scratch(ctx, 2, (size_t)nwarps * CLRQ * 4, reinterpret_cast<void**>(&clrq)));
+        uint32_t& ep = ctx->lz_epoch;
+        if (fresh || ep + per_warp > MAX_EPOCH) {
+            CUDA_TRY(cudaMemsetAsync(tables, 0, ctx->cap[1], ctx->stream));
+            ep = 0;
+        }
+        const unsigned grid = (unsigned)(nwarps / 4);
+        B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
+        if (variant == 0)
+            lz77_parse_kernel<0><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
+        else
+            lz77_parse_kernel<1><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
+        B200_TIMED_END(ctx);
+        ep += (uint32_t)per_warp;
+    }
     lz77_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(block_bytes, nblocks, d_block_off, out_capacity, info);
     const uint32_t pieces = (uint32_t)((stride + 32767) / 32768);
     lz77_gather_kernel<<<(unsigned)(nblocks * pieces), 256, 0, ctx->stream>>>(scratch, stride, block_bytes, d_block_off, pieces, d_out, info);
@@ -388,6 +401,21 @@ extern "C" int b200_lz77_encode_dev(b200_ctx* ctx, int variant, const uint8_t* d
         if (reinterpret_cast<uint32_t*>(pin + 2)[0]) { B200_SET_ERR("lz77: slot-0 clear queue overflow"); return B200_ERR_DOMAIN; }
     }
     return B200_OK;
+}
+
+extern "C" int b200_lz77_encode_dev(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                                    uint8_t* d_out, uint64_t out_capacity, uint64_t* d_block_sizes, uint64_t* d_block_off,
+                                    uint64_t* h_total_bytes) {
+    return lz77_encode_impl(ctx, variant, d_in, n, block_size, d_out, out_capacity, d_block_sizes, d_block_off, h_total_bytes, nullptr);
+}
+
+// Test hook: same as b200_lz77_encode_dev, additionally dumping the per-position token
+// candidates of the match finder (0 = literal, else offset | len << 16) for every block,
+// 65536 entries per block. Only for blocks <= 65536 bytes.
+extern "C" int b200_lz77_encode_debug_dev(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                                          uint8_t* d_out, uint64_t out_capacity, uint64_t* d_block_sizes, uint64_t* d_block_off,
+                                          uint64_t* h_total_bytes, uint32_t* d_tok) {
+    return lz77_encode_impl(ctx, variant, d_in, n, block_size, d_out, out_capacity, d_block_sizes, d_block_off, h_total_bytes, d_tok);
 }
 
 extern "C" int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d_stream, const uint64_t* d_block_off,

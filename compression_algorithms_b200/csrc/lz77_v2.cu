@@ -1,0 +1,515 @@
+// LZ77 v2: the reference's 2^20-slot hash table emulated slot-exactly inside ONE SM's
+// shared memory, for blocks of up to 65536 bytes (the reference's BUFFER_SIZE,
+// algorithms/deflate/deflate.h:8).
+//
+// Why this is exact (DESIGN.md "LZ77 v2" has the full argument):
+//  * every position is inserted exactly once, in order (lz77.c:295,333-336;
+//    deflate/lz77.c:228,267-270) and find is read-only, so F(p) = find(word(p)) after
+//    inserts 0..p-1 is a pure function of the data; the parse only selects which F(p)
+//    are used.
+//  * with expiry, the set of live slots is always a subset of the slots occupied when
+//    nothing ever expires, and that set does not depend on insertion order. So the
+//    no-expiry occupancy bitmap (built with parallel atomicOr linear probing) bounds
+//    every probe walk; rank(slot) in that bitmap is a dense "compact slot" index, and the
+//    whole table becomes u16 T[n] (key = position+1, 0 = never used) = 128 KiB.
+//  * maximal runs of occupied slots ("clusters") never interact, so the slot space is
+//    cut into 32 ranges at cluster ends and each warp simulates one range over its own
+//    time-ordered list of positions.
+//  * inside a warp 32 consecutive list entries walk the table speculatively; a lane keeps
+//    a cursor (all slots before it proven live at its time), re-validates it after every
+//    commit round and commits once no lower uncommitted lane shares its cursor. That is
+//    the sequential semantics, because a placement only ever turns a dead slot live.
+//  * the cluster touching slot 0 (and, for the wrapping deflate insert, the one touching
+//    slot 2^20-1) is simulated serially with the reference's early slot-0 clear
+//    (lz77.c:70-85, U10).
+//
+// Phases per block (one persistent CTA of 1024 threads per SM):
+//   P0 load block -> smem | P1 occupancy bitmap | P2 rank prefix, range cuts
+//   P3 compact index + stable partition into 32 per-range lists (global, L2 resident)
+//   P4 table simulation -> tok[p] = 0 (literal) | offset | len<<16   (global, L2 resident)
+//   P5 greedy parse: per-64-position chunk exit functions (backward DP), entry offsets
+//   P6 token emission into the block's scratch slot (then lz77_offsets/gather as in v1)
+#include "common.cuh"
+#include "../../include/b200comp.h"
+
+namespace {
+
+constexpr uint32_t SLOTS = 1u << 20;
+constexpr uint32_t GUARD_BITS = 65536u;
+constexpr uint32_t BM_WORDS = (SLOTS + GUARD_BITS) / 32;     // 34816
+constexpr uint32_t PRE_CHUNK = 8;                            // words per rank-prefix entry
+constexpr uint32_t PRE_N = BM_WORDS / PRE_CHUNK;             // 4352
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t MAXB = 65536;                             // max block bytes on this path
+constexpr uint32_t NTHREADS = 1024;
+constexpr uint32_t NR = 32;                                  // ranges == warps
+
+// shared memory layout (bytes)
+constexpr uint32_t OFF_DATA = 0;
+constexpr uint32_t SZ_DATA = MAXB + 128;                     // zero pad behind the block (U1)
+constexpr uint32_t OFF_BIG = OFF_DATA + SZ_DATA;
+constexpr uint32_t SZ_BIG = BM_WORDS * 4;                    // 139264: bitmap | T+B1 | adv+exit | staging
+constexpr uint32_t OFF_PRE = OFF_BIG + SZ_BIG;               // must directly follow BIG (staging may spill)
+constexpr uint32_t SZ_PRE = (PRE_N + 4) * 4;
+constexpr uint32_t OFF_MISC = OFF_PRE + SZ_PRE;
+constexpr uint32_t SZ_MISC = 8192;
+constexpr uint32_t SMEM_BYTES = OFF_MISC + SZ_MISC;          // 230,544 <= 232,448
+
+constexpr uint32_t T_ENTRIES = MAXB + 64;
+constexpr uint32_t OFF_T = 0;                                // inside BIG
+constexpr uint32_t OFF_B1 = T_ENTRIES * 2;                   // inside BIG, u16[2052]
+constexpr uint32_t OFF_ADV = 0;                              // inside BIG, u8[MAXB+64]
+constexpr uint32_t OFF_EXIT = MAXB + 64;                     // inside BIG, u8[MAXB]
+constexpr uint32_t OFF_STAGE = MAXB + 64;                    // inside BIG (after adv), u32 words, V0 only
+
+struct Misc {
+    uint32_t cut[NR + 1];
+    uint32_t top_start, sp_lo_end, sp_hi_start, pad0;
+    uint32_t rstart[NR + 1];
+    uint32_t cnt[NR][NR];        // [warp][range]
+    uint32_t clr[64];            // slot-0 clear times (warp 0)
+    uint8_t  sexit[NR][32];      // super-chunk exit functions
+    uint8_t  sentry[NR + 1];
+    uint32_t scan[34];
+    uint32_t entry_pad;
+};
+static_assert(sizeof(Misc) <= SZ_MISC, "misc region too small");
+
+template <int V> struct Cfg;
+template <> struct Cfg<0> { static constexpr uint32_t W = 1u << 14, MAXLEN = 15; };
+template <> struct Cfg<1> { static constexpr uint32_t W = 1u << 15, MAXLEN = 31; };
+
+__device__ __forceinline__ uint32_t sm_word(const uint8_t* data, uint32_t p) {
+    // unaligned little-endian 4-byte read from shared memory (pad behind the block is zero)
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(data + (p & ~3u));
+    return __funnelshift_r(a[0], a[1], (p & 3u) * 8);
+}
+
+__device__ __forceinline__ uint32_t bm_rank(const uint32_t* bm, const uint32_t* pre, uint32_t s) {
+    const uint32_t wi = s >> 5;
+    uint32_t r = pre[wi / PRE_CHUNK];
+    for (uint32_t w = wi & ~(PRE_CHUNK - 1); w < wi; ++w) r += __popc(bm[w]);
+    return r + __popc(bm[wi] & ((1u << (s & 31)) - 1u));
+}
+
+template <int V>
+__global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t bs, uint32_t nblocks,
+                                                             uint32_t* __restrict__ lists_all, uint32_t* __restrict__ tok_all,
+                                                             uint8_t* __restrict__ scratch, uint64_t stride,
+                                                             uint64_t* __restrict__ block_sizes, uint64_t* __restrict__ block_bytes,
+                                                             uint32_t* __restrict__ dbg_tok) {
+    constexpr uint32_t W = Cfg<V>::W, MAXLEN = Cfg<V>::MAXLEN;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* data = smem + OFF_DATA;
+    uint8_t* big = smem + OFF_BIG;
+    uint32_t* bm = reinterpret_cast<uint32_t*>(big);
+    uint32_t* pre = reinterpret_cast<uint32_t*>(smem + OFF_PRE);
+    Misc* ms = reinterpret_cast<Misc*>(smem + OFF_MISC);
+    uint16_t* T = reinterpret_cast<uint16_t*>(big + OFF_T);
+    uint16_t* B1 = reinterpret_cast<uint16_t*>(big + OFF_B1);
+    uint8_t* adv = big + OFF_ADV;
+    uint8_t* exitof = big + OFF_EXIT;
+    uint32_t* stage = reinterpret_cast<uint32_t*>(big + OFF_STAGE);
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* lists = lists_all + (uint64_t)blockIdx.x * MAXB;
+    uint32_t* tokb = tok_all + (uint64_t)blockIdx.x * MAXB;
+
+    for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const uint8_t* src = in + (uint64_t)b * bs;
+        const uint32_t len = (uint32_t)(n - (uint64_t)b * bs < bs ? n - (uint64_t)b * bs : bs);
+
+        // ---------------- P0: block -> shared memory, zero pad, zero bitmap
+        {
+            const bool al = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+            for (uint32_t i = tid * 16; i < len + 128 && i < SZ_DATA; i += NTHREADS * 16) {
+                if (al && i + 16 <= len) *reinterpret_cast<uint4*>(data + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
+                else for (uint32_t k = 0; k < 16 && i + k < SZ_DATA; ++k) data[i + k] = (i + k < len) ? __ldg(src + i + k) : 0;
+            }
+            for (uint32_t i = tid; i < BM_WORDS; i += NTHREADS) bm[i] = 0;
+        }
+        __syncthreads();
+
+        // ---------------- P1: no-expiry occupancy (order independent) by atomic linear probing
+        for (uint32_t i = tid; i < len; i += NTHREADS) {
+            uint32_t s = lz_hash(sm_word(data, i));
+            for (;;) {
+                const uint32_t wi = s >> 5;
+                const uint32_t free_bits = ~bm[wi] & (0xFFFFFFFFu << (s & 31));
+                if (free_bits) {
+                    const uint32_t bit = 1u << (__ffs(free_bits) - 1);
+                    if (!(atomicOr(&bm[wi], bit) & bit)) break;
+                    continue;  // lost the race for that bit: look again in the same word
+                }
+                s = (wi + 1) << 5;
+                if (V == 1 && s >= SLOTS) s = 0;   // the deflate insert wraps (deflate/lz77.c:99-101)
+            }
+        }
+        __syncthreads();
+
+        // ---------------- P2: rank prefix per 8-word chunk, range cuts, special cluster bounds
+        {
+            // thread t owns chunks [5t, 5t+5)
+            uint32_t c0 = tid * 5, mine = 0;
+            uint32_t part[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                uint32_t s = 0;
+                if (c0 + k < PRE_N) for (uint32_t w = 0; w < PRE_CHUNK; ++w) s += __popc(bm[(c0 + k) * PRE_CHUNK + w]);
+                part[k] = s; mine += s;
+            }
+            const uint32_t incl = warp_incl_scan_u32(mine);
+            if (lane == 31) ms->scan[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t t = ms->scan[lane];
+                const uint32_t ti = warp_incl_scan_u32(t);
+                ms->scan[lane] = ti - t;
+            }
+            __syncthreads();
+            uint32_t run = ms->scan[warp] + incl - mine;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) { if (c0 + k < PRE_N) pre[c0 + k] = run; run += part[k]; }
+            if (tid < NR) {
+                uint32_t s = tid << 15;   // first free slot at/after the slice start, a word at a time
+                for (;;) {
+                    const uint32_t wi = s >> 5;
+                    const uint32_t z = ~bm[wi] & (0xFFFFFFFFu << (s & 31));
+                    if (z) { s = (wi << 5) + (uint32_t)(__ffs(z) - 1); break; }
+                    s = (wi + 1) << 5;
+                    if (s >= SLOTS + GUARD_BITS) break;
+                }
+                ms->cut[tid] = s;
+            }
+            if (tid == NR) {
+                ms->cut[NR] = SLOTS + GUARD_BITS;
+                uint32_t ts = SLOTS;
+                if (V == 1 && ((bm[(SLOTS - 1) >> 5] >> 31) & 1u)) {
+                    ts = SLOTS - 1;   // walk down to the first slot of the run that ends at the last slot
+                    while (ts > 0) {
+                        if ((ts & 31) == 0 && bm[(ts - 1) >> 5] == 0xFFFFFFFFu) { ts -= 32; continue; }
+                        if (!((bm[(ts - 1) >> 5] >> ((ts - 1) & 31)) & 1u)) break;
+                        --ts;
+                    }
+                }
+                ms->top_start = ts;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            ms->sp_lo_end = bm_rank(bm, pre, ms->cut[0]);
+            ms->sp_hi_start = ms->top_start < SLOTS ? bm_rank(bm, pre, ms->top_start) : 0xFFFFFFFFu;
+        }
+        for (uint32_t i = tid; i < NR * NR; i += NTHREADS) (&ms->cnt[0][0])[i] = 0;
+        __syncthreads();
+
+        // ---------------- P3: compact index + stable partition by range into per-range lists
+        const uint32_t slice = ((len + NTHREADS - 1) / NTHREADS) * 32;   // positions per warp (multiple of 32)
+        const uint32_t p_lo = warp * slice, p_hi = (p_lo + slice < len) ? p_lo + slice : len;
+        const uint32_t top_start = ms->top_start;
+        // pass 1: counts per (warp, range)
+        for (uint32_t base = p_lo; base < p_hi; base += 32) {
+            const uint32_t i = base + lane;
+            if (i < p_hi) {
+                const uint32_t h = lz_hash(sm_word(data, i));
+                uint32_t r = h >> 15;
+                while (r > 0 && h < ms->cut[r]) --r;
+                if (V == 1 && h >= top_start) r = 0;
+                atomicAdd(&ms->cnt[warp][r], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid < NR) {           // totals per range -> range start offsets (thread r sums column r)
+            uint32_t t = 0;
+            for (uint32_t w = 0; w < NR; ++w) t += ms->cnt[w][tid];
+            const uint32_t incl = warp_incl_scan_u32(t);
+            ms->rstart[tid] = incl - t;
+            if (tid == NR - 1) ms->rstart[NR] = incl;
+        }
+        __syncthreads();
+        {   // turn cnt[w][r] into the running write cursor of (warp w, range r)
+            uint32_t mycur = 0;
+            if (tid < NR * NR) {
+                const uint32_t w = tid >> 5, r = tid & 31;
+                mycur = ms->rstart[r];
+                for (uint32_t w2 = 0; w2 < w; ++w2) mycur += ms->cnt[w2][r];
+            }
+            __syncthreads();
+            if (tid < NR * NR) ms->cnt[tid >> 5][tid & 31] = mycur;
+        }
+        __syncthreads();
+        // pass 2: ordered scatter (warp = contiguous time slice, lanes in position order)
+        for (uint32_t base = p_lo; base < p_hi; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < p_hi;
+            uint32_t r = 0xFFu, c = 0;
+            if (valid) {
+                const uint32_t h = lz_hash(sm_word(data, i));
+                r = h >> 15;
+                while (r > 0 && h < ms->cut[r]) --r;
+                if (V == 1 && h >= top_start) r = 0;
+                c = bm_rank(bm, pre, h);
+            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, r);
+            const uint32_t myrank = __popc(peers & lt_mask);
+            uint32_t basepos = 0;
+            if (valid) basepos = ms->cnt[warp][r];
+            __syncwarp();
+            if (valid) {
+                lists[basepos + myrank] = i | (c << 16);
+                if (myrank == 0) ms->cnt[warp][r] = basepos + __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---------------- P4: table simulation. T[k] = position+1 of the entry in compact slot k, 0 = never used
+        for (uint32_t i = tid; i < (T_ENTRIES + 2052) / 2 + 2; i += NTHREADS) reinterpret_cast<uint32_t*>(big)[i] = 0;   // T and B1
+        __syncthreads();
+        {
+            const uint32_t sp_lo_end = ms->sp_lo_end, sp_hi_start = ms->sp_hi_start;
+            uint32_t cur = ms->rstart[warp];
+            const uint32_t end = ms->rstart[warp + 1];
+            uint32_t qh = 0, qt = 0;                       // slot-0 clear queue (only warp 0 ever uses it)
+            if (warp == 0) { if (lane == 0) ms->clr[0] = W - 1; qt = 1; }
+            __syncwarp();
+            while (cur < end) {
+                const uint32_t lanes = end - cur < 32 ? end - cur : 32;
+                uint32_t q = 0, kk = 0;
+                bool special = false;
+                if (lane < lanes) {
+                    const uint32_t ent = lists[cur + lane];
+                    q = ent & 0xFFFFu; kk = ent >> 16;
+                    special = kk < sp_lo_end || kk >= sp_hi_start;
+                }
+                const uint32_t spmask = __ballot_sync(0xffffffffu, special);
+                if (spmask & 1u) {
+                    // ---- serial path for the cluster that touches slot 0 / the table end: exact reference order
+                    const uint32_t q0 = __shfl_sync(0xffffffffu, q, 0), c0 = __shfl_sync(0xffffffffu, kk, 0);
+                    if (lane == 0) {
+                        while (qh < qt && ms->clr[qh & 63] < q0) { if (sp_lo_end) { T[0] = 0; B1[0] = 0; } ++qh; }
+                        const uint32_t dthr = q0 > W ? q0 - W : 0;
+                        const uint32_t w = sm_word(data, q0);
+                        uint32_t k = c0, m = NONE;
+                        bool ran_off = false;
+                        for (;;) {
+                            const uint32_t v = T[k];
+                            if (v <= dthr) break;
+                            if (sm_word(data, v - 1) == w) { m = v - 1; break; }
+                            if (k + 1 == len) { ran_off = true; break; }   // find does not wrap (lz77.c:102, deflate/lz77.c:168)
+                            ++k;
+                        }
+                        uint32_t e = ran_off ? 0 : k;                      // the wrapping insert continues at slot 0
+                        for (;;) { if (T[e] <= dthr) break; ++e; if (e == len) e = 0; }
+                        if (q0 != 65535u) T[e] = (uint16_t)(q0 + 1);
+                        if (e == 0 && sp_lo_end) { ms->clr[qt & 63] = q0 + W; ++qt; }
+                        if (qh < qt && ms->clr[qh & 63] == q0) { if (sp_lo_end) { T[0] = 0; B1[0] = 0; } ++qh; }
+                        // token candidate
+                        uint32_t tk = 0;
+                        const bool reject = (m == NONE) || (V ? (q0 - m >= W - 1) : (q0 - m == W));
+                        if (!reject) {
+                            uint32_t l = 4;
+                            while (l < MAXLEN && data[m + l] == data[q0 + l]) ++l;
+                            tk = (q0 - m) | (l << 16);
+                        }
+                        tokb[q0] = tk;
+                    }
+                    qh = __shfl_sync(0xffffffffu, qh, 0); qt = __shfl_sync(0xffffffffu, qt, 0);
+                    cur += 1;
+                    __syncwarp();
+                    continue;
+                }
+                const uint32_t L = spmask ? (uint32_t)(__ffs(spmask) - 1) : lanes;   // stop before the first special entry
+                bool done = lane >= L;
+                const uint32_t dthr = q > W ? q - W : 0;
+                const uint32_t w = done ? 0u : sm_word(data, q);
+                uint32_t fm = NONE; bool pend = true;
+                uint32_t gstart = (kk & 31) == 0 ? kk : NONE, gmin = 0xFFFFu;
+                while (__ballot_sync(0xffffffffu, !done)) {
+                    if (!done) {
+                        // advance the cursor to the first slot that is dead at time q
+                        for (;;) {
+                            if (!pend && (kk & 31) == 0 && B1[kk >> 5] > dthr) { kk += 32; gstart = kk; continue; }
+                            const uint32_t v = T[kk];
+                            if (v <= dthr) break;
+                            if (pend && sm_word(data, v - 1) == w) { fm = v - 1; pend = false; }
+                            if ((kk & 31) == 0) { gmin = v; gstart = kk; } else if (v < gmin) gmin = v;
+                            if ((kk & 31) == 31 && gstart == (kk & ~31u)) B1[kk >> 5] = (uint16_t)gmin;   // full group seen live: lower bound
+                            ++kk;
+                        }
+                    }
+                    __syncwarp();
+                    const uint32_t key = done ? (0x80000000u | lane) : kk;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+                    const bool conflict = !done && (peers & lt_mask) != 0;
+                    const uint32_t cmask = __ballot_sync(0xffffffffu, conflict);
+                    const uint32_t firstc = cmask ? (uint32_t)(__ffs(cmask) - 1) : 32u;
+                    if (!done && lane < firstc) {
+                        if (q != 65535u) T[kk] = (uint16_t)(q + 1);      // position 65535 is never looked up again
+                        uint32_t tk = 0;
+                        const uint32_t m = fm;
+                        const bool reject = (m == NONE) || (V ? (q - m >= W - 1) : (q - m == W));
+                        if (!reject) {
+                            uint32_t l = 4;
+                            while (l < MAXLEN && data[m + l] == data[q + l]) ++l;
+                            tk = (q - m) | (l << 16);
+                        }
+                        tokb[q] = tk;
+                        done = true;
+                    }
+                    __syncwarp();
+                }
+                cur += L;
+            }
+        }
+        __syncthreads();
+
+        // ---------------- P5: greedy parse. adv[p] = bytes consumed by the token that would start at p
+        for (uint32_t i = tid; i < len; i += NTHREADS) {
+            const uint32_t t = tokb[i];
+            if (dbg_tok) dbg_tok[(uint64_t)b * MAXB + i] = t;
+            adv[i] = (uint8_t)((t >> 16) ? (t >> 16) : 1u);
+        }
+        __syncthreads();
+        const uint32_t nchunks = (len + 63) >> 6;
+        if (tid < nchunks) {   // exit function of chunk tid by backward DP over its 64 positions
+            const uint32_t lo = tid << 6, cend = lo + 64;
+            const uint32_t hi = cend < len ? cend : len;
+            for (uint32_t p = hi; p-- > lo;) {
+                const uint32_t nx = p + adv[p];
+                exitof[p] = (uint8_t)(nx >= cend ? nx - cend : exitof[nx]);
+            }
+        }
+        __syncthreads();
+        {   // entry offset of every chunk: 32 super-chunks of 32 chunks
+            const uint32_t s = warp;
+            uint32_t e = lane;
+            for (uint32_t k = 0; k < 32; ++k) {
+                const uint32_t ch = s * 32 + k;
+                const uint32_t p = (ch << 6) + e;
+                if (ch < nchunks && p < len && e < 31) e = exitof[p];
+            }
+            ms->sexit[s][lane] = (uint8_t)e;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t e = 0;
+            for (uint32_t s = 0; s < NR; ++s) { ms->sentry[s] = (uint8_t)e; e = ms->sexit[s][e]; }
+        }
+        __syncthreads();
+        uint8_t* centry = reinterpret_cast<uint8_t*>(pre) + 8192;   // rank prefix is dead: u8[1024] chunk entry offsets (clear of the V0 staging spill)
+        if (lane == 0) {
+            uint32_t e = ms->sentry[warp];
+            for (uint32_t k = 0; k < 32; ++k) {
+                const uint32_t ch = warp * 32 + k;
+                centry[ch] = (uint8_t)e;
+                const uint32_t p = (ch << 6) + e;
+                if (ch < nchunks && p < len) e = exitof[p];
+            }
+        }
+        __syncthreads();
+        // per-chunk output size, CTA exclusive scan
+        uint32_t my_units = 0;   // bytes (V1) or bits (V0)
+        if (tid < nchunks) {
+            const uint32_t cend = (tid << 6) + 64;
+            const uint32_t hi = cend < len ? cend : len;
+            for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[p]) {
+                const bool lit = adv[p] == 1;   // matches are at least 4 long
+                my_units += V ? (lit ? 2u : 4u) : (lit ? 9u : 19u);
+            }
+        }
+        uint32_t my_off;
+        {
+            const uint32_t incl = warp_incl_scan_u32(my_units);
+            if (lane == 31) ms->scan[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t t = ms->scan[lane];
+                const uint32_t ti = warp_incl_scan_u32(t);
+                ms->scan[lane] = ti - t;
+                if (lane == 31) ms->scan[32] = ti;
+            }
+            __syncthreads();
+            my_off = ms->scan[warp] + incl - my_units;
+        }
+        const uint32_t total_units = ms->scan[32];
+        uint8_t* out = scratch + (uint64_t)b * stride;
+
+        // ---------------- P6: emission
+        if (V == 1) {
+            if (tid < nchunks) {
+                const uint32_t cend = (tid << 6) + 64;
+                const uint32_t hi = cend < len ? cend : len;
+                uint32_t o = my_off;
+                for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[p]) {
+                    const uint32_t t = tokb[p];
+                    if (t == 0) { *reinterpret_cast<uint16_t*>(out + o) = (uint16_t)((uint32_t)data[p] << 8); o += 2; }
+                    else {
+                        const uint32_t off = t & 0xFFFFu, ml = t >> 16;
+                        *reinterpret_cast<uint16_t*>(out + o) = (uint16_t)(1u | ((off & 0xFFu) << 8));
+                        *reinterpret_cast<uint16_t*>(out + o + 2) = (uint16_t)((off >> 8) | (ml << 8));
+                        o += 4;
+                    }
+                }
+            }
+            if (tid == 0) { block_sizes[b] = total_units; block_bytes[b] = total_units; }
+        } else {
+            // LSB-first bit stream staged in shared memory (exitof is dead now), then stored coalesced
+            const uint32_t nwords = (total_units >> 5) + 2;
+            __syncthreads();
+            for (uint32_t i = tid; i < nwords; i += NTHREADS) stage[i] = 0;
+            __syncthreads();
+            if (tid < nchunks && my_units) {
+                const uint32_t cend = (tid << 6) + 64;
+                const uint32_t hi = cend < len ? cend : len;
+                uint32_t wi = my_off >> 5, have = my_off & 31;
+                bool first = have != 0;
+                uint64_t acc = 0;
+                for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[p]) {
+                    const uint32_t t = tokb[p];
+                    uint32_t v, nb;
+                    if (t == 0) { v = (uint32_t)data[p] << 1; nb = 9; }
+                    else { v = 1u | ((t & 0xFFFFu) << 1) | ((t >> 16) << 15); nb = 19; }
+                    acc |= (uint64_t)v << have;
+                    have += nb;
+                    if (have >= 32) {
+                        if (first) { atomicOr(&stage[wi], (uint32_t)acc); first = false; } else stage[wi] = (uint32_t)acc;
+                        ++wi; acc >>= 32; have -= 32;
+                    }
+                }
+                if (have) atomicOr(&stage[wi], (uint32_t)acc);
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < nwords; i += NTHREADS) reinterpret_cast<uint32_t*>(out)[i] = stage[i];
+            if (tid == 0) { block_sizes[b] = total_units; block_bytes[b] = (uint64_t)total_units / 8 + 1; }
+        }
+        __syncthreads();   // smem is reused by the next block
+    }
+}
+
+}  // namespace
+
+bool lz77_v2_supported(uint64_t bs) { return bs <= MAXB; }
+
+// scratch slots: 13 = lists, 14 = tok
+int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
+                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(lz77_v2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(lz77_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_done = true;
+    }
+    uint64_t grid = (uint64_t)ctx->sm_count;
+    if (grid > nblocks) grid = nblocks;
+    uint32_t *lists, *tok;
+    B200_TRY(b200_scratch(ctx, 13, (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&lists)));
+    B200_TRY(b200_scratch(ctx, 14, (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&tok)));
+    if (variant == 0)
+        lz77_v2_kernel<0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, lists, tok, scratch, stride, d_block_sizes, block_bytes, dbg_tok);
+    else
+        lz77_v2_kernel<1><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, lists, tok, scratch, stride, d_block_sizes, block_bytes, dbg_tok);
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}

@@ -208,6 +208,22 @@ def lz77_encode(ctx, data, variant=LZ_DEFLATE, block_size=DEFAULT_BLOCK, stream=
     return st
 
 
+def lz77_encode_debug(ctx, data, variant, block_size):
+    """Test hook: (stream, tok) where tok[b, p] is the match finder's candidate for position p
+    of block b (0 = literal, else offset | len << 16). Blocks must be <= 65536 bytes."""
+    _check_u8(data)
+    n = data.numel()
+    st = lz77_alloc(ctx, n, block_size, variant)
+    nblocks = st.block_sizes.numel()
+    tok = torch.zeros(nblocks * 65536, dtype=torch.int32, device=ctx.device)
+    tb = C.c_uint64(0)
+    _lib.check(_lib.core().b200_lz77_encode_debug_dev(
+        ctx.handle, variant, _ptr(data), n, block_size, _ptr(st.out), st.out.numel(), _ptr(st.block_sizes), _ptr(st.block_off),
+        C.byref(tb), _ptr(tok)))
+    st.total_bytes = tb.value
+    return st, tok.view(nblocks, 65536)
+
+
 def lz77_decode(ctx, st, out=None):
     if out is None:
         out = torch.empty(st.n, dtype=torch.uint8, device=ctx.device)

@@ -131,6 +131,12 @@ uint64_t b200_lz77_block_stride(uint64_t block_size);
 int b200_lz77_encode_dev(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t block_size,
                          uint8_t* d_out, uint64_t out_capacity,
                          uint64_t* d_block_sizes, uint64_t* d_block_off, uint64_t* h_total_bytes);
+/* Test hook: as b200_lz77_encode_dev, additionally dumping the match finder's per-position
+ * token candidates (0 = literal, else offset | len << 16), 65536 entries per block.
+ * Blocks must be <= 65536 bytes (the shared-memory path). */
+int b200_lz77_encode_debug_dev(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                               uint8_t* d_out, uint64_t out_capacity, uint64_t* d_block_sizes, uint64_t* d_block_off,
+                               uint64_t* h_total_bytes, uint32_t* d_tok);
 int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d_stream,
                          const uint64_t* d_block_off, const uint64_t* d_block_sizes,
                          uint64_t n, uint64_t block_size, uint8_t* d_out);

@@ -156,3 +156,36 @@ def test_full_size_roundtrip(ctx):
         assert int(off[-1].item()) == st.total_bytes
         dec = dv.lz77_decode(ctx, st)
         assert torch.equal(dec, data)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_hbm_table_path_still_exact(ctx, ob, variant, monkeypatch):
+    """blocks <= 64 KiB normally take the shared-memory match finder; force the HBM-table
+    kernel (the path used for larger blocks) on the same input"""
+    monkeypatch.setenv("B200_LZ_FORCE_V1", "1")
+    _encode_check(ctx, ob, _corpus(300_000, 0, 21), variant, 65536)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_match_finder_candidates(ctx, ob, variant):
+    """token candidates of the shared-memory match finder at every token start == the
+    reference's find() result + extension (via the oracle port's recorded find results)"""
+    from compression_algorithms_b200 import device as dv
+    data = _corpus(140_000, 0, 23)
+    st, tok = dv.lz77_encode_debug(ctx, _to_dev(ctx, data), variant, 65536)
+    tok = tok.cpu().numpy().view(np.uint32)
+    W, MAXLEN = (32768, 31) if variant else (16384, 15)
+    for b in range(3):
+        blk = data[b * 65536: (b + 1) * 65536]
+        F = (ob.port_deflate_lz77_compress(blk, want_F=True)[1] if variant else ob.port_lz77_compress(blk, want_F=True)[2])
+        pad = np.concatenate([blk, np.zeros(64, dtype=np.uint8)])
+        for p in np.nonzero(F != 0xFFFFFFFE)[0]:
+            m = int(F[p])
+            rej = m == 0xFFFFFFFF or ((p - m >= W - 1) if variant else (p - m == W))
+            want = 0
+            if not rej:
+                l = 4
+                while l < MAXLEN and pad[m + l] == pad[p + l]:
+                    l += 1
+                want = (p - m) | (l << 16)
+            assert int(tok[b, p]) == want, "block %d position %d" % (b, p)
