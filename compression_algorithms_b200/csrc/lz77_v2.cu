@@ -85,6 +85,20 @@ __device__ __forceinline__ uint32_t sm_word(const uint8_t* data, uint32_t p) {
     return __funnelshift_r(a[0], a[1], (p & 3u) * 8);
 }
 
+// length of the common prefix of data[m..] and data[q..], at least 4 (the hashed word), capped
+// at MAXLEN: compares 4 bytes per step (lz77.c:302-311, deflate/lz77.c:238-247)
+template <uint32_t MAXLEN>
+__device__ __forceinline__ uint32_t match_len(const uint8_t* data, uint32_t m, uint32_t q) {
+    uint32_t l = 4;
+#pragma unroll 1
+    while (l < MAXLEN) {
+        const uint32_t x = sm_word(data, m + l) ^ sm_word(data, q + l);
+        if (x) { l += (uint32_t)(__ffs(x) - 1) >> 3; break; }
+        l += 4;
+    }
+    return l < MAXLEN ? l : MAXLEN;
+}
+
 __device__ __forceinline__ uint32_t bm_rank(const uint32_t* bm, const uint32_t* pre, uint32_t s) {
     const uint32_t wi = s >> 5;
     uint32_t r = pre[wi / PRE_CHUNK];
@@ -116,7 +130,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
     uint32_t* lists = lists_all + (uint64_t)blockIdx.x * MAXB;
     uint32_t* tokb = tok_all + (uint64_t)blockIdx.x * MAXB;
 
+    uint32_t* dbg_stats = dbg_tok ? dbg_tok + (uint64_t)nblocks * MAXB : nullptr;   // [block][8 phase stamps + 32 warps x 4]
     for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const long long t_begin = clock64();
+#define PHASE_STAMP(k) do { if (dbg_stats && tid == 0) dbg_stats[(uint64_t)b * 136 + (k)] = (uint32_t)(clock64() - t_begin); } while (0)
         const uint8_t* src = in + (uint64_t)b * bs;
         const uint32_t len = (uint32_t)(n - (uint64_t)b * bs < bs ? n - (uint64_t)b * bs : bs);
 
@@ -131,6 +148,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         }
         __syncthreads();
 
+        PHASE_STAMP(0);
         // ---------------- P1: no-expiry occupancy (order independent) by atomic linear probing
         for (uint32_t i = tid; i < len; i += NTHREADS) {
             uint32_t s = lz_hash(sm_word(data, i));
@@ -148,6 +166,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         }
         __syncthreads();
 
+        PHASE_STAMP(1);
         // ---------------- P2: rank prefix per 8-word chunk, range cuts, special cluster bounds
         {
             // thread t owns chunks [5t, 5t+5)
@@ -204,6 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         for (uint32_t i = tid; i < NR * NR; i += NTHREADS) (&ms->cnt[0][0])[i] = 0;
         __syncthreads();
 
+        PHASE_STAMP(2);
         // ---------------- P3: compact index + stable partition by range into per-range lists
         const uint32_t slice = ((len + NTHREADS - 1) / NTHREADS) * 32;   // positions per warp (multiple of 32)
         const uint32_t p_lo = warp * slice, p_hi = (p_lo + slice < len) ? p_lo + slice : len;
@@ -264,13 +284,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         }
         __syncthreads();
 
+        PHASE_STAMP(3);
         // ---------------- P4: table simulation. T[k] = position+1 of the entry in compact slot k, 0 = never used
         for (uint32_t i = tid; i < (T_ENTRIES + 2052) / 2 + 2; i += NTHREADS) reinterpret_cast<uint32_t*>(big)[i] = 0;   // T and B1
+        uint32_t* S1 = pre;   // rank prefix is dead: per-group pattern-signature filter, u32[2052]
+        for (uint32_t i = tid; i < 2052; i += NTHREADS) S1[i] = 0;
         __syncthreads();
         {
             const uint32_t sp_lo_end = ms->sp_lo_end, sp_hi_start = ms->sp_hi_start;
             uint32_t cur = ms->rstart[warp];
             const uint32_t end = ms->rstart[warp + 1];
+            const long long t_p4 = clock64();
+            uint32_t st_rounds = 0, st_coop = 0, st_entries = end - cur, st_iters = 0;
+            long long tq = 0, tc = 0, tm = 0, tl = 0, t_mark;
             uint32_t qh = 0, qt = 0;                       // slot-0 clear queue (only warp 0 ever uses it)
             if (warp == 0) { if (lane == 0) ms->clr[0] = W - 1; qt = 1; }
             __syncwarp();
@@ -308,11 +334,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                         // token candidate
                         uint32_t tk = 0;
                         const bool reject = (m == NONE) || (V ? (q0 - m >= W - 1) : (q0 - m == W));
-                        if (!reject) {
-                            uint32_t l = 4;
-                            while (l < MAXLEN && data[m + l] == data[q0 + l]) ++l;
-                            tk = (q0 - m) | (l << 16);
-                        }
+                        if (!reject) tk = (q0 - m) | (match_len<MAXLEN>(data, m, q0) << 16);
                         tokb[q0] = tk;
                     }
                     qh = __shfl_sync(0xffffffffu, qh, 0); qt = __shfl_sync(0xffffffffu, qt, 0);
@@ -324,47 +346,107 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 bool done = lane >= L;
                 const uint32_t dthr = q > W ? q - W : 0;
                 const uint32_t w = done ? 0u : sm_word(data, q);
+                const uint32_t sig = (w * 0x9E3779B1u) >> 27;   // 5-bit pattern signature for the per-group filter
                 uint32_t fm = NONE; bool pend = true;
-                uint32_t gstart = (kk & 31) == 0 ? kk : NONE, gmin = 0xFFFFu;
                 while (__ballot_sync(0xffffffffu, !done)) {
+                    ++st_rounds;
+                    t_mark = clock64();
+                    // advance every cursor to the first slot that is dead at the lane's time.
+                    // (a) a few private steps: most walks are 1-3 slots long
+                    bool need = false;
                     if (!done) {
-                        // advance the cursor to the first slot that is dead at time q
-                        for (;;) {
-                            if (!pend && (kk & 31) == 0 && B1[kk >> 5] > dthr) { kk += 32; gstart = kk; continue; }
+                        need = true;
+#pragma unroll 1
+                        for (int it = 0; it < 6; ++it) {
                             const uint32_t v = T[kk];
-                            if (v <= dthr) break;
+                            if (v <= dthr) { need = false; break; }
                             if (pend && sm_word(data, v - 1) == w) { fm = v - 1; pend = false; }
-                            if ((kk & 31) == 0) { gmin = v; gstart = kk; } else if (v < gmin) gmin = v;
-                            if ((kk & 31) == 31 && gstart == (kk & ~31u)) B1[kk >> 5] = (uint16_t)gmin;   // full group seen live: lower bound
                             ++kk;
                         }
                     }
+                    // (b) long walks (hot chains): the whole warp serves one lane at a time, 32 slots
+                    //     or 32 groups per step, skipping groups the bound/signature tables prove irrelevant
+                    uint32_t needmask = __ballot_sync(0xffffffffu, need);
+                    tq += clock64() - t_mark; t_mark = clock64();
+                    while (needmask) {
+                        const int j = __ffs(needmask) - 1;
+                        needmask &= needmask - 1;
+                        ++st_coop;
+                        uint32_t ckk = __shfl_sync(0xffffffffu, kk, j);
+                        const uint32_t cd = __shfl_sync(0xffffffffu, dthr, j);
+                        const uint32_t cw = __shfl_sync(0xffffffffu, w, j);
+                        const uint32_t csig = __shfl_sync(0xffffffffu, sig, j);
+                        bool cpend = __shfl_sync(0xffffffffu, (int)pend, j) != 0;
+                        uint32_t cfm = NONE;
+                        for (;;) {
+                            ++st_iters;
+                            if ((ckk & 31) == 0) {
+                                const uint32_t g = (ckk >> 5) + lane;
+                                const bool ok = g < 2050u && B1[g] > cd && (!cpend || !((S1[g] >> csig) & 1u));
+                                const uint32_t stop = __ballot_sync(0xffffffffu, !ok);
+                                const uint32_t nskip = stop ? (uint32_t)(__ffs(stop) - 1) : 32u;
+                                ckk += 32u * nskip;
+                                if (nskip == 32u) continue;
+                            }
+                            const uint32_t lim = 32u - (ckk & 31u);
+                            const bool inwin = lane < lim;
+                            const uint32_t v = inwin ? (uint32_t)T[ckk + lane] : 0xFFFFFFFFu;
+                            const bool live = v > cd;
+                            const bool mt = inwin && live && cpend && sm_word(data, v - 1) == cw;
+                            const uint32_t dm = __ballot_sync(0xffffffffu, !live);
+                            const uint32_t mm = __ballot_sync(0xffffffffu, mt);
+                            const uint32_t fd = dm ? (uint32_t)(__ffs(dm) - 1) : 32u;
+                            if (mm) {
+                                const uint32_t fx = (uint32_t)(__ffs(mm) - 1);
+                                const uint32_t mv = __shfl_sync(0xffffffffu, v, fx);
+                                if (fx < fd) { cfm = mv - 1; cpend = false; }
+                            }
+                            if (dm) { ckk += fd; break; }
+                            if (lim == 32u) {   // a whole aligned group is live: publish its minimum key as the group's lower bound
+                                const uint32_t mn = __reduce_min_sync(0xffffffffu, v);
+                                if (lane == 0) B1[ckk >> 5] = (uint16_t)mn;
+                            }
+                            ckk += lim;
+                        }
+                        if ((int)lane == j) { kk = ckk; if (pend && !cpend) { fm = cfm; pend = false; } }
+                    }
                     __syncwarp();
+                    tc += clock64() - t_mark; t_mark = clock64();
                     const uint32_t key = done ? (0x80000000u | lane) : kk;
                     const uint32_t peers = __match_any_sync(0xffffffffu, key);
-                    const bool conflict = !done && (peers & lt_mask) != 0;
-                    const uint32_t cmask = __ballot_sync(0xffffffffu, conflict);
+                    const bool blocked = !done && (peers & lt_mask) != 0;
+                    const uint32_t cmask = __ballot_sync(0xffffffffu, blocked);
                     const uint32_t firstc = cmask ? (uint32_t)(__ffs(cmask) - 1) : 32u;
                     if (!done && lane < firstc) {
                         if (q != 65535u) T[kk] = (uint16_t)(q + 1);      // position 65535 is never looked up again
-                        uint32_t tk = 0;
-                        const uint32_t m = fm;
-                        const bool reject = (m == NONE) || (V ? (q - m >= W - 1) : (q - m == W));
-                        if (!reject) {
-                            uint32_t l = 4;
-                            while (l < MAXLEN && data[m + l] == data[q + l]) ++l;
-                            tk = (q - m) | (l << 16);
-                        }
-                        tokb[q] = tk;
+                        atomicOr(&S1[kk >> 5], 1u << sig);
                         done = true;
                     }
                     __syncwarp();
+                    tm += clock64() - t_mark;
                 }
+                t_mark = clock64();
+                // token candidates of the whole batch at once (outside the commit rounds)
+                if (lane < L) {
+                    uint32_t tk = 0;
+                    const uint32_t m = fm;
+                    const bool reject = (m == NONE) || (V ? (q - m >= W - 1) : (q - m == W));
+                    if (!reject) tk = (q - m) | (match_len<MAXLEN>(data, m, q) << 16);
+                    tokb[q] = tk;
+                }
+                tl += clock64() - t_mark;
                 cur += L;
+            }
+            if (dbg_stats && lane == 0) {
+                uint32_t* o = dbg_stats + (uint64_t)b * 136 + 8 + warp * 4;
+                o[0] = (uint32_t)(clock64() - t_p4); o[1] = st_entries | (st_iters << 16); o[2] = st_rounds | ((uint32_t)(tq >> 10) << 16); o[3] = st_coop | ((uint32_t)(tc >> 10) << 16);
+                if (warp < 8) dbg_stats[(uint64_t)b * 136 + 7] = 0;
+                atomicMax(&dbg_stats[(uint64_t)b * 136 + 7], ((uint32_t)(tm >> 10) << 16) | (uint32_t)(tl >> 10));
             }
         }
         __syncthreads();
 
+        PHASE_STAMP(4);
         // ---------------- P5: greedy parse. adv[p] = bytes consumed by the token that would start at p
         for (uint32_t i = tid; i < len; i += NTHREADS) {
             const uint32_t t = tokb[i];
@@ -436,6 +518,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         const uint32_t total_units = ms->scan[32];
         uint8_t* out = scratch + (uint64_t)b * stride;
 
+        PHASE_STAMP(5);
         // ---------------- P6: emission
         if (V == 1) {
             if (tid < nchunks) {
@@ -485,6 +568,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             if (tid == 0) { block_sizes[b] = total_units; block_bytes[b] = (uint64_t)total_units / 8 + 1; }
         }
         __syncthreads();   // smem is reused by the next block
+        PHASE_STAMP(6);
     }
 }
 

@@ -215,13 +215,14 @@ def lz77_encode_debug(ctx, data, variant, block_size):
     n = data.numel()
     st = lz77_alloc(ctx, n, block_size, variant)
     nblocks = st.block_sizes.numel()
-    tok = torch.zeros(nblocks * 65536, dtype=torch.int32, device=ctx.device)
+    tok = torch.zeros(nblocks * 65536 + nblocks * 136, dtype=torch.int32, device=ctx.device)
     tb = C.c_uint64(0)
     _lib.check(_lib.core().b200_lz77_encode_debug_dev(
         ctx.handle, variant, _ptr(data), n, block_size, _ptr(st.out), st.out.numel(), _ptr(st.block_sizes), _ptr(st.block_off),
         C.byref(tb), _ptr(tok)))
     st.total_bytes = tb.value
-    return st, tok.view(nblocks, 65536)
+    st.debug_stats = tok[nblocks * 65536:].view(nblocks, 136)   # 8 phase stamps + 32 warps x (cycles, entries, rounds, coop)
+    return st, tok[: nblocks * 65536].view(nblocks, 65536)
 
 
 def lz77_decode(ctx, st, out=None):
