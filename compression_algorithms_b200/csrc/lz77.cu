@@ -236,90 +236,80 @@ __global__ void __launch_bounds__(256) lz77_gather_kernel(const uint8_t* __restr
     if (threadIdx.x < cnt - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
 }
 
-// ------------------------------------------------------------------ decoders (v1)
-// One warp per block. The last 64 KiB of output live in a shared-memory ring
-// (offsets are < 32768), flushed to HBM in 16 KiB coalesced pieces. All lanes
-// parse the token stream redundantly; copies are done one byte per lane, with
+// ------------------------------------------------------------------ decoders
+// One warp per block, 4 warps per CTA, no shared memory: up to 64 blocks in flight per
+// SM hide the latency of the one dependent read per match. The token stream is held in
+// a 2048-bit register window (two u32 per lane, the second prefetched); runs of up to 32
+// literal tokens are recognised with one ballot (token k of a run sits at a fixed stride)
+// and stored with one coalesced byte store; a match is copied one byte per lane, with
 // overlapping matches (offset < length) resolved by the period rule
-// out[o+k] = out[o - off + k % off].
-constexpr uint32_t RING = 65536, FLUSH = 16384;
-
-__device__ __forceinline__ void ring_flush(const uint8_t* ring, uint8_t* gout, uint32_t from, uint32_t to, unsigned lane) {
-    // [from, to) with from % FLUSH == 0; to may be ragged at the end of the block
-    const uint32_t full = (to - from) / 16;
-    for (uint32_t i = lane; i < full; i += 32) {
-        const uint4 v = *reinterpret_cast<const uint4*>(ring + ((from + i * 16) & (RING - 1)));
-        uint8_t* g = gout + from + i * 16;
-        if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) *reinterpret_cast<uint4*>(g) = v;
-        else { const uint8_t* pv = reinterpret_cast<const uint8_t*>(&v); for (int k = 0; k < 16; ++k) g[k] = pv[k]; }
-    }
-    for (uint32_t i = from + full * 16 + lane; i < to; i += 32) gout[i] = ring[i & (RING - 1)];
-}
-
+// out[o+k] = out[o - off + k % off]. Source bytes are read with ld.cg because they
+// were written by other lanes of the same warp.
 template <int V>
-__global__ void __launch_bounds__(32) lz77_decode_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ block_off,
-                                                        const uint64_t* __restrict__ block_sizes, uint64_t n, uint64_t bs,
-                                                        uint8_t* __restrict__ out) {
-    extern __shared__ __align__(16) uint8_t ring[];
-    const unsigned lane = threadIdx.x;
-    const uint64_t b = blockIdx.x;
+__global__ void __launch_bounds__(128) lz77_decode_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ block_off,
+                                                         const uint64_t* __restrict__ block_sizes, uint64_t n, uint64_t bs,
+                                                         uint64_t nblocks, uint8_t* __restrict__ out) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t b = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= nblocks) return;
     const uint32_t len = (uint32_t)(n - b * bs < bs ? n - b * bs : bs);
     const uint8_t* tk = stream + block_off[b];
     uint8_t* gout = out + b * bs;
-    uint32_t o = 0, flushed = 0;
-    if (V == 0) {
-        // LSB-first bit tokens: 0 + 8-bit literal | 1 + 14-bit offset + 4-bit length (lz77.c:358-372)
-        uint64_t win = 0; uint32_t avail = 0; uint64_t rp = 0;
-        const uint64_t nbytes = block_sizes[b] / 8 + 1;
-        while (o < len) {
-            while (avail <= 56) { const uint64_t by = rp < nbytes ? (uint64_t)__ldg(tk + rp) : 0; ++rp; win |= by << avail; avail += 8; }
-            if (win & 1) {
-                const uint32_t off = (uint32_t)(win >> 1) & 0x3FFF, ml = (uint32_t)(win >> 15) & 0xF;
-                win >>= 19; avail -= 19;
-                if (lane < ml) {
-                    const uint32_t src = off ? o - off + (lane % off) : o;
-                    ring[(o + lane) & (RING - 1)] = ring[src & (RING - 1)];
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(tk) & 3);
+    const uint32_t* wbase = reinterpret_cast<const uint32_t*>(tk - mis);
+    const uint64_t total_bits = (uint64_t)mis * 8 + (V ? block_sizes[b] * 8 : block_sizes[b]);
+    const uint32_t nwords = (uint32_t)((total_bits + 31) >> 5);
+    constexpr uint32_t STRIDE = V ? 16 : 9, MATCH_BITS = V ? 32 : 19;
+    uint32_t wo = 0;                       // word offset of the window start
+    uint32_t t = mis * 8;                  // bit cursor relative to the window start
+    uint64_t tend = total_bits;            // end of the stream relative to the window start
+    uint32_t cur = lane < nwords ? __ldg(wbase + lane) : 0u;
+    uint32_t nxt = 32 + lane < nwords ? __ldg(wbase + 32 + lane) : 0u;
+    uint32_t o = 0;
+
+    // value of `nb` <= 32 bits at window bit position p (may differ per lane)
+    auto extract = [&](uint32_t p, uint32_t nb) -> uint32_t {
+        const uint32_t i0 = p >> 5, i1 = i0 + 1;
+        const uint32_t a0 = __shfl_sync(0xffffffffu, cur, i0 & 31), a1 = __shfl_sync(0xffffffffu, nxt, i0 & 31);
+        const uint32_t b0 = __shfl_sync(0xffffffffu, cur, i1 & 31), b1 = __shfl_sync(0xffffffffu, nxt, i1 & 31);
+        const uint32_t lo = i0 < 32 ? a0 : a1, hi = i1 < 32 ? b0 : (i1 < 64 ? b1 : 0u);
+        const uint32_t v = __funnelshift_r(lo, hi, p & 31);
+        return nb >= 32 ? v : (v & ((1u << nb) - 1u));
+    };
+
+    for (;;) {
+        if (V ? (t >= tend) : (o >= len)) break;
+        // ---- a run of literal tokens
+        const uint32_t p = t + STRIDE * lane;
+        const uint32_t v = extract(p, STRIDE);
+        const bool lit = (uint64_t)p + STRIDE <= tend && (V ? (v & 0xFFu) == 0u : ((v & 1u) == 0u && o + lane < len));
+        const unsigned stop = __ballot_sync(0xffffffffu, !lit);
+        const uint32_t run = stop ? (uint32_t)(__ffs(stop) - 1) : 32u;
+        if (lane < run && o + lane < len) gout[o + lane] = (uint8_t)(V ? (v >> 8) : (v >> 1));
+        o += run; t += run * STRIDE;
+        // ---- then at most one match token
+        if (run < 32 && (V ? (t < tend) : (o < len))) {
+            const uint32_t mv = extract(t, MATCH_BITS);
+            const bool is_match = V ? ((mv & 0xFFu) != 0u) : ((mv & 1u) != 0u);
+            if (is_match) {
+                const uint32_t off = V ? ((mv >> 8) & 0xFFFFu) : ((mv >> 1) & 0x3FFFu);
+                const uint32_t ml = V ? (mv >> 24) : ((mv >> 15) & 0xFu);
+                __syncwarp();
+                if (lane < ml && off != 0 && off <= o && o + lane < len) {
+                    const uint8_t c = __ldcg(gout + (o - off + (lane % off)));
+                    gout[o + lane] = c;
                 }
-                o += ml;
-                if (ml == 0 && off == 0) break;  // corrupt stream guard: no progress
-            } else {
-                if (lane == 0) ring[o & (RING - 1)] = (uint8_t)(win >> 1);
-                win >>= 9; avail -= 9;
-                ++o;
+                o += ml; t += MATCH_BITS;
+                if (ml == 0 && !V) break;   // corrupt stream: no progress possible
             }
-            __syncwarp();
-            while (o >= flushed + FLUSH + 64) { ring_flush(ring, gout, flushed, flushed + FLUSH, lane); flushed += FLUSH; }
         }
-    } else {
-        // byte tokens: 00 cc | 01 dist_lo dist_hi len (deflate/lz77.c:176-197)
-        const uint64_t ntok = block_sizes[b];
-        uint64_t i = 0;
-        while (i < ntok) {
-            const uint32_t flag = __ldg(tk + i);
-            if (flag == 0) {
-                // batch a run of literals: lane k looks at the token 2k bytes ahead
-                const uint64_t at = i + 2 * (uint64_t)lane;
-                const bool lit = at < ntok && __ldg(tk + at) == 0;
-                const unsigned mask = __ballot_sync(0xffffffffu, !lit);
-                const uint32_t run = mask ? (uint32_t)(__ffs(mask) - 1) : 32u;
-                if (lane < run) ring[(o + lane) & (RING - 1)] = __ldg(tk + at + 1);
-                o += run; i += 2 * (uint64_t)run;
-            } else {
-                const uint32_t off = (uint32_t)__ldg(tk + i + 1) | ((uint32_t)__ldg(tk + i + 2) << 8);
-                const uint32_t ml = __ldg(tk + i + 3);
-                if (lane < ml) {
-                    const uint32_t src = off ? o - off + (lane % off) : o;
-                    ring[(o + lane) & (RING - 1)] = ring[src & (RING - 1)];
-                }
-                o += ml; i += 4;
-            }
-            __syncwarp();
-            while (o >= flushed + FLUSH + 64) { ring_flush(ring, gout, flushed, flushed + FLUSH, lane); flushed += FLUSH; }
+        __syncwarp();
+        if (t >= 1024) {                    // first window register consumed: slide by 32 words
+            wo += 32; t -= 1024; tend -= 1024;
+            cur = nxt;
+            nxt = wo + 32 + lane < nwords ? __ldg(wbase + wo + 32 + lane) : 0u;
         }
     }
-    __syncwarp();
-    const uint32_t end = o < len ? o : len;   // a final match may overshoot the block (U1)
-    if (end > flushed) ring_flush(ring, gout, flushed, end, lane);
 }
 
 inline uint64_t round16(uint64_t x) { return (x + 15) & ~(uint64_t)15; }
@@ -424,15 +414,10 @@ extern "C" int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d
     if (n == 0) return B200_OK;
     const uint64_t bs = (block_size == 0 || block_size > n) ? n : block_size;
     const uint64_t nblocks = (n + bs - 1) / bs;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[variant]) {
-        if (variant == 0) CUDA_TRY(cudaFuncSetAttribute(lz77_decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RING));
-        else CUDA_TRY(cudaFuncSetAttribute(lz77_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RING));
-        attr_done[variant] = true;
-    }
+    const unsigned grid = (unsigned)((nblocks + 3) / 4);
     B200_TIMED_BEGIN(ctx, B200_K_LZ_DECODE);
-    if (variant == 0) lz77_decode_kernel<0><<<(unsigned)nblocks, 32, RING, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, d_out);
-    else lz77_decode_kernel<1><<<(unsigned)nblocks, 32, RING, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, d_out);
+    if (variant == 0) lz77_decode_kernel<0><<<grid, 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
+    else lz77_decode_kernel<1><<<grid, 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
     B200_TIMED_END(ctx);
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
