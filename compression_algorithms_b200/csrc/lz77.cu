@@ -41,8 +41,18 @@ __device__ __forceinline__ uint32_t word_at(const uint8_t* __restrict__ d, uint3
     return byte_at(d, len, p) | (byte_at(d, len, p + 1) << 8) | (byte_at(d, len, p + 2) << 16) | (byte_at(d, len, p + 3) << 24);
 }
 
+// slot tag: blocks up to 4 MiB carry an epoch (no clearing between blocks); larger blocks
+// (whole-buffer calls of the standalone codec) use tag = index + 1 on a table that the host
+// clears before the launch, one block per warp
+template <bool BIG> __device__ __forceinline__ bool tag_live(uint32_t tag, uint32_t epoch, uint32_t W, uint32_t p) {
+    if (BIG) return tag != 0u && (uint64_t)(tag - 1u) + W >= p;
+    return (tag >> IDX_BITS) == epoch && (tag & IDX_MASK) + W >= p;
+}
+template <bool BIG> __device__ __forceinline__ uint32_t tag_index(uint32_t tag) { return BIG ? tag - 1u : (tag & IDX_MASK); }
+template <bool BIG> __device__ __forceinline__ uint32_t tag_make(uint32_t epoch, uint32_t q) { return BIG ? q + 1u : ((epoch << IDX_BITS) | q); }
+
 // ------------------------------------------------------------------ parse (v1)
-template <int V>
+template <int V, bool BIG>
 __global__ void __launch_bounds__(128) lz77_parse_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t bs, uint64_t nblocks,
                                                         uint2* __restrict__ tables, uint32_t* __restrict__ clrq, uint32_t epoch0,
                                                         uint8_t* __restrict__ scratch, uint64_t stride,
@@ -85,12 +95,12 @@ __global__ void __launch_bounds__(128) lz77_parse_kernel(const uint8_t* __restri
             bool stop_dead = false;
             for (;;) {
                 const uint2 e = __ldcg(&T[s + lane]);
-                const bool live = (e.y >> IDX_BITS) == epoch && (e.y & IDX_MASK) + W >= p;
+                const bool live = tag_live<BIG>(e.y, epoch, W, p);
                 const bool stop = !live || e.x == pat;
                 const unsigned mask = __ballot_sync(0xffffffffu, stop);
                 if (mask) {
                     const int k = __ffs(mask) - 1;
-                    const uint32_t idx = __shfl_sync(0xffffffffu, e.y & IDX_MASK, k);
+                    const uint32_t idx = __shfl_sync(0xffffffffu, tag_index<BIG>(e.y), k);
                     const bool lv = __shfl_sync(0xffffffffu, (int)live, k) != 0;
                     m = lv ? idx : NONE;
                     stop_slot = s + k; stop_dead = !lv;
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(128) lz77_parse_kernel(const uint8_t* __restri
                 while (!have) {
                     const uint32_t at = V ? ((t + lane) & (TABLE_SLOTS - 1)) : (t + lane);  // deflate insert wraps (deflate/lz77.c:99-101)
                     const uint2 e = __ldcg(&T[at]);
-                    const bool live = (e.y >> IDX_BITS) == epoch && (e.y & IDX_MASK) + W >= q;
+                    const bool live = tag_live<BIG>(e.y, epoch, W, q);
                     const unsigned mask = __ballot_sync(0xffffffffu, !live);
                     if (mask) {
                         const uint32_t k = (uint32_t)(__ffs(mask) - 1);
@@ -149,7 +159,7 @@ __global__ void __launch_bounds__(128) lz77_parse_kernel(const uint8_t* __restri
                     }
                     t += 32;
                 }
-                if (lane == 0) __stcg(&T[slot], make_uint2(pq, (epoch << IDX_BITS) | q));
+                if (lane == 0) __stcg(&T[slot], make_uint2(pq, tag_make<BIG>(epoch, q)));
                 if (slot == 0) {
                     if (qt - qh < CLRQ) { if (lane == 0) Q[qt % CLRQ] = q + W; }
                     else if (lane == 0) atomicOr(err, 2u);
@@ -333,7 +343,8 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
         return B200_OK;
     }
     const uint64_t bs = (block_size == 0 || block_size > n) ? n : block_size;
-    if (bs > MAX_BLOCK) { B200_SET_ERR("lz77: block of %llu bytes exceeds the %llu-byte limit of this build", (unsigned long long)bs, (unsigned long long)MAX_BLOCK); return B200_ERR_ARG; }
+    if (bs >= 0xFFFFFFF0ull) { B200_SET_ERR("lz77: block of %llu bytes exceeds the 4 GiB limit", (unsigned long long)bs); return B200_ERR_ARG; }
+    const bool big = bs > MAX_BLOCK;   // index does not fit the epoch tag: clear the table, one block per warp per launch
     const uint64_t nblocks = (n + bs - 1) / bs;
     const uint64_t stride = b200_lz77_block_stride(bs);
 
@@ -357,6 +368,7 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
         uint64_t nwarps = (uint64_t)ctx->sm_count * wps;
         if (nwarps > nblocks) nwarps = nblocks;
         nwarps = (nwarps + 3) / 4 * 4;  // 4 warps per CTA
+        if (big && nwarps > 256) nwarps = 256;
         const uint64_t per_warp = (nblocks + nwarps - 1) / nwarps;
         const size_t table_bytes = (size_t)nwarps * (TABLE_SLOTS + GUARD) * sizeof(uint2);
         uint2* tables; uint32_t* clrq;
@@ -364,18 +376,35 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
         B200_TRY(b200_scratch(ctx, 1, table_bytes, reinterpret_cast<void**>(&tables)));
         B200_TRY(b200_scratch(ctx, 2, (size_t)nwarps * CLRQ * 4, reinterpret_cast<void**>(&clrq)));
         uint32_t& ep = ctx->lz_epoch;
-        if (fresh || ep + per_warp > MAX_EPOCH) {
-            CUDA_TRY(cudaMemsetAsync(tables, 0, ctx->cap[1], ctx->stream));
-            ep = 0;
-        }
         const unsigned grid = (unsigned)(nwarps / 4);
-        B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
-        if (variant == 0)
-            lz77_parse_kernel<0><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
-        else
-            lz77_parse_kernel<1><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
-        B200_TIMED_END(ctx);
-        ep += (uint32_t)per_warp;
+        if (big) {
+            // waves of nwarps blocks; the epoch tags of earlier calls are wiped, so restart them
+            B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
+            for (uint64_t first = 0; first < nblocks; first += nwarps) {
+                const uint64_t cnt = nblocks - first < nwarps ? nblocks - first : nwarps;
+                CUDA_TRY(cudaMemsetAsync(tables, 0, table_bytes, ctx->stream));
+                const uint64_t n_here = (first + cnt) * bs < n ? cnt * bs : n - first * bs;
+                if (variant == 0)
+                    lz77_parse_kernel<0, true><<<grid, 128, 0, ctx->stream>>>(d_in + first * bs, n_here, bs, cnt, tables, clrq, 0, scratch + first * stride, stride, d_block_sizes + first, block_bytes + first, err);
+                else
+                    lz77_parse_kernel<1, true><<<grid, 128, 0, ctx->stream>>>(d_in + first * bs, n_here, bs, cnt, tables, clrq, 0, scratch + first * stride, stride, d_block_sizes + first, block_bytes + first, err);
+                ctx->launches += 1;
+            }
+            B200_TIMED_END(ctx);
+            ep = MAX_EPOCH;   // forces a clear before the next epoch-tagged call
+        } else {
+            if (fresh || ep + per_warp > MAX_EPOCH) {
+                CUDA_TRY(cudaMemsetAsync(tables, 0, ctx->cap[1], ctx->stream));
+                ep = 0;
+            }
+            B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
+            if (variant == 0)
+                lz77_parse_kernel<0, false><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
+            else
+                lz77_parse_kernel<1, false><<<grid, 128, 0, ctx->stream>>>(d_in, n, bs, nblocks, tables, clrq, ep, scratch, stride, d_block_sizes, block_bytes, err);
+            B200_TIMED_END(ctx);
+            ep += (uint32_t)per_warp;
+        }
     }
     lz77_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(block_bytes, nblocks, d_block_off, out_capacity, info);
     const uint32_t pieces = (uint32_t)((stride + 32767) / 32768);
