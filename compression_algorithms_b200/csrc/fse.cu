@@ -32,8 +32,9 @@ inline uint64_t seg_stride_words(uint64_t seg) { return seg / 8 + 2; }  // 8 bit
 
 // ------------------------------------------------------------ normalise + tables
 // One warp per block; lane l owns symbols 8l..8l+7.
-__global__ void __launch_bounds__(32) fse_tables_kernel(const uint32_t* __restrict__ freq, uint16_t* __restrict__ norm_out,
-                                                       uint32_t* __restrict__ tt_out) {
+// norm_in != NULL: the counts are already normalised (decoding a container), only the table is built.
+__global__ void __launch_bounds__(32) fse_tables_kernel(const uint32_t* __restrict__ freq, const uint16_t* __restrict__ norm_in,
+                                                       uint16_t* __restrict__ norm_out, uint32_t* __restrict__ tt_out) {
     __shared__ uint8_t  sym_at[TSIZE];
     __shared__ uint16_t next[256];
     const uint64_t b = blockIdx.x;
@@ -41,7 +42,10 @@ __global__ void __launch_bounds__(32) fse_tables_kernel(const uint32_t* __restri
     uint64_t f[8];
     uint64_t total = 0; uint32_t present = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { f[k] = freq[b * 256 + lane * 8 + k]; total += f[k]; present += f[k] != 0; }
+    for (int k = 0; k < 8; ++k) {
+        f[k] = norm_in ? (uint64_t)norm_in[b * 256 + lane * 8 + k] : (uint64_t)freq[b * 256 + lane * 8 + k];
+        total += f[k]; present += f[k] != 0;
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { total += __shfl_xor_sync(0xffffffffu, total, d); present += __shfl_xor_sync(0xffffffffu, present, d); }
     if (total == 0) {
@@ -71,8 +75,18 @@ __global__ void __launch_bounds__(32) fse_tables_kernel(const uint32_t* __restri
         const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, d), oi = __shfl_xor_sync(0xffffffffu, besti, d);
         if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
     }
-    const uint32_t remaining = TSIZE - sum;
+    uint32_t remaining = TSIZE - sum;
     uint32_t my_sum = lane_sum;
+    if (norm_in) {   // take the stored counts as they are (a corrupt table that does not sum to 256 decodes to garbage, not out of bounds)
+        my_sum = 0; remaining = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { nf[k] = (uint32_t)f[k]; my_sum += nf[k]; }
+        if (total != TSIZE) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { norm_out[b * 256 + lane * 8 + k] = 0; tt_out[b * 256 + lane * 8 + k] = 0; }
+            return;
+        }
+    }
     if (best > 0 && (besti >> 3) == lane) { nf[besti & 7] += remaining; my_sum += remaining; }
     // cumulative counts
     const uint32_t incl = warp_incl_scan_u32(my_sum);
@@ -295,7 +309,7 @@ static int fse_front(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t bl
     CUDA_TRY(cudaMemsetAsync(d_side, 0, L->off_norm, ctx->stream));  // info + histogram
     const uint32_t tpb = (uint32_t)((*bs + HIST_TILE - 1) / HIST_TILE);
     byte_hist_kernel<<<(unsigned)(L->nblocks * tpb), 256, 0, ctx->stream>>>(d_in, n, *bs, tpb, reinterpret_cast<uint32_t*>(d_side + L->off_freq));
-    fse_tables_kernel<<<(unsigned)L->nblocks, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_side + L->off_freq),
+    fse_tables_kernel<<<(unsigned)L->nblocks, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_side + L->off_freq), nullptr,
                                                                    reinterpret_cast<uint16_t*>(d_side + L->off_norm),
                                                                    reinterpret_cast<uint32_t*>(d_side + L->off_tt));
     ctx->launches += 2;
@@ -368,5 +382,49 @@ extern "C" int b200_fse_decode_dev(b200_ctx* ctx, const uint64_t* d_words, const
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         *h_bad_segments = pin[0];
     }
+    return B200_OK;
+}
+
+// Rebuild what the decoder needs from a container's stored tables: tt from the normalised
+// counts, seg_word from seg_bits. d_side holds norm and seg_bits already (layout L).
+extern "C" int b200_fse_rebuild_index_dev(b200_ctx* ctx, uint64_t n, uint64_t block_size, uint64_t seg_size,
+                                          uint8_t* d_side, uint64_t side_bytes) {
+    b200_fse_layout L;
+    B200_TRY(b200_fse_layout_for(n, block_size, seg_size, &L));
+    if (side_bytes < L.bytes) { B200_SET_ERR("fse: side buffer too small"); return B200_ERR_CAPACITY; }
+    uint64_t* info = reinterpret_cast<uint64_t*>(d_side);
+    fse_tables_kernel<<<(unsigned)L.nblocks, 32, 0, ctx->stream>>>(nullptr, reinterpret_cast<const uint16_t*>(d_side + L.off_norm),
+                                                                  reinterpret_cast<uint16_t*>(d_side + L.off_norm),
+                                                                  reinterpret_cast<uint32_t*>(d_side + L.off_tt));
+    fse_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_side + L.off_seg_bits), L.nsegs,
+                                                    reinterpret_cast<uint64_t*>(d_side + L.off_seg_word), ~0ull, info);
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+// normalizeFrequencyTable / buildTransitionTable on one table (main.zig:106-189): exactly one of
+// h_freq (raw counts -> normalise, then build) and h_norm_in (already normalised) is given.
+extern "C" int b200_fse_tables_host(b200_ctx* ctx, const uint32_t* h_freq, const uint16_t* h_norm_in,
+                                    uint16_t* h_norm_out, uint32_t* h_tt_out) {
+    if ((h_freq != nullptr) == (h_norm_in != nullptr)) { B200_SET_ERR("fse: give either counts or normalised counts"); return B200_ERR_ARG; }
+    uint8_t* d; uint8_t* pin;
+    B200_TRY(b200_scratch(ctx, 6, 4096, reinterpret_cast<void**>(&d)));
+    B200_TRY(b200_pinned(ctx, 4096, reinterpret_cast<void**>(&pin)));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint32_t* d_freq = reinterpret_cast<uint32_t*>(d + 64);
+    uint16_t* d_nin = reinterpret_cast<uint16_t*>(d + 64 + 1024);
+    uint16_t* d_nout = reinterpret_cast<uint16_t*>(d + 64 + 1536);
+    uint32_t* d_tt = reinterpret_cast<uint32_t*>(d + 64 + 2048);
+    if (h_freq) { memcpy(pin, h_freq, 1024); CUDA_TRY(cudaMemcpyAsync(d_freq, pin, 1024, cudaMemcpyHostToDevice, ctx->stream)); }
+    else { memcpy(pin, h_norm_in, 512); CUDA_TRY(cudaMemcpyAsync(d_nin, pin, 512, cudaMemcpyHostToDevice, ctx->stream)); }
+    fse_tables_kernel<<<1, 32, 0, ctx->stream>>>(h_freq ? d_freq : nullptr, h_freq ? nullptr : d_nin, d_nout, d_tt);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(pin + 1024, d_nout, 512, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(pin + 2048, d_tt, 1024, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_norm_out) memcpy(h_norm_out, pin + 1024, 512);
+    if (h_tt_out) memcpy(h_tt_out, pin + 2048, 1024);
     return B200_OK;
 }

@@ -124,3 +124,144 @@ extern "C" int b200_huffman_decompress_serial_host(b200_ctx* ctx, const uint32_t
     if (h_count) *h_count = cnt;
     return B200_OK;
 }
+
+// build_huffman_tree + gather_codes from a host buffer: only the side buffer comes back
+extern "C" int b200_huffman_tables_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
+                                        uint8_t* h_side, uint64_t side_bytes) {
+    b200_huff_layout L;
+    B200_TRY(b200_huffman_layout(n, block_size, &L));
+    if (side_bytes < L.bytes) { B200_SET_ERR("huffman: host side buffer too small"); return B200_ERR_CAPACITY; }
+    uint8_t *d_in, *d_side;
+    B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
+    B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
+    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_huffman_tables_dev(ctx, d_in, n, block_size, d_side, L.bytes));
+    CUDA_TRY(cudaMemcpyAsync(h_side, d_side, L.off_block_bits, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+// _huffman_compress from host buffers: the caller's code table, one table for the whole buffer
+extern "C" int b200_huffman_compress_codes_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n,
+                                                const uint32_t* h_codes, const uint8_t* h_lens,
+                                                uint32_t* h_words, uint64_t words_capacity, uint8_t* h_side, uint64_t side_bytes,
+                                                uint64_t* h_total_words, uint32_t* h_worst_status) {
+    if (n == 0) { if (h_total_words) *h_total_words = 0; if (h_worst_status) *h_worst_status = 0; return B200_OK; }
+    b200_huff_layout L;
+    B200_TRY(b200_huffman_layout(n, 0, &L));
+    if (h_side && side_bytes < L.bytes) { B200_SET_ERR("huffman: host side buffer too small"); return B200_ERR_CAPACITY; }
+    // the reference allows up to 32 bits per symbol with a foreign table
+    uint64_t cap = 0;
+    { uint32_t mx = 0; for (int s = 0; s < 256; ++s) if (h_lens[s] > mx) mx = h_lens[s]; cap = (n * mx + 31) / 32 + 4; }
+    uint8_t *d_in, *d_side; uint32_t* d_words;
+    B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
+    B200_TRY(b200_scratch(ctx, 11, cap * 4, reinterpret_cast<void**>(&d_words)));
+    B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
+    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t total = 0; uint32_t worst = 0;
+    B200_TRY(b200_huffman_encode_with_codes_dev(ctx, d_in, n, h_codes, h_lens, d_words, cap, d_side, L.bytes, &total, &worst));
+    if (h_total_words) *h_total_words = total;
+    if (h_worst_status) *h_worst_status = worst;
+    if (worst) { B200_SET_ERR("huffman: a symbol of the input has no code (status %u)", worst); return B200_ERR_DOMAIN; }
+    if (total > words_capacity) { B200_SET_ERR("huffman: output needs %llu words, buffer has %llu", (unsigned long long)total, (unsigned long long)words_capacity); return B200_ERR_CAPACITY; }
+    CUDA_TRY(cudaMemcpyAsync(h_words, d_words, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_side) CUDA_TRY(cudaMemcpyAsync(h_side, d_side, L.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+// ---- FSE container: a self-describing stream so that fse_decompress needs nothing else.
+//   u64 header[8] = {magic, n, block_size, seg_size, nblocks, nsegs, stream_words, 0}
+//   u16 norm[nblocks][256]      normalised counts per block (main.zig:106-149)
+//   u32 seg_bits[nsegs]         exact bits of every segment stream (padded to a u64)
+//   u64 stream[stream_words]    the segment streams, each starting on a u64 word
+namespace {
+constexpr uint64_t FSE_MAGIC = 0x3130455346303042ull;   // "B00FSE01"
+inline uint64_t w8(uint64_t bytes) { return (bytes + 7) / 8; }
+}
+
+extern "C" uint64_t b200_fse_container_max_words(uint64_t n, uint64_t block_size, uint64_t seg_size) {
+    b200_fse_layout L;
+    if (b200_fse_layout_for(n ? n : 1, block_size, seg_size, &L) != B200_OK) return 0;
+    return 8 + w8(L.nblocks * 512) + w8(L.nsegs * 4) + b200_fse_max_words(n, seg_size);
+}
+
+extern "C" int b200_fse_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size, uint64_t seg_size,
+                                      uint64_t* h_out, uint64_t out_capacity_words, uint64_t* h_total_words) {
+    if (n == 0) { B200_SET_ERR("fse: empty input"); return B200_ERR_DOMAIN; }
+    b200_fse_layout L;
+    B200_TRY(b200_fse_layout_for(n, block_size, seg_size, &L));
+    const uint64_t cap = b200_fse_max_words(n, seg_size);
+    uint8_t *d_in, *d_side; uint64_t* d_words;
+    B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
+    B200_TRY(b200_scratch(ctx, 11, cap * 8, reinterpret_cast<void**>(&d_words)));
+    B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
+    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t total = 0;
+    B200_TRY(b200_fse_encode_dev(ctx, d_in, n, block_size, seg_size, d_words, cap, d_side, L.bytes, &total));
+    const uint64_t o_norm = 8, o_bits = o_norm + w8(L.nblocks * 512), o_stream = o_bits + w8(L.nsegs * 4);
+    if (o_stream + total > out_capacity_words) { B200_SET_ERR("fse: container needs %llu words, buffer has %llu", (unsigned long long)(o_stream + total), (unsigned long long)out_capacity_words); return B200_ERR_CAPACITY; }
+    const uint64_t bs_eff = L.segs_per_block * seg_size;
+    const uint64_t hdr[8] = {FSE_MAGIC, n, bs_eff, seg_size, L.nblocks, L.nsegs, total, 0};
+    memcpy(h_out, hdr, sizeof(hdr));
+    if ((L.nsegs * 4) % 8) h_out[o_stream - 1] = 0;
+    CUDA_TRY(cudaMemcpyAsync(h_out + o_norm, d_side + L.off_norm, L.nblocks * 512, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h_out + o_bits, d_side + L.off_seg_bits, L.nsegs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h_out + o_stream, d_words, total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_total_words) *h_total_words = o_stream + total;
+    return B200_OK;
+}
+
+extern "C" int b200_fse_container_size(const uint64_t* h_container, uint64_t words, uint64_t* h_n) {
+    if (!h_container || words < 8 || h_container[0] != FSE_MAGIC) { B200_SET_ERR("fse: not a B00FSE01 container"); return B200_ERR_FORMAT; }
+    if (h_n) *h_n = h_container[1];
+    return B200_OK;
+}
+
+extern "C" int b200_fse_decompress_host(b200_ctx* ctx, const uint64_t* h_container, uint64_t words,
+                                        uint8_t* h_out, uint64_t out_capacity, uint64_t* h_n) {
+    uint64_t n = 0;
+    B200_TRY(b200_fse_container_size(h_container, words, &n));
+    const uint64_t bs = h_container[2], seg = h_container[3], nblocks = h_container[4], nsegs = h_container[5], total = h_container[6];
+    b200_fse_layout L;
+    if (n == 0 || b200_fse_layout_for(n, bs, seg, &L) != B200_OK || L.nblocks != nblocks || L.nsegs != nsegs) {
+        B200_SET_ERR("fse: inconsistent container header"); return B200_ERR_FORMAT;
+    }
+    const uint64_t o_norm = 8, o_bits = o_norm + w8(nblocks * 512), o_stream = o_bits + w8(nsegs * 4);
+    if (o_stream + total > words) { B200_SET_ERR("fse: truncated container"); return B200_ERR_FORMAT; }
+    if (n > out_capacity) { B200_SET_ERR("fse: output needs %llu bytes, buffer has %llu", (unsigned long long)n, (unsigned long long)out_capacity); return B200_ERR_CAPACITY; }
+    uint8_t *d_out, *d_side; uint64_t* d_words;
+    B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_out)));
+    B200_TRY(b200_scratch(ctx, 11, (total + 4) * 8, reinterpret_cast<void**>(&d_words)));
+    B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
+    CUDA_TRY(cudaMemcpyAsync(d_side + L.off_norm, h_container + o_norm, nblocks * 512, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_side + L.off_seg_bits, h_container + o_bits, nsegs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_words, h_container + o_stream, total * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d_words + total, 0, 32, ctx->stream));
+    B200_TRY(b200_fse_rebuild_index_dev(ctx, n, bs, seg, d_side, L.bytes));
+    uint32_t bad = 0;
+    B200_TRY(b200_fse_decode_dev(ctx, d_words, d_side, L.bytes, n, bs, seg, d_out, &bad));
+    if (bad) { B200_SET_ERR("fse: %u corrupt segment streams", bad); return B200_ERR_FORMAT; }
+    CUDA_TRY(cudaMemcpyAsync(h_out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_n) *h_n = n;
+    return B200_OK;
+}
+
+// histogram + normalisation of one table scope from a host buffer (buildFrequencyTable +
+// normalizeFrequencyTable, main.zig:88-149): freq[256] and norm[256] of block 0 come back
+extern "C" int b200_fse_normalize_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint32_t* h_freq, uint16_t* h_norm) {
+    if (n == 0) { B200_SET_ERR("fse: empty input"); return B200_ERR_DOMAIN; }
+    b200_fse_layout L;
+    B200_TRY(b200_fse_layout_for(n, 0, 1024, &L));
+    uint8_t *d_in, *d_side;
+    B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
+    B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
+    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_fse_normalize_dev(ctx, d_in, n, 0, d_side, L.bytes));
+    if (h_freq) CUDA_TRY(cudaMemcpyAsync(h_freq, d_side + L.off_freq, 1024, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_norm) CUDA_TRY(cudaMemcpyAsync(h_norm, d_side + L.off_norm, 512, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}

@@ -494,11 +494,9 @@ extern "C" int b200_huffman_tables_dev(b200_ctx* ctx, const uint8_t* d_in, uint6
     return huff_tables(ctx, d_in, n, block_size, d_side, side_bytes, &L, &bs);
 }
 
-extern "C" int b200_huffman_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
-                                       uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
-                                       uint64_t* h_total_words, uint32_t* h_worst_status) {
-    b200_huff_layout L; uint64_t bs;
-    B200_TRY(huff_tables(ctx, d_in, n, block_size, d_side, side_bytes, &L, &bs));
+// chunk bit counts -> offsets -> bit packing, with the tables already in the side buffer
+static int huff_pack(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, const b200_huff_layout& L, uint32_t* d_words,
+                     uint64_t words_capacity, uint8_t* d_side, uint64_t* h_total_words, uint32_t* h_worst_status) {
     const uint32_t cpb = (uint32_t)L.chunks_per_block;
     uint64_t* info = reinterpret_cast<uint64_t*>(d_side);
     uint64_t* P = reinterpret_cast<uint64_t*>(d_side + L.off_sub_off + align8(L.nchunks * SUBS_PER_CHUNK * 4));
@@ -529,6 +527,51 @@ extern "C" int b200_huffman_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint6
         if (pin[1]) { B200_SET_ERR("huffman: stream needs %llu words, capacity %llu", (unsigned long long)pin[0], (unsigned long long)words_capacity); return B200_ERR_CAPACITY; }
     }
     return B200_OK;
+}
+
+extern "C" int b200_huffman_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                                       uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
+                                       uint64_t* h_total_words, uint32_t* h_worst_status) {
+    b200_huff_layout L; uint64_t bs;
+    B200_TRY(huff_tables(ctx, d_in, n, block_size, d_side, side_bytes, &L, &bs));
+    return huff_pack(ctx, d_in, n, L, d_words, words_capacity, d_side, h_total_words, h_worst_status);
+}
+
+// _huffman_compress (huffman.c:267-285): bit packing with the caller's code table, one
+// table for the whole buffer. A symbol without a code makes the reference exit(1)
+// (:274-277); here it is reported as status 3.
+__global__ void __launch_bounds__(256) huff_check_codes_kernel(const uint32_t* __restrict__ freq, const uint8_t* __restrict__ lens,
+                                                               uint32_t* __restrict__ meta) {
+    const bool bad = freq[threadIdx.x] != 0 && lens[threadIdx.x] == 0;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) meta[0] = 3;
+}
+
+extern "C" int b200_huffman_encode_with_codes_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n,
+                                                  const uint32_t* h_codes, const uint8_t* h_lens,
+                                                  uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
+                                                  uint64_t* h_total_words, uint32_t* h_worst_status) {
+    if (n == 0) { if (h_total_words) *h_total_words = 0; if (h_worst_status) *h_worst_status = 0; return B200_OK; }
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_side) & 7)) {
+        B200_SET_ERR("huffman: d_in must be 16-byte and d_side 8-byte aligned"); return B200_ERR_ARG;
+    }
+    b200_huff_layout L;
+    B200_TRY(b200_huffman_layout(n, 0, &L));
+    if (side_bytes < L.bytes) { B200_SET_ERR("huffman: side buffer too small"); return B200_ERR_CAPACITY; }
+    CUDA_TRY(cudaMemsetAsync(d_side, 0, L.off_block_bits, ctx->stream));   // info, freq, codes, lens, tree, meta
+    uint8_t* pin; B200_TRY(b200_pinned(ctx, 2048, reinterpret_cast<void**>(&pin)));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // the pinned staging area may still be in flight
+    memcpy(pin + 256, h_codes, 1024); memcpy(pin + 1280, h_lens, 256);
+    CUDA_TRY(cudaMemcpyAsync(d_side + L.off_codes, pin + 256, 1024, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_side + L.off_lens, pin + 1280, 256, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t tpb = (uint32_t)((L.chunks_per_block + TILE_CHUNKS - 1) / TILE_CHUNKS);
+    byte_hist_kernel<<<tpb, 256, 0, ctx->stream>>>(d_in, n, eff_block(n, 0), tpb, reinterpret_cast<uint32_t*>(d_side + L.off_freq));
+    huff_check_codes_kernel<<<1, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_side + L.off_freq), d_side + L.off_lens,
+                                                        reinterpret_cast<uint32_t*>(d_side + L.off_meta));
+    ctx->launches += 2;
+    uint32_t worst = 0;
+    const int rc = huff_pack(ctx, d_in, n, L, d_words, words_capacity, d_side, h_total_words, &worst);
+    if (h_worst_status) *h_worst_status = worst;
+    return rc;
 }
 
 extern "C" int b200_huffman_decode_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words, const uint8_t* d_side,

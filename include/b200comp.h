@@ -102,6 +102,13 @@ int b200_huffman_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint
 /* only the histogram + table build (build_huffman_tree + gather_codes) */
 int b200_huffman_tables_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
                             uint8_t* d_side, uint64_t side_bytes);
+/* _huffman_compress (huffman.c:267-285): bit packing with the caller's code table (host
+ * arrays of 256 entries), one table for the whole buffer. status 3 = a symbol of the input
+ * has no code (the reference prints an error and exits, huffman.c:274-277). */
+int b200_huffman_encode_with_codes_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n,
+                                       const uint32_t* h_codes, const uint8_t* h_lens,
+                                       uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
+                                       uint64_t* h_total_words, uint32_t* h_worst_status);
 /* table-lookup decoder driven by the side index written by the encoder */
 int b200_huffman_decode_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words,
                             const uint8_t* d_side, uint64_t side_bytes,
@@ -164,6 +171,10 @@ int b200_fse_decode_dev(b200_ctx* ctx, const uint64_t* d_words, const uint8_t* d
 /* histogram + normalisation only (the part of FSE whose parity is pinned) */
 int b200_fse_normalize_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
                            uint8_t* d_side, uint64_t side_bytes);
+/* decoder side of a stored stream: with norm[] and seg_bits[] already in d_side, rebuild
+ * the transition tables and the segment word offsets */
+int b200_fse_rebuild_index_dev(b200_ctx* ctx, uint64_t n, uint64_t block_size, uint64_t seg_size,
+                               uint8_t* d_side, uint64_t side_bytes);
 
 /* ---- host-buffer wrappers: H2D -> *_dev -> D2H, synchronous ------------------
  * These are what the reference-named shims call; bench.py's "e2e" number is
@@ -185,6 +196,27 @@ int b200_huffman_decompress_host(b200_ctx* ctx, const uint32_t* h_words, uint64_
 int b200_huffman_decompress_serial_host(b200_ctx* ctx, const uint32_t* h_words, uint64_t nwords,
                                         uint64_t buffer_size, const uint32_t* h_codes, const uint8_t* h_lens,
                                         uint8_t* h_out, uint64_t out_capacity, uint64_t* h_count);
+
+int b200_huffman_tables_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
+                             uint8_t* h_side, uint64_t side_bytes);
+int b200_huffman_compress_codes_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n,
+                                     const uint32_t* h_codes, const uint8_t* h_lens,
+                                     uint32_t* h_words, uint64_t words_capacity, uint8_t* h_side, uint64_t side_bytes,
+                                     uint64_t* h_total_words, uint32_t* h_worst_status);
+/* FSE container (self-describing, what fse_compress of the C mirror returns):
+ *   u64 header[8] = {magic "B00FSE01", n, block_size, seg_size, nblocks, nsegs, stream_words, 0}
+ *   u16 norm[nblocks][256] | u32 seg_bits[nsegs] | u64 stream[stream_words], each part padded to a u64 */
+uint64_t b200_fse_container_max_words(uint64_t n, uint64_t block_size, uint64_t seg_size);
+int b200_fse_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size, uint64_t seg_size,
+                           uint64_t* h_out, uint64_t out_capacity_words, uint64_t* h_total_words);
+int b200_fse_container_size(const uint64_t* h_container, uint64_t words, uint64_t* h_n);
+int b200_fse_decompress_host(b200_ctx* ctx, const uint64_t* h_container, uint64_t words,
+                             uint8_t* h_out, uint64_t out_capacity, uint64_t* h_n);
+int b200_fse_normalize_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint32_t* h_freq, uint16_t* h_norm);
+/* one table: normalise 256 raw counts and build the transition table (h_freq given), or
+ * build the table of already normalised counts (h_norm_in given) */
+int b200_fse_tables_host(b200_ctx* ctx, const uint32_t* h_freq, const uint16_t* h_norm_in,
+                         uint16_t* h_norm_out, uint32_t* h_tt_out);
 
 #ifdef __cplusplus
 }
