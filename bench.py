@@ -280,7 +280,8 @@ def main():
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get("lz77_v2_kernel<1>", {}).get("dram_bytes_per_launch")
+                per_byte = json.load(f).get("lz77_v2_kernel<1>", {}).get("dram_bytes_per_input_byte")
+            traffic = int(per_byte * n) if per_byte else None   # ncu capture at 100 MB, scaled to this launch's input
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "lz77_v2_kernel<1> (deflate-variant match finder: shared-memory table simulation + greedy parse + token emission)",
