@@ -106,7 +106,55 @@ __device__ __forceinline__ uint32_t bm_rank(const uint32_t* bm, const uint32_t* 
     return r + __popc(bm[wi] & ((1u << (s & 31)) - 1u));
 }
 
-template <int V>
+// Long walks (hot chains). From cursor kk (every slot before it proven live at the lane's time)
+// to the first slot with T <= dthr, one aligned group of 32 slots per step: the 64 bytes of the
+// group are read with four 16-byte loads, the dead slots found with packed u16 compares. Whole
+// groups are skipped while the group's lower bound B1[g] proves every slot live and, for a lane
+// whose find is still pending, the signature filter S1[g] proves the pattern absent. Every group
+// that is read gets its exact minimum published to B1 (T only grows, so any snapshot minimum stays
+// a valid lower bound). Slots of a neighbouring range may be in the group; the walk ends inside
+// the lane's own cluster, so they never decide anything.
+__device__ __forceinline__ uint32_t walk_groups(const uint16_t* T, uint16_t* B1, const uint32_t* S1, const uint8_t* data,
+                                                uint32_t kk, uint32_t dthr, uint32_t w, uint32_t sig, bool& pend, uint32_t& fm,
+                                                uint32_t& iters) {
+    const uint32_t thr2 = dthr | (dthr << 16);
+    for (;;) {
+        uint32_t g = kk >> 5;
+        const uint32_t j0 = kk & 31u;
+        if (j0 == 0) {
+            while (B1[g] > dthr && !(pend && ((S1[g] >> sig) & 1u))) ++g;   // unused tail groups have B1 == 0
+            kk = g << 5;
+        }
+        ++iters;
+        const uint4* gp = reinterpret_cast<const uint4*>(T + (g << 5));
+        const uint4 q0 = gp[0], q1 = gp[1], q2 = gp[2], q3 = gp[3];
+        const uint32_t wd[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+        uint32_t dm = 0, mn2 = 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t r = __vsetleu2(wd[i], thr2);             // 1 per halfword that is <= dthr
+            dm |= ((r & 1u) | ((r >> 15) & 2u)) << (2 * i);
+            mn2 = __vminu2(mn2, wd[i]);
+        }
+        B1[g] = (uint16_t)min(mn2 & 0xFFFFu, mn2 >> 16);
+        dm &= 0xFFFFFFFFu << j0;
+        const uint32_t stop = dm ? (uint32_t)(__ffs(dm) - 1) : 32u;
+        if (pend) {
+#pragma unroll 1
+            for (uint32_t j = j0; j < stop; ++j) {
+                const uint32_t v = T[(g << 5) + j];
+                if (sm_word(data, v - 1) == w) { fm = v - 1; pend = false; break; }
+            }
+        }
+        if (dm) return (g << 5) + stop;
+        kk = (g + 1) << 5;
+    }
+}
+
+// DBG: phase stamps and per-warp cycle counters (tools/lz_stats.py); the clock reads cost a few
+// per cent, so the production instantiation leaves them out
+#define CLK() (DBG ? clock64() : 0ll)
+template <int V, bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t bs, uint32_t nblocks,
                                                              uint32_t* __restrict__ lists_all, uint32_t* __restrict__ tok_all,
                                                              uint8_t* __restrict__ scratch, uint64_t stride,
@@ -132,8 +180,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
 
     uint32_t* dbg_stats = dbg_tok ? dbg_tok + (uint64_t)nblocks * MAXB : nullptr;   // [block][8 phase stamps + 32 warps x 4]
     for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
-        const long long t_begin = clock64();
-#define PHASE_STAMP(k) do { if (dbg_stats && tid == 0) dbg_stats[(uint64_t)b * 136 + (k)] = (uint32_t)(clock64() - t_begin); } while (0)
+        const long long t_begin = CLK();
+#define PHASE_STAMP(k) do { if (DBG && dbg_stats && tid == 0) dbg_stats[(uint64_t)b * 136 + (k)] = (uint32_t)(clock64() - t_begin); } while (0)
         const uint8_t* src = in + (uint64_t)b * bs;
         const uint32_t len = (uint32_t)(n - (uint64_t)b * bs < bs ? n - (uint64_t)b * bs : bs);
 
@@ -294,7 +342,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             const uint32_t sp_lo_end = ms->sp_lo_end, sp_hi_start = ms->sp_hi_start;
             uint32_t cur = ms->rstart[warp];
             const uint32_t end = ms->rstart[warp + 1];
-            const long long t_p4 = clock64();
+            const long long t_p4 = CLK();
             uint32_t st_rounds = 0, st_coop = 0, st_entries = end - cur, st_iters = 0;
             long long tq = 0, tc = 0, tm = 0, tl = 0, t_mark;
             uint32_t qh = 0, qt = 0;                       // slot-0 clear queue (only warp 0 ever uses it)
@@ -350,68 +398,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 uint32_t fm = NONE; bool pend = true;
                 while (__ballot_sync(0xffffffffu, !done)) {
                     ++st_rounds;
-                    t_mark = clock64();
-                    // advance every cursor to the first slot that is dead at the lane's time.
-                    // (a) a few private steps: most walks are 1-3 slots long
-                    bool need = false;
+                    t_mark = CLK();
+                    // advance every cursor to the first slot that is dead at the lane's time: a few
+                    // single-slot probes (most walks are 1-3 slots long), then whole aligned groups of
+                    // 32 slots per step (walk_groups), all lanes walking privately and concurrently
                     if (!done) {
-                        need = true;
+                        bool need = true;
 #pragma unroll 1
-                        for (int it = 0; it < 6; ++it) {
+                        for (int it = 0; it < 3; ++it) {
                             const uint32_t v = T[kk];
                             if (v <= dthr) { need = false; break; }
                             if (pend && sm_word(data, v - 1) == w) { fm = v - 1; pend = false; }
                             ++kk;
                         }
+                        if (need) { ++st_coop; kk = walk_groups(T, B1, S1, data, kk, dthr, w, sig, pend, fm, st_iters); }
                     }
-                    // (b) long walks (hot chains): the whole warp serves one lane at a time, 32 slots
-                    //     or 32 groups per step, skipping groups the bound/signature tables prove irrelevant
-                    uint32_t needmask = __ballot_sync(0xffffffffu, need);
-                    tq += clock64() - t_mark; t_mark = clock64();
-                    while (needmask) {
-                        const int j = __ffs(needmask) - 1;
-                        needmask &= needmask - 1;
-                        ++st_coop;
-                        uint32_t ckk = __shfl_sync(0xffffffffu, kk, j);
-                        const uint32_t cd = __shfl_sync(0xffffffffu, dthr, j);
-                        const uint32_t cw = __shfl_sync(0xffffffffu, w, j);
-                        const uint32_t csig = __shfl_sync(0xffffffffu, sig, j);
-                        bool cpend = __shfl_sync(0xffffffffu, (int)pend, j) != 0;
-                        uint32_t cfm = NONE;
-                        for (;;) {
-                            ++st_iters;
-                            if ((ckk & 31) == 0) {
-                                const uint32_t g = (ckk >> 5) + lane;
-                                const bool ok = g < 2050u && B1[g] > cd && (!cpend || !((S1[g] >> csig) & 1u));
-                                const uint32_t stop = __ballot_sync(0xffffffffu, !ok);
-                                const uint32_t nskip = stop ? (uint32_t)(__ffs(stop) - 1) : 32u;
-                                ckk += 32u * nskip;
-                                if (nskip == 32u) continue;
-                            }
-                            const uint32_t lim = 32u - (ckk & 31u);
-                            const bool inwin = lane < lim;
-                            const uint32_t v = inwin ? (uint32_t)T[ckk + lane] : 0xFFFFFFFFu;
-                            const bool live = v > cd;
-                            const bool mt = inwin && live && cpend && sm_word(data, v - 1) == cw;
-                            const uint32_t dm = __ballot_sync(0xffffffffu, !live);
-                            const uint32_t mm = __ballot_sync(0xffffffffu, mt);
-                            const uint32_t fd = dm ? (uint32_t)(__ffs(dm) - 1) : 32u;
-                            if (mm) {
-                                const uint32_t fx = (uint32_t)(__ffs(mm) - 1);
-                                const uint32_t mv = __shfl_sync(0xffffffffu, v, fx);
-                                if (fx < fd) { cfm = mv - 1; cpend = false; }
-                            }
-                            if (dm) { ckk += fd; break; }
-                            if (lim == 32u) {   // a whole aligned group is live: publish its minimum key as the group's lower bound
-                                const uint32_t mn = __reduce_min_sync(0xffffffffu, v);
-                                if (lane == 0) B1[ckk >> 5] = (uint16_t)mn;
-                            }
-                            ckk += lim;
-                        }
-                        if ((int)lane == j) { kk = ckk; if (pend && !cpend) { fm = cfm; pend = false; } }
-                    }
+                    tq += CLK() - t_mark; t_mark = CLK();
                     __syncwarp();
-                    tc += clock64() - t_mark; t_mark = clock64();
+                    tc += CLK() - t_mark; t_mark = CLK();
                     const uint32_t key = done ? (0x80000000u | lane) : kk;
                     const uint32_t peers = __match_any_sync(0xffffffffu, key);
                     const bool blocked = !done && (peers & lt_mask) != 0;
@@ -423,9 +427,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                         done = true;
                     }
                     __syncwarp();
-                    tm += clock64() - t_mark;
+                    tm += CLK() - t_mark;
                 }
-                t_mark = clock64();
+                t_mark = CLK();
                 // token candidates of the whole batch at once (outside the commit rounds)
                 if (lane < L) {
                     uint32_t tk = 0;
@@ -434,10 +438,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                     if (!reject) tk = (q - m) | (match_len<MAXLEN>(data, m, q) << 16);
                     tokb[q] = tk;
                 }
-                tl += clock64() - t_mark;
+                tl += CLK() - t_mark;
                 cur += L;
             }
-            if (dbg_stats && lane == 0) {
+            if (DBG && dbg_stats && lane == 0) {
                 uint32_t* o = dbg_stats + (uint64_t)b * 136 + 8 + warp * 4;
                 o[0] = (uint32_t)(clock64() - t_p4); o[1] = st_entries | (st_iters << 16); o[2] = st_rounds | ((uint32_t)(tq >> 10) << 16); o[3] = st_coop | ((uint32_t)(tc >> 10) << 16);
                 if (warp < 8) dbg_stats[(uint64_t)b * 136 + 7] = 0;
@@ -581,8 +585,10 @@ int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, 
                    uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok) {
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(lz77_v2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(lz77_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(lz77_v2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(lz77_v2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(lz77_v2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(lz77_v2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_done = true;
     }
     uint64_t grid = (uint64_t)ctx->sm_count;
@@ -590,10 +596,9 @@ int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, 
     uint32_t *lists, *tok;
     B200_TRY(b200_scratch(ctx, 13, (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&lists)));
     B200_TRY(b200_scratch(ctx, 14, (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&tok)));
-    if (variant == 0)
-        lz77_v2_kernel<0><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, lists, tok, scratch, stride, d_block_sizes, block_bytes, dbg_tok);
-    else
-        lz77_v2_kernel<1><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, lists, tok, scratch, stride, d_block_sizes, block_bytes, dbg_tok);
+#define LZ_V2_LAUNCH(V, D) lz77_v2_kernel<V, D><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, lists, tok, scratch, stride, d_block_sizes, block_bytes, dbg_tok)
+    if (dbg_tok) { if (variant == 0) LZ_V2_LAUNCH(0, true); else LZ_V2_LAUNCH(1, true); }
+    else { if (variant == 0) LZ_V2_LAUNCH(0, false); else LZ_V2_LAUNCH(1, false); }
     CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }
