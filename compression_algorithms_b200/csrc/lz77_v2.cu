@@ -495,13 +495,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             }
         }
         __syncthreads();
-        // per-chunk output size, CTA exclusive scan
+        // per-chunk output size, CTA exclusive scan. V1 also notes, for every token start, its byte
+        // offset inside the chunk's output (in 2-byte units, exitof is dead now) so that P6 can emit
+        // one position per thread with coalesced reads
+        uint8_t* orel = exitof;
+        if (V == 1) {
+            for (uint32_t i = tid; i < (MAXB >> 2); i += NTHREADS) reinterpret_cast<uint32_t*>(orel)[i] = 0xFFFFFFFFu;
+            __syncthreads();
+        }
         uint32_t my_units = 0;   // bytes (V1) or bits (V0)
         if (tid < nchunks) {
             const uint32_t cend = (tid << 6) + 64;
             const uint32_t hi = cend < len ? cend : len;
             for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[p]) {
                 const bool lit = adv[p] == 1;   // matches are at least 4 long
+                if (V == 1) orel[p] = (uint8_t)(my_units >> 1);
                 my_units += V ? (lit ? 2u : 4u) : (lit ? 9u : 19u);
             }
         }
@@ -525,18 +533,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         PHASE_STAMP(5);
         // ---------------- P6: emission
         if (V == 1) {
-            if (tid < nchunks) {
-                const uint32_t cend = (tid << 6) + 64;
-                const uint32_t hi = cend < len ? cend : len;
-                uint32_t o = my_off;
-                for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[p]) {
-                    const uint32_t t = tokb[p];
-                    if (t == 0) { *reinterpret_cast<uint16_t*>(out + o) = (uint16_t)((uint32_t)data[p] << 8); o += 2; }
+            uint32_t* coff = pre + 3072;          // u32[1024] output offset of every chunk (the P4 tables are dead)
+            if (tid < nchunks) coff[tid] = my_off;
+            __syncthreads();
+            for (uint32_t p0 = tid; p0 < len; p0 += 4 * NTHREADS) {
+                uint32_t tk[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) { const uint32_t p = p0 + k * NTHREADS; tk[k] = p < len ? tokb[p] : 0u; }
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                    const uint32_t p = p0 + k * NTHREADS;
+                    if (p >= len) break;
+                    const uint32_t r = orel[p];
+                    if (r == 0xFFu) continue;     // not a token start of the greedy parse
+                    const uint32_t o = coff[p >> 6] + 2u * r, t = tk[k];
+                    if (t == 0) *reinterpret_cast<uint16_t*>(out + o) = (uint16_t)((uint32_t)data[p] << 8);
                     else {
                         const uint32_t off = t & 0xFFFFu, ml = t >> 16;
                         *reinterpret_cast<uint16_t*>(out + o) = (uint16_t)(1u | ((off & 0xFFu) << 8));
                         *reinterpret_cast<uint16_t*>(out + o + 2) = (uint16_t)((off >> 8) | (ml << 8));
-                        o += 4;
                     }
                 }
             }
