@@ -117,6 +117,26 @@ __device__ __forceinline__ uint64_t cta_scan_step(uint64_t v, uint64_t* warp_tot
     return warp_tot[w] + incl - v;
 }
 
+// Exclusive scan of n values by ONE 1024-thread CTA, 16 consecutive values per thread and step
+// (the loads of a step are independent, so a step costs one memory round trip for 16384 values).
+// load(i) -> uint64_t value i; store(i, exclusive_prefix). Returns the total to every thread.
+template <typename LoadF, typename StoreF>
+__device__ __forceinline__ uint64_t cta_exscan_1024(uint64_t n, uint64_t* warp_tot, LoadF load, StoreF store) {
+    constexpr int ITEMS = 16;
+    uint64_t carry = 0, tot;
+    for (uint64_t base = 0; base < n; base += 1024ull * ITEMS) {
+        const uint64_t i0 = base + (uint64_t)threadIdx.x * ITEMS;
+        uint64_t v[ITEMS], sum = 0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) { v[k] = i0 + k < n ? load(i0 + k) : 0; sum += v[k]; }
+        uint64_t run = carry + cta_scan_step(sum, warp_tot, &tot);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) { if (i0 + k < n) store(i0 + k, run); run += v[k]; }
+        carry += tot;
+    }
+    return carry;
+}
+
 // murmur3-style hash of one u32 key, seed 0, no length xor, masked to 2^20 slots
 // (reference: algorithms/lz77/lz77.c:13-41, algorithms/deflate/lz77.c:14-42).
 __host__ __device__ __forceinline__ uint32_t lz_hash(uint32_t k) {

@@ -192,15 +192,9 @@ __global__ void __launch_bounds__(1024) fse_offsets_kernel(const uint32_t* __res
                                                            uint64_t* __restrict__ seg_word, uint64_t capacity,
                                                            uint64_t* __restrict__ info) {
     __shared__ uint64_t warp_tot[33];
-    uint64_t carry = 0, tot;
-    for (uint64_t base = 0; base < nsegs; base += 1024) {
-        const uint64_t i = base + threadIdx.x;
-        const uint64_t v = i < nsegs ? ((uint64_t)seg_bits[i] + 63) >> 6 : 0;
-        const uint64_t ex = cta_scan_step(v, warp_tot, &tot);
-        if (i < nsegs) seg_word[i] = carry + ex;
-        carry += tot;
-    }
-    if (threadIdx.x == 0) { seg_word[nsegs] = carry; info[0] = carry; info[1] = carry > capacity ? 1 : 0; }
+    const uint64_t total = cta_exscan_1024(nsegs, warp_tot,
+        [&](uint64_t i) { return ((uint64_t)seg_bits[i] + 63) >> 6; }, [&](uint64_t i, uint64_t ex) { seg_word[i] = ex; });
+    if (threadIdx.x == 0) { seg_word[nsegs] = total; info[0] = total; info[1] = total > capacity ? 1 : 0; }
 }
 
 __global__ void __launch_bounds__(256) fse_gather_kernel(const uint64_t* __restrict__ scratch, uint32_t stride_words,

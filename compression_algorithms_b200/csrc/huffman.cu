@@ -39,64 +39,64 @@ __global__ void __launch_bounds__(32) huff_build_kernel(const uint32_t* __restri
     __shared__ uint32_t nfreq[511];
     __shared__ int16_t  left[511], right[511], parent[511];
     __shared__ uint8_t  isright[511];
-    __shared__ uint32_t hf[256];
-    __shared__ uint16_t hn[256];
+    __shared__ uint64_t hq[256];   // heap entry = frequency << 32 | node: one load / store per element; only the frequency is compared
     __shared__ int s_nn, s_root, s_distinct;
     const uint64_t b = blockIdx.x;
     const unsigned lane = threadIdx.x;
     for (int s = lane; s < 256; s += 32) fr[s] = freq[b * 256 + s];
     __syncwarp();
     if (lane == 0) {
+#define HQ_F(x) ((uint32_t)((x) >> 32))
+        auto sift_up = [&](int idx) {
+            const uint64_t x = hq[idx];
+            while (idx > 0) {
+                const int p = (idx - 1) >> 1;
+                const uint64_t y = hq[p];
+                if (!(HQ_F(x) < HQ_F(y))) break;
+                hq[idx] = y;              // the swaps of heapify_up move x up and each parent down
+                idx = p;
+            }
+            hq[idx] = x;
+        };
         int size = 0, nn = 0;
         for (int s = 0; s < 256; ++s) {
             const uint32_t f = fr[s];
             if (!f) continue;
             nfreq[nn] = f; left[nn] = -1; right[nn] = (int16_t)s; parent[nn] = -1; isright[nn] = 0;
-            int idx = size++;
-            hf[idx] = f; hn[idx] = (uint16_t)nn; ++nn;
-            while (idx > 0) {
-                const int p = (idx - 1) >> 1;
-                if (!(hf[idx] < hf[p])) break;
-                const uint32_t tf = hf[idx]; hf[idx] = hf[p]; hf[p] = tf;
-                const uint16_t tn = hn[idx]; hn[idx] = hn[p]; hn[p] = tn;
-                idx = p;
-            }
+            hq[size] = ((uint64_t)f << 32) | (uint32_t)nn; ++nn;
+            sift_up(size++);
         }
         const int distinct = nn;
         while (size > 1) {
             int pick[2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                pick[q] = hn[0];
+                pick[q] = (int)(uint32_t)hq[0];
                 --size;
-                hf[0] = hf[size]; hn[0] = hn[size];
+                const uint64_t x = hq[size];   // dequeue: the last element goes to the root, then sifts down
                 int idx = 0;
                 for (;;) {
                     const int l = 2 * idx + 1, r = l + 1;
-                    int sm = idx; uint32_t fs = hf[idx];
-                    if (l < size && hf[l] < fs) { sm = l; fs = hf[l]; }
-                    if (r < size && hf[r] < fs) { sm = r; }
+                    if (l >= size) break;
+                    const uint64_t yl = hq[l], yr = r < size ? hq[r] : 0xFFFFFFFFFFFFFFFFull;
+                    // smallest of (x, left, right) with the reference's order of comparisons (strict <, left first)
+                    int sm = idx; uint64_t ys = x;
+                    if (HQ_F(yl) < HQ_F(ys)) { sm = l; ys = yl; }
+                    if (r < size && HQ_F(yr) < HQ_F(ys)) { sm = r; ys = yr; }
                     if (sm == idx) break;
-                    const uint32_t tf = hf[idx]; hf[idx] = hf[sm]; hf[sm] = tf;
-                    const uint16_t tn = hn[idx]; hn[idx] = hn[sm]; hn[sm] = tn;
+                    hq[idx] = ys;
                     idx = sm;
                 }
+                if (size > 0) hq[idx] = x;
             }
             const uint32_t f = nfreq[pick[0]] + nfreq[pick[1]];  // u32 wrap like init_node(uint32_t)
             nfreq[nn] = f; left[nn] = (int16_t)pick[0]; right[nn] = (int16_t)pick[1]; parent[nn] = -1; isright[nn] = 0;
             parent[pick[0]] = (int16_t)nn; isright[pick[0]] = 0;
             parent[pick[1]] = (int16_t)nn; isright[pick[1]] = 1;
-            int idx = size++;
-            hf[idx] = f; hn[idx] = (uint16_t)nn; ++nn;
-            while (idx > 0) {
-                const int p = (idx - 1) >> 1;
-                if (!(hf[idx] < hf[p])) break;
-                const uint32_t tf = hf[idx]; hf[idx] = hf[p]; hf[p] = tf;
-                const uint16_t tn = hn[idx]; hn[idx] = hn[p]; hn[p] = tn;
-                idx = p;
-            }
+            hq[size] = ((uint64_t)f << 32) | (uint32_t)nn; ++nn;
+            sift_up(size++);
         }
-        s_nn = nn; s_distinct = distinct; s_root = distinct ? hn[0] : 0;
+        s_nn = nn; s_distinct = distinct; s_root = distinct ? (int)(uint32_t)hq[0] : 0;
     }
     __syncwarp();
     const int nn = s_nn, distinct = s_distinct, root = s_root;
@@ -164,48 +164,38 @@ __global__ void __launch_bounds__(256) huff_chunkbits_kernel(const uint8_t* __re
 __global__ void __launch_bounds__(1024) huff_offsets_kernel(const uint32_t* __restrict__ chunk_bits, uint64_t nchunks,
                                                             uint32_t cpb, uint64_t nblocks, uint64_t* __restrict__ P,
                                                             uint64_t* __restrict__ block_bits, uint64_t* __restrict__ block_word,
-                                                            uint64_t* __restrict__ chunk_off, uint32_t* __restrict__ words,
                                                             uint64_t words_capacity, uint64_t* __restrict__ info) {
     __shared__ uint64_t warp_tot[33];
-    uint64_t carry = 0, tot;
-    for (uint64_t base = 0; base < nchunks; base += 1024) {
-        const uint64_t i = base + threadIdx.x;
-        const uint64_t v = i < nchunks ? chunk_bits[i] : 0;
-        const uint64_t ex = cta_scan_step(v, warp_tot, &tot);
-        if (i < nchunks) P[i] = carry + ex;
-        carry += tot;
-    }
-    if (threadIdx.x == 0) P[nchunks] = carry;
+    const uint64_t total_bits = cta_exscan_1024(nchunks, warp_tot,
+        [&](uint64_t i) { return (uint64_t)chunk_bits[i]; }, [&](uint64_t i, uint64_t ex) { P[i] = ex; });
+    if (threadIdx.x == 0) P[nchunks] = total_bits;
     __syncthreads();
-    carry = 0;
-    for (uint64_t base = 0; base < nblocks; base += 1024) {
-        const uint64_t b = base + threadIdx.x;
-        uint64_t wds = 0;
-        if (b < nblocks) {
+    const uint64_t total_words = cta_exscan_1024(nblocks, warp_tot,
+        [&](uint64_t b) {
             const uint64_t first = b * cpb;
             uint64_t last = first + cpb; if (last > nchunks) last = nchunks;
             const uint64_t bits = P[last] - P[first];
             block_bits[b] = bits;
-            wds = (bits + 31) >> 5;
-        }
-        const uint64_t ex = cta_scan_step(wds, warp_tot, &tot);
-        if (b < nblocks) block_word[b] = carry + ex;
-        carry += tot;
-    }
-    const uint64_t total_words = carry;
+            return (bits + 31) >> 5;
+        },
+        [&](uint64_t b, uint64_t ex) { block_word[b] = ex; });
     if (threadIdx.x == 0) {
         block_word[nblocks] = total_words;
         info[0] = total_words;
         info[1] = total_words > words_capacity ? 1 : 0;
     }
-    __syncthreads();
-    const bool fits = total_words <= words_capacity;
-    for (uint64_t c = threadIdx.x; c < nchunks; c += 1024) {
-        const uint64_t b = c / cpb;
-        const uint64_t off = block_word[b] * 32 + (P[c] - P[b * cpb]);
-        chunk_off[c] = off;
-        if (fits && (off & 31)) words[off >> 5] = 0;
-    }
+}
+
+// absolute bit offset of every chunk; zeroes the words shared by two chunks so the encoder can OR into them
+__global__ void __launch_bounds__(256) huff_chunkoff_kernel(uint64_t nchunks, uint32_t cpb, const uint64_t* __restrict__ P,
+                                                            const uint64_t* __restrict__ block_word, uint64_t* __restrict__ chunk_off,
+                                                            uint32_t* __restrict__ words, const uint64_t* __restrict__ info) {
+    const uint64_t c = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= nchunks) return;
+    const uint64_t b = c / cpb;
+    const uint64_t off = block_word[b] * 32 + (P[c] - P[b * cpb]);
+    chunk_off[c] = off;
+    if (!info[1] && (off & 31)) words[off >> 5] = 0;
 }
 
 // ---------------------------------------------------------------- K5 encode
@@ -301,39 +291,30 @@ __global__ void __launch_bounds__(256) huff_encode_kernel(const uint8_t* __restr
 
 // ---------------------------------------------------------------- K6 decode
 // One CTA per tile of 16 chunks of one block (256 threads, one 256-symbol sub-chunk
-// each). A 12-bit primary table in shared memory resolves codes up to 12 bits in
-// one lookup; longer (rare) codes are matched against the short list of long codes.
+// each). A 12-bit primary table in shared memory resolves codes up to 12 bits in one
+// lookup: entry = 0x8000 | len << 8 | symbol. A longer (rare) code finds in the table the
+// tree node reached after its first 12 bits and walks the reference's own tree from there,
+// one bit per step (children in shared memory), so its cost is len - 12 steps and not a
+// search over all long codes.
 __global__ void __launch_bounds__(256) huff_decode_kernel(const uint32_t* __restrict__ words, uint64_t total_words,
                                                           uint64_t n, uint64_t bs, uint32_t cpb, uint32_t tiles_per_block,
-                                                          const uint32_t* __restrict__ codes, const uint8_t* __restrict__ lens,
+                                                          const int16_t* __restrict__ tree, const uint32_t* __restrict__ meta,
                                                           const uint64_t* __restrict__ chunk_off, const uint32_t* __restrict__ sub_off,
                                                           uint8_t* __restrict__ out) {
     __shared__ uint16_t lut[1u << LUT_BITS];
-    __shared__ uint32_t sc[256];
-    __shared__ uint8_t  sl[256];
-    __shared__ uint8_t  long_sym[256];
-    __shared__ uint32_t n_long;
+    __shared__ int16_t  kids[511][2];          // {left, right}; leaf = {-1, symbol}
     const uint64_t b = blockIdx.x / tiles_per_block, k = blockIdx.x % tiles_per_block;
-    if (threadIdx.x == 0) n_long = 0;
-    sc[threadIdx.x] = codes[b * 256 + threadIdx.x];
-    sl[threadIdx.x] = lens[b * 256 + threadIdx.x];
-    __syncthreads();
     {
-        const uint32_t s = threadIdx.x;
-        const uint32_t L = sl[s];
-        if (L > LUT_BITS) {
-            const uint32_t slot = atomicAdd(&n_long, 1u);
-            long_sym[slot] = (uint8_t)s;
-            lut[sc[s] >> (L - LUT_BITS)] = 0;
-        }
+        const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tree + b * 511 * 2);
+        uint32_t* k32 = reinterpret_cast<uint32_t*>(&kids[0][0]);
+        for (uint32_t i = threadIdx.x; i < 511; i += 256) k32[i] = t32[i];
     }
-    const unsigned warp = threadIdx.x >> 5;
-    for (uint32_t s = warp; s < 256; s += 8) {
-        const uint32_t L = sl[s];
-        if (L == 0 || L > LUT_BITS) continue;
-        const uint32_t base = sc[s] << (LUT_BITS - L), count = 1u << (LUT_BITS - L);
-        const uint16_t e = (uint16_t)(0x8000u | (L << 8) | s);
-        for (uint32_t i = lane_id(); i < count; i += 32) lut[base + i] = e;
+    const uint32_t root = meta[b * 4 + 2];
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < (1u << LUT_BITS); i += 256) {
+        uint32_t v = root, d = 0;
+        while (d < LUT_BITS && kids[v][0] >= 0) { v = (uint32_t)kids[v][(i >> (LUT_BITS - 1 - d)) & 1u]; ++d; }
+        lut[i] = kids[v][0] < 0 ? (uint16_t)(0x8000u | (d << 8) | (uint32_t)(uint16_t)kids[v][1]) : (uint16_t)v;   // leaf | inner node after 12 bits
     }
     __syncthreads();
 
@@ -354,8 +335,8 @@ __global__ void __launch_bounds__(256) huff_decode_kernel(const uint32_t* __rest
         const uint64_t w1 = wi < total_words ? __ldg(&words[wi]) : 0; ++wi;
         win |= w1 << (32 - avail); avail += 32;
     }
+    uint32_t nextw = wi < total_words ? __ldg(&words[wi]) : 0;   // one word ahead: the refill never waits for memory
     uint8_t* o = out + sym0;
-    const uint32_t nl = n_long;
     uint32_t done = 0;
     while (done < count) {
         uint32_t pack[4] = {0, 0, 0, 0};
@@ -364,19 +345,17 @@ __global__ void __launch_bounds__(256) huff_decode_kernel(const uint32_t* __rest
         for (uint32_t q = 0; q < 16; ++q) {
             if (q < batch) {
                 if (avail <= 32) {
-                    const uint64_t w = wi < total_words ? __ldg(&words[wi]) : 0; ++wi;
-                    win |= w << (32 - avail); avail += 32;
+                    win |= (uint64_t)nextw << (32 - avail); avail += 32;
+                    ++wi;
+                    nextw = wi < total_words ? __ldg(&words[wi]) : 0;
                 }
                 const uint32_t e = lut[(uint32_t)(win >> (64 - LUT_BITS))];
                 uint32_t s, L;
                 if (e & 0x8000u) { s = e & 0xFF; L = (e >> 8) & 0x7F; }
                 else {
-                    const uint32_t top = (uint32_t)(win >> 32);
-                    s = 0; L = 1;
-                    for (uint32_t j = 0; j < nl; ++j) {
-                        const uint32_t cs = long_sym[j], cl = sl[cs];
-                        if ((top >> (32 - cl)) == sc[cs]) { s = cs; L = cl; break; }
-                    }
+                    uint32_t v = e; L = LUT_BITS;          // codes are at most 32 bits (status 2 otherwise), the window holds > 32
+                    while (kids[v][0] >= 0 && L < 40) { v = (uint32_t)kids[v][(uint32_t)(win >> (63 - L)) & 1u]; ++L; }
+                    s = (uint32_t)(uint16_t)kids[v][1] & 0xFF;
                 }
                 win <<= L; avail -= L;
                 pack[q >> 2] |= s << (8 * (q & 3));
@@ -504,15 +483,17 @@ static int huff_pack(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, const b200_
                                                                          reinterpret_cast<uint32_t*>(d_side + L.off_chunk_bits));
     huff_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_side + L.off_chunk_bits), L.nchunks, cpb,
                                                      L.nblocks, P, reinterpret_cast<uint64_t*>(d_side + L.off_block_bits),
-                                                     reinterpret_cast<uint64_t*>(d_side + L.off_block_word),
-                                                     reinterpret_cast<uint64_t*>(d_side + L.off_chunk_off), d_words, words_capacity, info);
+                                                     reinterpret_cast<uint64_t*>(d_side + L.off_block_word), words_capacity, info);
+    huff_chunkoff_kernel<<<(unsigned)((L.nchunks + 255) / 256), 256, 0, ctx->stream>>>(
+        L.nchunks, cpb, P, reinterpret_cast<const uint64_t*>(d_side + L.off_block_word),
+        reinterpret_cast<uint64_t*>(d_side + L.off_chunk_off), d_words, info);
     B200_TIMED_BEGIN(ctx, B200_K_HUFF_ENCODE);
     huff_encode_kernel<<<(unsigned)L.nchunks, 256, 0, ctx->stream>>>(
         d_in, n, cpb, reinterpret_cast<const uint32_t*>(d_side + L.off_codes), d_side + L.off_lens,
         reinterpret_cast<const uint32_t*>(d_side + L.off_meta), reinterpret_cast<const uint32_t*>(d_side + L.off_chunk_bits),
         reinterpret_cast<const uint64_t*>(d_side + L.off_chunk_off), reinterpret_cast<uint32_t*>(d_side + L.off_sub_off), d_words, info);
     B200_TIMED_END(ctx);
-    ctx->launches += 3;
+    ctx->launches += 4;
     CUDA_TRY(cudaGetLastError());
     if (h_total_words || h_worst_status) {
         uint64_t* pin; B200_TRY(b200_pinned(ctx, 16 + L.nblocks * 16, reinterpret_cast<void**>(&pin)));
@@ -558,11 +539,38 @@ extern "C" int b200_huffman_encode_with_codes_dev(b200_ctx* ctx, const uint8_t* 
     B200_TRY(b200_huffman_layout(n, 0, &L));
     if (side_bytes < L.bytes) { B200_SET_ERR("huffman: side buffer too small"); return B200_ERR_CAPACITY; }
     CUDA_TRY(cudaMemsetAsync(d_side, 0, L.off_block_bits, ctx->stream));   // info, freq, codes, lens, tree, meta
-    uint8_t* pin; B200_TRY(b200_pinned(ctx, 2048, reinterpret_cast<void**>(&pin)));
+    uint8_t* pin; B200_TRY(b200_pinned(ctx, 4096, reinterpret_cast<void**>(&pin)));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // the pinned staging area may still be in flight
     memcpy(pin + 256, h_codes, 1024); memcpy(pin + 1280, h_lens, 256);
     CUDA_TRY(cudaMemcpyAsync(d_side + L.off_codes, pin + 256, 1024, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(d_side + L.off_lens, pin + 1280, 256, cudaMemcpyHostToDevice, ctx->stream));
+    {   // the decoder walks a tree: rebuild it from the code table (root = node 0, leaf = {-1, symbol})
+        int16_t* kids = reinterpret_cast<int16_t*>(pin + 1536);
+        int nn = 1; kids[0] = kids[1] = -2;   // -2 = no child yet
+        for (int sym = 0; sym < 256; ++sym) {
+            const int len = h_lens[sym];
+            if (!len) continue;
+            if (len > 32) { B200_SET_ERR("huffman: code of symbol %d is longer than 32 bits", sym); return B200_ERR_ARG; }
+            int v = 0;
+            for (int bit = len - 1; bit >= 0; --bit) {
+                if (kids[2 * v] == -1) { B200_SET_ERR("huffman: the code table is not prefix free"); return B200_ERR_ARG; }
+                int16_t* nx = &kids[2 * v + ((h_codes[sym] >> bit) & 1)];
+                if (*nx < 0) {
+                    if (nn >= 511) { B200_SET_ERR("huffman: the code table needs more than 511 tree nodes"); return B200_ERR_ARG; }
+                    *nx = (int16_t)nn; kids[2 * nn] = kids[2 * nn + 1] = -2; ++nn;
+                }
+                v = *nx;
+            }
+            if (kids[2 * v] != -2 || kids[2 * v + 1] != -2) { B200_SET_ERR("huffman: the code table is not prefix free"); return B200_ERR_ARG; }
+            kids[2 * v] = -1; kids[2 * v + 1] = (int16_t)sym;
+        }
+        // an inner node with one missing child: point it at itself's sibling-less side as a leaf of symbol 0 so walks terminate
+        for (int v = 0; v < nn; ++v) if (kids[2 * v] != -1) for (int c = 0; c < 2; ++c) if (kids[2 * v + c] == -2) {
+            if (nn >= 511) { B200_SET_ERR("huffman: the code table needs more than 511 tree nodes"); return B200_ERR_ARG; }
+            kids[2 * v + c] = (int16_t)nn; kids[2 * nn] = -1; kids[2 * nn + 1] = 0; ++nn;
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_side + L.off_tree, kids, (size_t)nn * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
     const uint32_t tpb = (uint32_t)((L.chunks_per_block + TILE_CHUNKS - 1) / TILE_CHUNKS);
     byte_hist_kernel<<<tpb, 256, 0, ctx->stream>>>(d_in, n, eff_block(n, 0), tpb, reinterpret_cast<uint32_t*>(d_side + L.off_freq));
     huff_check_codes_kernel<<<1, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_side + L.off_freq), d_side + L.off_lens,
@@ -585,7 +593,8 @@ extern "C" int b200_huffman_decode_dev(b200_ctx* ctx, const uint32_t* d_words, u
     const uint32_t tpb = (cpb + TILE_CHUNKS - 1) / TILE_CHUNKS;
     B200_TIMED_BEGIN(ctx, B200_K_HUFF_DECODE);
     huff_decode_kernel<<<(unsigned)(L.nblocks * tpb), 256, 0, ctx->stream>>>(
-        d_words, total_words, n, bs, cpb, tpb, reinterpret_cast<const uint32_t*>(d_side + L.off_codes), d_side + L.off_lens,
+        d_words, total_words, n, bs, cpb, tpb, reinterpret_cast<const int16_t*>(d_side + L.off_tree),
+        reinterpret_cast<const uint32_t*>(d_side + L.off_meta),
         reinterpret_cast<const uint64_t*>(d_side + L.off_chunk_off), reinterpret_cast<const uint32_t*>(d_side + L.off_sub_off), d_out);
     B200_TIMED_END(ctx);
     ctx->launches += 1;

@@ -197,15 +197,9 @@ __global__ void __launch_bounds__(1024) lz77_offsets_kernel(const uint64_t* __re
                                                             uint64_t* __restrict__ block_off, uint64_t capacity,
                                                             uint64_t* __restrict__ info) {
     __shared__ uint64_t warp_tot[33];
-    uint64_t carry = 0, tot;
-    for (uint64_t base = 0; base < nblocks; base += 1024) {
-        const uint64_t b = base + threadIdx.x;
-        const uint64_t v = b < nblocks ? block_bytes[b] : 0;
-        const uint64_t ex = cta_scan_step(v, warp_tot, &tot);
-        if (b < nblocks) block_off[b] = carry + ex;
-        carry += tot;
-    }
-    if (threadIdx.x == 0) { block_off[nblocks] = carry; info[0] = carry; info[1] = carry > capacity ? 1 : 0; }
+    const uint64_t total = cta_exscan_1024(nblocks, warp_tot,
+        [&](uint64_t b) { return block_bytes[b]; }, [&](uint64_t b, uint64_t ex) { block_off[b] = ex; });
+    if (threadIdx.x == 0) { block_off[nblocks] = total; info[0] = total; info[1] = total > capacity ? 1 : 0; }
 }
 
 // ------------------------------------------------------------------ compaction
