@@ -53,7 +53,14 @@ struct b200_ctx {
     cudaEvent_t  ev_a[kTimed], ev_b[kTimed];
     int          ev_kind[kTimed];
     int          ev_created, ev_used;
+    // copy streams + events of the host-buffer entry points (host_api.cu): input chunks are copied
+    // in on s_in, results copied out on s_out, while the codec kernels run on `stream`
+    static const int kPipe = 16;
+    cudaStream_t s_in, s_out;
+    cudaEvent_t  ev_in[kPipe], ev_done[kPipe];
+    bool         pipe_ready;
 };
+int b200_pipe_init(b200_ctx* ctx);
 
 int b200_scratch(b200_ctx* ctx, int slot, size_t bytes, void** out);
 int b200_pinned(b200_ctx* ctx, size_t bytes, void** out);

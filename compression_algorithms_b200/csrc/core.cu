@@ -40,8 +40,24 @@ extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
     for (int i = 0; i < b200_ctx::kSlots; ++i) if (ctx->buf[i]) cudaFree(ctx->buf[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < ctx->ev_created; ++i) { cudaEventDestroy(ctx->ev_a[i]); cudaEventDestroy(ctx->ev_b[i]); }
+    if (ctx->pipe_ready) {
+        for (int i = 0; i < b200_ctx::kPipe; ++i) { cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_done[i]); }
+        cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+int b200_pipe_init(b200_ctx* ctx) {
+    if (ctx->pipe_ready) return B200_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < b200_ctx::kPipe; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+    }
+    ctx->pipe_ready = true;
+    return B200_OK;
 }
 
 extern "C" int b200_ctx_sync(b200_ctx* ctx) {

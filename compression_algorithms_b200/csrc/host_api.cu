@@ -17,44 +17,120 @@ extern "C" uint64_t b200_lz77_max_bytes(int variant, uint64_t n, uint64_t block_
     return lz_cap(variant, n, nblocks);
 }
 
+// Blocks per pipeline chunk: a multiple of the SM count (the shared-memory match finder runs one
+// block per SM at a time) and at most kPipe chunks.
+static uint64_t lz_chunk_blocks(const b200_ctx* ctx, uint64_t nblocks) {
+    const uint64_t sms = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
+    if (nblocks < 4 * sms) return nblocks;                       // too small to be worth splitting
+    uint64_t per = (nblocks + 7) / 8;                            // aim at 8 chunks
+    per = (per + sms - 1) / sms * sms;
+    while ((nblocks + per - 1) / per > (uint64_t)b200_ctx::kPipe) per += sms;
+    return per;
+}
+
+// Compress from / to HOST buffers. The input is copied in chunk by chunk on its own stream, every
+// chunk is compressed as soon as it has landed, and its tokens are copied out on a third stream
+// while the next chunk is being compressed: H2D, kernels and D2H overlap.
 extern "C" int b200_lz77_compress_host(b200_ctx* ctx, int variant, const uint8_t* h_in, uint64_t n, uint64_t block_size,
                                        uint8_t* h_out, uint64_t out_capacity, uint64_t* h_block_sizes,
                                        uint64_t* h_block_off, uint64_t* h_total_bytes) {
     if (n == 0) { if (h_block_off) h_block_off[0] = 0; if (h_total_bytes) *h_total_bytes = 0; return B200_OK; }
+    if (variant != 0 && variant != 1) { B200_SET_ERR("lz77: variant must be 0 or 1"); return B200_ERR_ARG; }
     const uint64_t bs = lz_bs(n, block_size);
     const uint64_t nblocks = (n + bs - 1) / bs;
     const uint64_t cap = lz_cap(variant, n, nblocks);
-    uint8_t *d_in, *d_out; uint64_t* d_idx;
+    B200_TRY(b200_pipe_init(ctx));
+    const uint64_t per = lz_chunk_blocks(ctx, nblocks);
+    const uint64_t nchunks = (nblocks + per - 1) / per;
+    uint8_t *d_in, *d_out; uint64_t* d_idx; uint64_t* pin;
     B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
-    B200_TRY(b200_scratch(ctx, 9, cap, reinterpret_cast<void**>(&d_out)));
-    B200_TRY(b200_scratch(ctx, 10, (2 * nblocks + 2) * 8, reinterpret_cast<void**>(&d_idx)));
-    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_scratch(ctx, 9, cap + 128 * (nchunks + 1), reinterpret_cast<void**>(&d_out)));
+    B200_TRY(b200_scratch(ctx, 10, (2 * nblocks + 2 * nchunks + 2) * 8, reinterpret_cast<void**>(&d_idx)));
+    B200_TRY(b200_pinned(ctx, 64 + nchunks * 16, reinterpret_cast<void**>(&pin)));
+    uint64_t* d_sizes = d_idx;                       // [nblocks]
+    uint64_t* d_boff = d_idx + nblocks;              // per chunk: blocks_c + 1 chunk-local offsets
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));    // scratch and pinned staging are free again
+    // 1. all input copies are queued at once; a chunk's kernels wait only for their own chunk
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const uint64_t o = c * per * bs, len = o + per * bs < n ? per * bs : n - o;
+        CUDA_TRY(cudaMemcpyAsync(d_in + o, h_in + o, len, cudaMemcpyHostToDevice, ctx->s_in));
+        CUDA_TRY(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+    }
+    // 2. kernels, chunk by chunk, each into its own worst-case slot of d_out
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const uint64_t b0 = c * per, nb = b0 + per < nblocks ? per : nblocks - b0;
+        const uint64_t o = b0 * bs, len = o + nb * bs < n ? nb * bs : n - o;
+        const uint64_t slot = lz_cap(variant, b0 * bs, b0) + 128 * c;  // worst cases are additive over chunks; 128 covers the rounding
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0));
+        B200_TRY(b200_lz77_encode_dev(ctx, variant, d_in + o, len, bs, d_out + slot, lz_cap(variant, len, nb), d_sizes + b0,
+                                      d_boff + b0 + c, nullptr));
+        CUDA_TRY(cudaMemcpyAsync(pin + 8 + c, d_boff + b0 + c + nb, 8, cudaMemcpyDeviceToHost, ctx->stream));   // chunk total
+        CUDA_TRY(cudaEventRecord(ctx->ev_done[c], ctx->stream));
+    }
+    // 3. as each chunk finishes, its tokens go home while later chunks are still being compressed
     uint64_t total = 0;
-    B200_TRY(b200_lz77_encode_dev(ctx, variant, d_in, n, block_size, d_out, cap, d_idx, d_idx + nblocks, &total));
-    if (total > out_capacity) { B200_SET_ERR("lz77: output needs %llu bytes, buffer has %llu", (unsigned long long)total, (unsigned long long)out_capacity); return B200_ERR_CAPACITY; }
-    CUDA_TRY(cudaMemcpyAsync(h_out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
-    if (h_block_sizes) CUDA_TRY(cudaMemcpyAsync(h_block_sizes, d_idx, nblocks * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (h_block_off) CUDA_TRY(cudaMemcpyAsync(h_block_off, d_idx + nblocks, (nblocks + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = B200_OK;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const uint64_t b0 = c * per, nb = b0 + per < nblocks ? per : nblocks - b0;
+        const uint64_t slot = lz_cap(variant, b0 * bs, b0) + 128 * c;
+        CUDA_TRY(cudaEventSynchronize(ctx->ev_done[c]));
+        const uint64_t tc = pin[8 + c];
+        if (total + tc > out_capacity) { rc = B200_ERR_CAPACITY; total += tc; continue; }
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(h_out + total, d_out + slot, tc, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (h_block_sizes) CUDA_TRY(cudaMemcpyAsync(h_block_sizes + b0, d_sizes + b0, nb * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (h_block_off) CUDA_TRY(cudaMemcpyAsync(h_block_off + b0, d_boff + b0 + c, nb * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        pin[8 + nchunks + c] = total;                // base of this chunk in the final stream
+        total += tc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (h_total_bytes) *h_total_bytes = total;
+    if (rc != B200_OK) { B200_SET_ERR("lz77: output needs %llu bytes, buffer has %llu", (unsigned long long)total, (unsigned long long)out_capacity); return rc; }
+    if (h_block_off) {                               // chunk-local offsets -> offsets in the concatenated stream
+        for (uint64_t c = 1; c < nchunks; ++c) {
+            const uint64_t b0 = c * per, nb = b0 + per < nblocks ? per : nblocks - b0, base = pin[8 + nchunks + c];
+            for (uint64_t j = 0; j < nb; ++j) h_block_off[b0 + j] += base;
+        }
+        h_block_off[nblocks] = total;
+    }
     return B200_OK;
 }
 
+// Decompress from / to HOST buffers with the same three-stream overlap (all sizes are known on the host).
 extern "C" int b200_lz77_decompress_host(b200_ctx* ctx, int variant, const uint8_t* h_stream, uint64_t stream_bytes,
                                          const uint64_t* h_block_off, const uint64_t* h_block_sizes,
                                          uint64_t n, uint64_t block_size, uint8_t* h_out) {
     if (n == 0) return B200_OK;
     const uint64_t bs = lz_bs(n, block_size);
     const uint64_t nblocks = (n + bs - 1) / bs;
+    B200_TRY(b200_pipe_init(ctx));
+    const uint64_t per = lz_chunk_blocks(ctx, nblocks);
+    const uint64_t nchunks = (nblocks + per - 1) / per;
     uint8_t *d_stream, *d_out; uint64_t* d_idx;
     B200_TRY(b200_scratch(ctx, 9, stream_bytes + 64, reinterpret_cast<void**>(&d_stream)));
     B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_out)));
     B200_TRY(b200_scratch(ctx, 10, (2 * nblocks + 2) * 8, reinterpret_cast<void**>(&d_idx)));
-    CUDA_TRY(cudaMemcpyAsync(d_stream, h_stream, stream_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_idx, h_block_sizes, nblocks * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_idx + nblocks, h_block_off, (nblocks + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    B200_TRY(b200_lz77_decode_dev(ctx, variant, d_stream, d_idx + nblocks, d_idx, n, block_size, d_out));
-    CUDA_TRY(cudaMemcpyAsync(h_out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_idx, h_block_sizes, nblocks * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    CUDA_TRY(cudaMemcpyAsync(d_idx + nblocks, h_block_off, (nblocks + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const uint64_t b0 = c * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
+        const uint64_t s0 = h_block_off[b0], s1 = b1 < nblocks ? h_block_off[b1] : stream_bytes;
+        if (s1 < s0 || s1 > stream_bytes) { B200_SET_ERR("lz77: block offsets are not monotone / exceed the stream"); return B200_ERR_FORMAT; }
+        CUDA_TRY(cudaMemcpyAsync(d_stream + s0, h_stream + s0, s1 - s0, cudaMemcpyHostToDevice, ctx->s_in));
+        CUDA_TRY(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+    }
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const uint64_t b0 = c * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
+        const uint64_t o = b0 * bs, len = b1 * bs < n ? (b1 - b0) * bs : n - o;
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0));
+        B200_TRY(b200_lz77_decode_dev(ctx, variant, d_stream, d_idx + nblocks + b0, d_idx + b0, len, bs, d_out + o));
+        CUDA_TRY(cudaEventRecord(ctx->ev_done[c], ctx->stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(h_out + o, d_out + o, len, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }

@@ -189,3 +189,31 @@ def test_match_finder_candidates(ctx, ob, variant):
                     l += 1
                 want = (p - m) | (l << 16)
             assert int(tok[b, p]) == want, "block %d position %d" % (b, p)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,block", [(700 * 65536 + 321, 65536), (1000, 65536), (300_000, 0)])
+def test_host_pipeline_matches_device(ctx, variant, n, block):
+    """b200_lz77_compress_host / _decompress_host (chunked, three streams: H2D, kernels, D2H overlapped)
+    give the same stream, sizes and offsets as the device-resident call, and round-trip."""
+    import ctypes as C
+    import torch
+    from compression_algorithms_b200 import _lib, corpus, device as dv
+    lib = _lib.core()
+    data = corpus.generate(n, 0, 3)
+    nb = 1 if block == 0 else (n + block - 1) // block
+    cap = int(lib.b200_lz77_max_bytes(variant, n, block))
+    h_in = torch.from_numpy(data.copy()).pin_memory()
+    h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    sizes = np.zeros(nb, dtype=np.uint64); off = np.zeros(nb + 1, dtype=np.uint64); tot = C.c_uint64(0)
+    _lib.check(lib.b200_lz77_compress_host(ctx.handle, variant, h_in.data_ptr(), n, block, h_out.data_ptr(), cap,
+                                           sizes.ctypes.data, off.ctypes.data, C.byref(tot)))
+    st = dv.lz77_encode(ctx, h_in.to(ctx.device), variant, block)
+    assert st.total_bytes == tot.value
+    assert np.array_equal(st.out[: st.total_bytes].cpu().numpy(), h_out.numpy()[: tot.value])
+    assert np.array_equal(st.block_off.cpu().numpy().astype(np.uint64), off)
+    assert np.array_equal(st.block_sizes.cpu().numpy().astype(np.uint64), sizes)
+    h_dec = torch.empty(n, dtype=torch.uint8).pin_memory()
+    _lib.check(lib.b200_lz77_decompress_host(ctx.handle, variant, h_out.data_ptr(), tot.value, off.ctypes.data, sizes.ctypes.data,
+                                             n, block, h_dec.data_ptr()))
+    assert np.array_equal(h_dec.numpy(), data)
