@@ -198,6 +198,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
 
         PHASE_STAMP(0);
         // ---------------- P1: no-expiry occupancy (order independent) by atomic linear probing
+        // (a per-home "frontier hint" table that lets later walks skip the full words of a hot chain was
+        // tried and did not pay: 175 K -> 190 K cycles; the phase is bound by the latency of the
+        // dependent hash -> read -> atomicOr chain of the 64 positions each thread owns)
         for (uint32_t i = tid; i < len; i += NTHREADS) {
             uint32_t s = lz_hash(sm_word(data, i));
             for (;;) {
@@ -452,10 +455,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
 
         PHASE_STAMP(4);
         // ---------------- P5: greedy parse. adv[p] = bytes consumed by the token that would start at p
-        for (uint32_t i = tid; i < len; i += NTHREADS) {
-            const uint32_t t = tokb[i];
-            if (dbg_tok) dbg_tok[(uint64_t)b * MAXB + i] = t;
-            adv[i] = (uint8_t)((t >> 16) ? (t >> 16) : 1u);
+        for (uint32_t i0 = tid; i0 < len; i0 += 8 * NTHREADS) {   // eight independent reads in flight per thread
+            uint32_t tv[8];
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) { const uint32_t i = i0 + k * NTHREADS; tv[k] = i < len ? tokb[i] : 0u; }
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) {
+                const uint32_t i = i0 + k * NTHREADS;
+                if (i < len) {
+                    if (dbg_tok) dbg_tok[(uint64_t)b * MAXB + i] = tv[k];
+                    adv[i] = (uint8_t)((tv[k] >> 16) ? (tv[k] >> 16) : 1u);
+                }
+            }
         }
         __syncthreads();
         const uint32_t nchunks = (len + 63) >> 6;
