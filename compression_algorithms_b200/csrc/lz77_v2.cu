@@ -43,6 +43,7 @@ constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint32_t MAXB = 65536;                             // max block bytes on this path
 constexpr uint32_t NTHREADS = 1024;
 constexpr uint32_t NR = 32;                                  // ranges == warps
+constexpr uint32_t HOT_WEIGHT = 1024;                         // extra cost of a fully occupied bitmap word when balancing the ranges (swept 96..16384 on B200: 1024 best)
 
 // shared memory layout (bytes)
 constexpr uint32_t OFF_DATA = 0;
@@ -221,13 +222,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         // ---------------- P2: rank prefix per 8-word chunk, range cuts, special cluster bounds
         {
             // thread t owns chunks [5t, 5t+5)
-            uint32_t c0 = tid * 5, mine = 0;
-            uint32_t part[5];
+            uint32_t c0 = tid * 5, mine = 0, mine_cost = 0;
+            uint32_t part[5], cost[5];
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                uint32_t s = 0;
-                if (c0 + k < PRE_N) for (uint32_t w = 0; w < PRE_CHUNK; ++w) s += __popc(bm[(c0 + k) * PRE_CHUNK + w]);
+                uint32_t s = 0, full = 0;
+                if (c0 + k < PRE_N) for (uint32_t w = 0; w < PRE_CHUNK; ++w) { const uint32_t x = bm[(c0 + k) * PRE_CHUNK + w]; s += __popc(x); full += x == 0xFFFFFFFFu; }
                 part[k] = s; mine += s;
+                cost[k] = s + HOT_WEIGHT * full; mine_cost += cost[k];   // entries of long chains cost several times the others
             }
             const uint32_t incl = warp_incl_scan_u32(mine);
             if (lane == 31) ms->scan[warp] = incl;
@@ -241,16 +243,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             uint32_t run = ms->scan[warp] + incl - mine;
 #pragma unroll
             for (int k = 0; k < 5; ++k) { if (c0 + k < PRE_N) pre[c0 + k] = run; run += part[k]; }
-            if (tid < NR) {
-                uint32_t s = tid << 15;   // first free slot at/after the slice start, a word at a time
+            // range cuts: the 32 ranges get equal shares of the estimated simulation cost, each cut moved up to
+            // the next cluster end (clusters never interact). Cost = entries + HOT_WEIGHT per fully occupied
+            // bitmap word, so that a hot chain ends up (almost) alone in its warp instead of on top of a full share.
+            const uint32_t cincl = warp_incl_scan_u32(mine_cost);
+            __syncthreads();
+            if (lane == 31) ms->scan[warp] = cincl;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t t = ms->scan[lane];
+                const uint32_t ti = warp_incl_scan_u32(t);
+                ms->scan[lane] = ti - t;
+                if (lane == 31) ms->scan[32] = ti;
+            }
+            __syncthreads();
+            {
+                const uint64_t ctot = ms->scan[32];
+                uint64_t crun = (uint64_t)ms->scan[warp] + cincl - mine_cost;
+#pragma unroll 1
+                for (int k = 0; k < 5; ++k) {
+                    if (cost[k] && c0 + k < PRE_N) {
+                        uint32_t r = (uint32_t)((crun * NR + ctot - 1) / ctot);      // first quantile at/after this chunk's start
+                        if (r == 0) r = 1;
+                        while (r < NR && ctot * r < (crun + cost[k]) * NR) {
+                            uint32_t sl = (c0 + k) * PRE_CHUNK * 32;                 // first free slot at/after the chunk start
+                            for (;;) {
+                                const uint32_t z = ~bm[sl >> 5] & (0xFFFFFFFFu << (sl & 31));
+                                if (z) { sl = (sl & ~31u) + (uint32_t)(__ffs(z) - 1); break; }
+                                sl = (sl & ~31u) + 32;
+                                if (sl >= SLOTS + GUARD_BITS) break;
+                            }
+                            ms->cut[r] = sl;
+                            ++r;
+                        }
+                    }
+                    crun += cost[k];
+                }
+            }
+            if (tid == 0) {
+                uint32_t s = 0;   // cut[0]: end of the cluster that touches slot 0
                 for (;;) {
-                    const uint32_t wi = s >> 5;
-                    const uint32_t z = ~bm[wi] & (0xFFFFFFFFu << (s & 31));
-                    if (z) { s = (wi << 5) + (uint32_t)(__ffs(z) - 1); break; }
-                    s = (wi + 1) << 5;
+                    const uint32_t z = ~bm[s >> 5];
+                    if (z) { s += (uint32_t)(__ffs(z) - 1); break; }
+                    s += 32;
                     if (s >= SLOTS + GUARD_BITS) break;
                 }
-                ms->cut[tid] = s;
+                ms->cut[0] = s;
             }
             if (tid == NR) {
                 ms->cut[NR] = SLOTS + GUARD_BITS;
@@ -284,8 +322,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             const uint32_t i = base + lane;
             if (i < p_hi) {
                 const uint32_t h = lz_hash(sm_word(data, i));
-                uint32_t r = h >> 15;
-                while (r > 0 && h < ms->cut[r]) --r;
+                uint32_t r = 0;             // largest r with cut[r] <= h (0 also for the cluster below cut[0])
+#pragma unroll
+                for (uint32_t st = 16; st > 0; st >>= 1) if (ms->cut[r + st] <= h) r += st;
                 if (V == 1 && h >= top_start) r = 0;
                 atomicAdd(&ms->cnt[warp][r], 1u);
             }
@@ -317,8 +356,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             uint32_t r = 0xFFu, c = 0;
             if (valid) {
                 const uint32_t h = lz_hash(sm_word(data, i));
-                r = h >> 15;
-                while (r > 0 && h < ms->cut[r]) --r;
+                r = 0;
+#pragma unroll
+                for (uint32_t st = 16; st > 0; st >>= 1) if (ms->cut[r + st] <= h) r += st;
                 if (V == 1 && h >= top_start) r = 0;
                 c = bm_rank(bm, pre, h);
             }
