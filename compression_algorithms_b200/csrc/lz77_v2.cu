@@ -223,13 +223,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         {
             // thread t owns chunks [5t, 5t+5)
             uint32_t c0 = tid * 5, mine = 0, mine_cost = 0;
-            uint32_t part[5], cost[5];
+            uint32_t part[5], cost[5], fullw[7];   // fullw[j]: fully occupied words of chunk c0 - 1 + j
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const uint32_t ch = c0 + j - 1;     // wraps for c0 == 0, j == 0: out of range, counts 0
+                uint32_t s = 0, full = 0;
+                if (ch < PRE_N) for (uint32_t w = 0; w < PRE_CHUNK; ++w) { const uint32_t x = bm[ch * PRE_CHUNK + w]; s += __popc(x); full += x == 0xFFFFFFFFu; }
+                fullw[j] = full;
+                if (j >= 1 && j <= 5) { part[j - 1] = s; mine += s; }
+            }
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                uint32_t s = 0, full = 0;
-                if (c0 + k < PRE_N) for (uint32_t w = 0; w < PRE_CHUNK; ++w) { const uint32_t x = bm[(c0 + k) * PRE_CHUNK + w]; s += __popc(x); full += x == 0xFFFFFFFFu; }
-                part[k] = s; mine += s;
-                cost[k] = s + HOT_WEIGHT * full; mine_cost += cost[k];   // entries of long chains cost several times the others
+                // a long chain costs several times its entries; its weight is booked on the chunks on either side
+                // of it so that the cost quantiles (the cuts) pile up just before and just after it
+                cost[k] = c0 + k < PRE_N ? part[k] + (HOT_WEIGHT / 2) * (fullw[k] + fullw[k + 2]) : 0u;
+                mine_cost += cost[k];
             }
             const uint32_t incl = warp_incl_scan_u32(mine);
             if (lane == 31) ms->scan[warp] = incl;
