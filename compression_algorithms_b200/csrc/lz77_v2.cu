@@ -43,7 +43,8 @@ constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint32_t MAXB = 65536;                             // max block bytes on this path
 constexpr uint32_t NTHREADS = 1024;
 constexpr uint32_t NR = 32;                                  // ranges == warps
-constexpr uint32_t HOT_WEIGHT = 1024;                         // extra cost of a fully occupied bitmap word when balancing the ranges (swept 96..16384 on B200: 1024 best)
+constexpr uint32_t CROWD_MIN = 12;                           // same-home entries in a batch from which the slot-ordered placement is used
+constexpr uint32_t HOT_MIN_WORDS = 7;                         // fully occupied words (of 8) in a 256-slot chunk from which its chain counts as hot (swept 2..8 on B200)
 
 // shared memory layout (bytes)
 constexpr uint32_t OFF_DATA = 0;
@@ -67,6 +68,7 @@ struct Misc {
     uint32_t cut[NR + 1];
     uint32_t top_start, sp_lo_end, sp_hi_start, pad0;
     uint32_t rstart[NR + 1];
+    uint32_t fcut[16], nfcut;    // cuts forced just before / after a hot chain
     uint32_t cnt[NR][NR];        // [warp][range]
     uint32_t clr[64];            // slot-0 clear times (warp 0)
     uint8_t  sexit[NR][32];      // super-chunk exit functions
@@ -232,12 +234,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 fullw[j] = full;
                 if (j >= 1 && j <= 5) { part[j - 1] = s; mine += s; }
             }
+            // Range cuts. A chunk with HOT_MIN_WORDS fully occupied bitmap words belongs to the chain of a hot
+            // 4-gram: such a chain gets a cut just before and just after it, so that it sits (almost) alone in a
+            // warp whose batches are then "crowded" and take the slot-ordered placement of P4. The remaining
+            // cuts give the other ranges equal numbers of ordinary entries. Every cut is moved up to the next
+            // cluster end (clusters never interact).
+            auto free_at_or_after = [&](uint32_t sl) {
+                for (;;) {
+                    const uint32_t z = ~bm[sl >> 5] & (0xFFFFFFFFu << (sl & 31));
+                    if (z) return (sl & ~31u) + (uint32_t)(__ffs(z) - 1);
+                    sl = (sl & ~31u) + 32;
+                    if (sl >= SLOTS + GUARD_BITS) return sl;
+                }
+            };
+            if (tid == 0) ms->nfcut = 0;
+            if (tid >= 1 && tid < NR) ms->cut[tid] = SLOTS + GUARD_BITS;   // a cut nobody sets leaves an empty range
+            __syncthreads();
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                // a long chain costs several times its entries; its weight is booked on the chunks on either side
-                // of it so that the cost quantiles (the cuts) pile up just before and just after it
-                cost[k] = c0 + k < PRE_N ? part[k] + (HOT_WEIGHT / 2) * (fullw[k] + fullw[k + 2]) : 0u;
+                const bool hot = fullw[k + 1] >= HOT_MIN_WORDS, hot_prev = fullw[k] >= HOT_MIN_WORDS, hot_next = fullw[k + 2] >= HOT_MIN_WORDS;
+                cost[k] = (c0 + k < PRE_N && !hot) ? part[k] : 0u;
                 mine_cost += cost[k];
+                if (hot && c0 + k < PRE_N) {
+                    if (!hot_prev && c0 + k >= 1) { const uint32_t i = atomicAdd(&ms->nfcut, 1u); if (i < 16) ms->fcut[i] = free_at_or_after((c0 + k - 1) * PRE_CHUNK * 32); }
+                    if (!hot_next && c0 + k + 1 < PRE_N) { const uint32_t i = atomicAdd(&ms->nfcut, 1u); if (i < 16) ms->fcut[i] = free_at_or_after((c0 + k + 1) * PRE_CHUNK * 32); }
+                }
             }
             const uint32_t incl = warp_incl_scan_u32(mine);
             if (lane == 31) ms->scan[warp] = incl;
@@ -251,9 +272,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             uint32_t run = ms->scan[warp] + incl - mine;
 #pragma unroll
             for (int k = 0; k < 5; ++k) { if (c0 + k < PRE_N) pre[c0 + k] = run; run += part[k]; }
-            // range cuts: the 32 ranges get equal shares of the estimated simulation cost, each cut moved up to
-            // the next cluster end (clusters never interact). Cost = entries + HOT_WEIGHT per fully occupied
-            // bitmap word, so that a hot chain ends up (almost) alone in its warp instead of on top of a full share.
             const uint32_t cincl = warp_incl_scan_u32(mine_cost);
             __syncthreads();
             if (lane == 31) ms->scan[warp] = cincl;
@@ -265,27 +283,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 if (lane == 31) ms->scan[32] = ti;
             }
             __syncthreads();
+            const uint32_t nforced = ms->nfcut < 16 ? ms->nfcut : 16;
+            const uint32_t nq = NR - nforced;                                    // ranges shared out by entry count
             {
-                const uint64_t ctot = ms->scan[32];
+                const uint64_t ctot = ms->scan[32] ? ms->scan[32] : 1;
                 uint64_t crun = (uint64_t)ms->scan[warp] + cincl - mine_cost;
 #pragma unroll 1
                 for (int k = 0; k < 5; ++k) {
-                    if (cost[k] && c0 + k < PRE_N) {
-                        uint32_t r = (uint32_t)((crun * NR + ctot - 1) / ctot);      // first quantile at/after this chunk's start
+                    if (cost[k]) {
+                        uint32_t r = (uint32_t)((crun * nq + ctot - 1) / ctot);      // first quantile at/after this chunk's start
                         if (r == 0) r = 1;
-                        while (r < NR && ctot * r < (crun + cost[k]) * NR) {
-                            uint32_t sl = (c0 + k) * PRE_CHUNK * 32;                 // first free slot at/after the chunk start
-                            for (;;) {
-                                const uint32_t z = ~bm[sl >> 5] & (0xFFFFFFFFu << (sl & 31));
-                                if (z) { sl = (sl & ~31u) + (uint32_t)(__ffs(z) - 1); break; }
-                                sl = (sl & ~31u) + 32;
-                                if (sl >= SLOTS + GUARD_BITS) break;
-                            }
-                            ms->cut[r] = sl;
-                            ++r;
-                        }
+                        while (r < nq && ctot * r < (crun + cost[k]) * nq) { ms->cut[r] = free_at_or_after((c0 + k) * PRE_CHUNK * 32); ++r; }
                     }
                     crun += cost[k];
+                }
+            }
+            if (tid < nforced) ms->cut[nq + tid] = ms->fcut[tid];
+            __syncthreads();
+            if (tid == 0) {                                                      // 31 cuts from two sources: sort them
+                for (uint32_t i = 2; i < NR; ++i) {
+                    const uint32_t v = ms->cut[i];
+                    uint32_t j = i;
+                    while (j > 1 && ms->cut[j - 1] > v) { ms->cut[j] = ms->cut[j - 1]; --j; }
+                    ms->cut[j] = v;
                 }
             }
             if (tid == 0) {
@@ -447,6 +467,83 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 const uint32_t w = done ? 0u : sm_word(data, q);
                 const uint32_t sig = (w * 0x9E3779B1u) >> 27;   // 5-bit pattern signature for the per-group filter
                 uint32_t fm = NONE; bool pend = true;
+                // ---- crowded batch (many entries with the same home: the chain of a hot 4-gram). The rounds
+                // below would commit about one of them per round. The sequential outcome is instead computed
+                // slot by slot: going through the slots that are dead by the end of the batch in ascending
+                // order, a slot goes to the EARLIEST entry that is still unplaced, whose home is at/before the
+                // slot and for which the slot is already dead -- exactly what the entry itself would have taken,
+                // because every lower dead slot it could reach has by then gone to an earlier entry.
+                {
+                    const uint32_t hp = __match_any_sync(0xffffffffu, done ? (0x80000000u | lane) : kk);
+                    // (valid while no placement of the batch can expire inside the batch: its time span is below W)
+                    const uint32_t q_first = __shfl_sync(0xffffffffu, q, 0), q_last = __shfl_sync(0xffffffffu, q, L - 1);
+                    if (q_last - q_first < W && __any_sync(0xffffffffu, !done && __popc(hp) >= CROWD_MIN)) {
+                        uint16_t* aslot = reinterpret_cast<uint16_t*>(&ms->cnt[warp][0]);   // [32] slot given to lane j (P3 counters are dead)
+                        uint16_t* aqpos = aslot + 32;                                       // [32] position of lane j
+                        const uint32_t home = kk;
+                        const uint32_t home_s = done ? 0xFFFFFFFFu : home, dthr_s = done ? 0xFFFFFFFFu : dthr;
+                        const uint32_t dmax = __shfl_sync(0xffffffffu, dthr, L - 1);        // entries are in time order
+                        uint32_t unplaced = __ballot_sync(0xffffffffu, !done);
+                        uint32_t my_e = NONE;
+                        uint32_t g = 0;
+                        while (unplaced) {
+                            // nothing below the lowest home of an unplaced entry can be taken any more
+                            const uint32_t hmin = __reduce_min_sync(0xffffffffu, ((unplaced >> lane) & 1u) ? home : 0xFFFFFFFFu);
+                            if ((hmin >> 5) > g) g = hmin >> 5;
+                            if (B1[g] > dmax) { ++g; continue; }                            // every slot of the group outlives the batch
+                            const uint32_t sl = (g << 5) + lane;
+                            const uint32_t tv = T[sl];
+                            const uint32_t mn = __reduce_min_sync(0xffffffffu, tv);
+                            if (lane == 0) B1[g] = (uint16_t)mn;
+                            uint32_t lo = 0;                                                // entries for which the slot is still live
+#pragma unroll
+                            for (uint32_t st = 16; st > 0; st >>= 1) {
+                                const uint32_t d = __shfl_sync(0xffffffffu, dthr_s, (lo + st - 1) & 31u);
+                                if (d < tv) lo += st;
+                            }
+                            const uint32_t qmask = lo >= 32 ? 0u : (0xFFFFFFFFu << lo);
+                            uint32_t cm = __ballot_sync(0xffffffffu, tv <= dmax && sl >= hmin && (qmask & unplaced) != 0u);
+                            while (cm && unplaced) {
+                                const int j = __ffs(cm) - 1;
+                                cm &= cm - 1;
+                                const uint32_t sj = (g << 5) + (uint32_t)j;
+                                const uint32_t am = __ballot_sync(0xffffffffu, home_s <= sj);   // entries whose home is at/before the slot
+                                const uint32_t ej = __shfl_sync(0xffffffffu, qmask, j) & am & unplaced;
+                                if (ej) {
+                                    const int pick = __ffs(ej) - 1;
+                                    if ((int)lane == pick) my_e = sj;
+                                    unplaced &= ~(1u << pick);
+                                }
+                            }
+                            ++g;
+                        }
+                        if (!done) { aslot[lane] = (uint16_t)my_e; aqpos[lane] = (uint16_t)q; atomicOr(&S1[my_e >> 5], 1u << sig); }
+                        __syncwarp();
+                        if (!done) {
+                            // find: first slot of [home, my_e) holding the pattern; a slot that was dead before the
+                            // batch has been given to an earlier entry of the batch (its pattern is read from there)
+                            uint32_t k2 = home;
+#pragma unroll 1
+                            while (k2 < my_e) {
+                                if ((k2 & 31u) == 0 && k2 + 32u <= my_e && !((S1[k2 >> 5] >> sig) & 1u)) { k2 += 32; continue; }
+                                const uint32_t v = T[k2];
+                                if (v > dthr) { if (sm_word(data, v - 1) == w) { fm = v - 1; break; } }
+                                else {
+                                    for (uint32_t j = 0; j < lane; ++j) if (aslot[j] == k2) {
+                                        if (sm_word(data, aqpos[j]) == w) fm = aqpos[j];
+                                        break;
+                                    }
+                                    if (fm != NONE) break;
+                                }
+                                ++k2;
+                            }
+                        }
+                        __syncwarp();
+                        if (!done) { if (q != 65535u) T[my_e] = (uint16_t)(q + 1); done = true; }
+                        __syncwarp();
+                        ++st_coop;
+                    }
+                }
                 while (__ballot_sync(0xffffffffu, !done)) {
                     ++st_rounds;
                     t_mark = CLK();

@@ -18,10 +18,13 @@ for variant in (1,):
         print("  %-13s median %8d  p90 %8d  max %8d cycles" % (nm, np.median(dtk), np.percentile(dtk, 90), dtk.max()))
     w = s[:, 8:].reshape(len(s), 32, 4)
     cyc = w[:, :, 0]
-    print("  P4b per-warp cycles (max over lanes): median of max %d, median of median %d, median of min %d" % (np.median(cyc.max(1)), np.median(np.median(cyc, 1)), np.median(cyc.min(1))))
+    print("  P4 per-warp cycles: median of max %d, median of median %d, median of min %d" % (np.median(cyc.max(1)), np.median(np.median(cyc, 1)), np.median(cyc.min(1))))
     b = 3
     order = np.argsort(-cyc[b])
     print("  block %d warps:" % b)
-    for wi in list(order[:6]) + list(order[-3:]):
+    for wi in list(order[:8]) + list(order[-2:]):
         r = w[b, wi]
-        print("    warp %2d: P4b cycles %d (coop part %d) entries %d largest-lane %d big-range entries %d long walks %d" % (wi, r[0], r[2], r[1] & 0xFFFF, r[1] >> 16, r[3] & 0xFFFF, r[3] >> 16))
+        ent, rounds = r[1] & 0xFFFF, r[2] & 0xFFFF
+        print("    warp %2d: cycles %7d entries %4d rounds %4d (%.1f per batch, %d cycles each) walks %d t_walk %dK t_sync %dK group steps %d" % (
+            wi, r[0], ent, rounds, rounds / max(1.0, ent / 32.0), r[0] // max(1, rounds), r[3] & 0xFFFF, r[2] >> 16, r[3] >> 16, r[1] >> 16))
+    print("  max over warps: t_commit %dK t_matchlen %dK" % (s[b, 7] >> 16, s[b, 7] & 0xFFFF))
