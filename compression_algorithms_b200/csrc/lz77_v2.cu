@@ -60,9 +60,13 @@ constexpr uint32_t SMEM_BYTES = OFF_MISC + SZ_MISC;          // 230,544 <= 232,4
 constexpr uint32_t T_ENTRIES = MAXB + 64;
 constexpr uint32_t OFF_T = 0;                                // inside BIG
 constexpr uint32_t OFF_B1 = T_ENTRIES * 2;                   // inside BIG, u16[2052]
-constexpr uint32_t OFF_ADV = 0;                              // inside BIG, u8[MAXB+64]
-constexpr uint32_t OFF_EXIT = MAXB + 64;                     // inside BIG, u8[MAXB]
-constexpr uint32_t OFF_STAGE = MAXB + 64;                    // inside BIG (after adv), u32 words, V0 only
+// adv / exitof are indexed through PADX: every 64-position chunk is followed by 4 pad bytes, so that the
+// phases in which thread t walks chunk t (stride 68 bytes = 17 words) are free of bank conflicts
+constexpr uint32_t PADDED = MAXB + (MAXB >> 6) * 4;          // 69632
+constexpr uint32_t OFF_ADV = 0;                              // inside BIG, u8[PADDED]
+constexpr uint32_t OFF_EXIT = PADDED;                        // inside BIG, u8[PADDED]: 2 * 69632 = 139264 = SZ_BIG
+constexpr uint32_t OFF_STAGE = PADDED;                       // inside BIG (after adv), u32 words, V0 only (may spill ~4 KB into PRE)
+#define PADX(p) ((p) + (((p) >> 6) << 2))
 
 struct Misc {
     uint32_t cut[NR + 1];
@@ -609,7 +613,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 const uint32_t i = i0 + k * NTHREADS;
                 if (i < len) {
                     if (dbg_tok) dbg_tok[(uint64_t)b * MAXB + i] = tv[k];
-                    adv[i] = (uint8_t)((tv[k] >> 16) ? (tv[k] >> 16) : 1u);
+                    adv[PADX(i)] = (uint8_t)((tv[k] >> 16) ? (tv[k] >> 16) : 1u);
                 }
             }
         }
@@ -619,8 +623,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             const uint32_t lo = tid << 6, cend = lo + 64;
             const uint32_t hi = cend < len ? cend : len;
             for (uint32_t p = hi; p-- > lo;) {
-                const uint32_t nx = p + adv[p];
-                exitof[p] = (uint8_t)(nx >= cend ? nx - cend : exitof[nx]);
+                const uint32_t nx = p + adv[PADX(p)];
+                exitof[PADX(p)] = (uint8_t)(nx >= cend ? nx - cend : exitof[PADX(nx)]);
             }
         }
         __syncthreads();
@@ -630,7 +634,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             for (uint32_t k = 0; k < 32; ++k) {
                 const uint32_t ch = s * 32 + k;
                 const uint32_t p = (ch << 6) + e;
-                if (ch < nchunks && p < len && e < 31) e = exitof[p];
+                if (ch < nchunks && p < len && e < 31) e = exitof[PADX(p)];
             }
             ms->sexit[s][lane] = (uint8_t)e;
         }
@@ -647,7 +651,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 const uint32_t ch = warp * 32 + k;
                 centry[ch] = (uint8_t)e;
                 const uint32_t p = (ch << 6) + e;
-                if (ch < nchunks && p < len) e = exitof[p];
+                if (ch < nchunks && p < len) e = exitof[PADX(p)];
             }
         }
         __syncthreads();
@@ -656,16 +660,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         // one position per thread with coalesced reads
         uint8_t* orel = exitof;
         if (V == 1) {
-            for (uint32_t i = tid; i < (MAXB >> 2); i += NTHREADS) reinterpret_cast<uint32_t*>(orel)[i] = 0xFFFFFFFFu;
+            for (uint32_t i = tid; i < (PADDED >> 2); i += NTHREADS) reinterpret_cast<uint32_t*>(orel)[i] = 0xFFFFFFFFu;
             __syncthreads();
         }
         uint32_t my_units = 0;   // bytes (V1) or bits (V0)
         if (tid < nchunks) {
             const uint32_t cend = (tid << 6) + 64;
             const uint32_t hi = cend < len ? cend : len;
-            for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[p]) {
-                const bool lit = adv[p] == 1;   // matches are at least 4 long
-                if (V == 1) orel[p] = (uint8_t)(my_units >> 1);
+            for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[PADX(p)]) {
+                const bool lit = adv[PADX(p)] == 1;   // matches are at least 4 long
+                if (V == 1) orel[PADX(p)] = (uint8_t)(my_units >> 1);
                 my_units += V ? (lit ? 2u : 4u) : (lit ? 9u : 19u);
             }
         }
@@ -700,7 +704,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 for (uint32_t k = 0; k < 4; ++k) {
                     const uint32_t p = p0 + k * NTHREADS;
                     if (p >= len) break;
-                    const uint32_t r = orel[p];
+                    const uint32_t r = orel[PADX(p)];
                     if (r == 0xFFu) continue;     // not a token start of the greedy parse
                     const uint32_t o = coff[p >> 6] + 2u * r, t = tk[k];
                     if (t == 0) *reinterpret_cast<uint16_t*>(out + o) = (uint16_t)((uint32_t)data[p] << 8);
@@ -724,7 +728,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 uint32_t wi = my_off >> 5, have = my_off & 31;
                 bool first = have != 0;
                 uint64_t acc = 0;
-                for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[p]) {
+                for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[PADX(p)]) {
                     const uint32_t t = tokb[p];
                     uint32_t v, nb;
                     if (t == 0) { v = (uint32_t)data[p] << 1; nb = 9; }
