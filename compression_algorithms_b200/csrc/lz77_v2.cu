@@ -423,12 +423,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             uint32_t qh = 0, qt = 0;                       // slot-0 clear queue (only warp 0 ever uses it)
             if (warp == 0) { if (lane == 0) ms->clr[0] = W - 1; qt = 1; }
             __syncwarp();
+            // the list entries cur .. cur+31 (ent) and cur+32 .. cur+63 (pf) are kept in registers, pf being
+            // re-read right after every advance: the L2 latency of the list stays off the critical path
+            uint32_t ent = cur + lane < end ? lists[cur + lane] : 0u;
+            uint32_t pf = cur + 32 + lane < end ? lists[cur + 32 + lane] : 0u;
+            auto advance = [&](uint32_t by) {
+                const uint32_t a = __shfl_sync(0xffffffffu, ent, (lane + by) & 31u), c = __shfl_sync(0xffffffffu, pf, (lane + by) & 31u);
+                ent = lane + by < 32 ? a : c;
+                cur += by;
+                pf = cur + 32 + lane < end ? lists[cur + 32 + lane] : 0u;
+            };
             while (cur < end) {
                 const uint32_t lanes = end - cur < 32 ? end - cur : 32;
                 uint32_t q = 0, kk = 0;
                 bool special = false;
                 if (lane < lanes) {
-                    const uint32_t ent = lists[cur + lane];
                     q = ent & 0xFFFFu; kk = ent >> 16;
                     special = kk < sp_lo_end || kk >= sp_hi_start;
                 }
@@ -461,7 +470,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                         tokb[q0] = tk;
                     }
                     qh = __shfl_sync(0xffffffffu, qh, 0); qt = __shfl_sync(0xffffffffu, qt, 0);
-                    cur += 1;
+                    advance(1);
                     __syncwarp();
                     continue;
                 }
@@ -478,10 +487,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 // slot and for which the slot is already dead -- exactly what the entry itself would have taken,
                 // because every lower dead slot it could reach has by then gone to an earlier entry.
                 {
-                    const uint32_t hp = __match_any_sync(0xffffffffu, done ? (0x80000000u | lane) : kk);
+                    // crowd detection: how many entries share the home of lane 0 / of the middle lane
+                    const uint32_t home_a = __shfl_sync(0xffffffffu, kk, 0), home_b = __shfl_sync(0xffffffffu, kk, L >> 1);
+                    const uint32_t same_a = __ballot_sync(0xffffffffu, !done && kk == home_a);
+                    const uint32_t same_b = __ballot_sync(0xffffffffu, !done && kk == home_b);
                     // (valid while no placement of the batch can expire inside the batch: its time span is below W)
                     const uint32_t q_first = __shfl_sync(0xffffffffu, q, 0), q_last = __shfl_sync(0xffffffffu, q, L - 1);
-                    if (q_last - q_first < W && __any_sync(0xffffffffu, !done && __popc(hp) >= CROWD_MIN)) {
+                    if (q_last - q_first < W && (__popc(same_a) >= CROWD_MIN || __popc(same_b) >= CROWD_MIN)) {
                         uint16_t* aslot = reinterpret_cast<uint16_t*>(&ms->cnt[warp][0]);   // [32] slot given to lane j (P3 counters are dead)
                         uint16_t* aqpos = aslot + 32;                                       // [32] position of lane j
                         const uint32_t home = kk;
@@ -591,7 +603,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                     tokb[q] = tk;
                 }
                 tl += CLK() - t_mark;
-                cur += L;
+                advance(L);
             }
             if (DBG && dbg_stats && lane == 0) {
                 uint32_t* o = dbg_stats + (uint64_t)b * 136 + 8 + warp * 4;
