@@ -107,10 +107,16 @@ __device__ __forceinline__ uint32_t match_len(const uint8_t* data, uint32_t m, u
 }
 
 __device__ __forceinline__ uint32_t bm_rank(const uint32_t* bm, const uint32_t* pre, uint32_t s) {
-    const uint32_t wi = s >> 5;
+    // set bits below slot s: prefix of the 8-word chunk + masked popcounts of the chunk (two 16-byte reads)
+    const uint32_t wi = s >> 5, j = wi & (PRE_CHUNK - 1);
+    const uint4* cp = reinterpret_cast<const uint4*>(bm + (wi & ~(PRE_CHUNK - 1)));
+    const uint4 lo = cp[0], hi = cp[1];
+    const uint32_t wd[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     uint32_t r = pre[wi / PRE_CHUNK];
-    for (uint32_t w = wi & ~(PRE_CHUNK - 1); w < wi; ++w) r += __popc(bm[w]);
-    return r + __popc(bm[wi] & ((1u << (s & 31)) - 1u));
+    const uint32_t below = (1u << (s & 31)) - 1u;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) r += __popc(wd[k] & (k < j ? 0xFFFFFFFFu : (k == j ? below : 0u)));
+    return r;
 }
 
 // Long walks (hot chains). From cursor kk (every slot before it proven live at the lane's time)
@@ -358,6 +364,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
 #pragma unroll
                 for (uint32_t st = 16; st > 0; st >>= 1) if (ms->cut[r + st] <= h) r += st;
                 if (V == 1 && h >= top_start) r = 0;
+                tokb[i] = h | (r << 21);    // kept for pass 2 (the token array is free until P4)
                 atomicAdd(&ms->cnt[warp][r], 1u);
             }
         }
@@ -382,18 +389,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         }
         __syncthreads();
         // pass 2: ordered scatter (warp = contiguous time slice, lanes in position order)
+        uint32_t hr_next = p_lo + lane < p_hi ? tokb[p_lo + lane] : 0u;
         for (uint32_t base = p_lo; base < p_hi; base += 32) {
             const uint32_t i = base + lane;
             const bool valid = i < p_hi;
+            const uint32_t hr = hr_next;
+            if (i + 32 < p_hi) hr_next = tokb[i + 32];       // prefetch
             uint32_t r = 0xFFu, c = 0;
-            if (valid) {
-                const uint32_t h = lz_hash(sm_word(data, i));
-                r = 0;
-#pragma unroll
-                for (uint32_t st = 16; st > 0; st >>= 1) if (ms->cut[r + st] <= h) r += st;
-                if (V == 1 && h >= top_start) r = 0;
-                c = bm_rank(bm, pre, h);
-            }
+            if (valid) { r = hr >> 21; c = bm_rank(bm, pre, hr & 0x1FFFFFu); }
             const uint32_t peers = __match_any_sync(0xffffffffu, r);
             const uint32_t myrank = __popc(peers & lt_mask);
             uint32_t basepos = 0;
