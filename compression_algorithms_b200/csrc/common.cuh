@@ -56,7 +56,7 @@ struct b200_ctx {
     // copy streams + events of the host-buffer entry points (host_api.cu): input chunks are copied
     // in on s_in, results copied out on s_out, while the codec kernels run on `stream`
     static const int kPipe = 16;
-    cudaStream_t s_in, s_out;
+    cudaStream_t s_in, s_out, s_aux;   // s_aux: second kernel stream, so that latency-bound chunk kernels overlap
     cudaEvent_t  ev_in[kPipe], ev_done[kPipe];
     bool         pipe_ready;
 };

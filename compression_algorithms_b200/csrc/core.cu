@@ -42,7 +42,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
     for (int i = 0; i < ctx->ev_created; ++i) { cudaEventDestroy(ctx->ev_a[i]); cudaEventDestroy(ctx->ev_b[i]); }
     if (ctx->pipe_ready) {
         for (int i = 0; i < b200_ctx::kPipe; ++i) { cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_done[i]); }
-        cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
+        cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); cudaStreamDestroy(ctx->s_aux);
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -52,6 +52,7 @@ int b200_pipe_init(b200_ctx* ctx) {
     if (ctx->pipe_ready) return B200_OK;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
     for (int i = 0; i < b200_ctx::kPipe; ++i) {
         CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));

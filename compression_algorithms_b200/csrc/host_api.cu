@@ -124,13 +124,21 @@ extern "C" int b200_lz77_decompress_host(b200_ctx* ctx, int variant, const uint8
     for (uint64_t c = 0; c < nchunks; ++c) {
         const uint64_t b0 = c * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
         const uint64_t o = b0 * bs, len = b1 * bs < n ? (b1 - b0) * bs : n - o;
-        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0));
-        B200_TRY(b200_lz77_decode_dev(ctx, variant, d_stream, d_idx + nblocks + b0, d_idx + b0, len, bs, d_out + o));
-        CUDA_TRY(cudaEventRecord(ctx->ev_done[c], ctx->stream));
+        // a chunk's decode is bound by the serial token chain of its blocks (about 4 ms whatever the chunk size), not
+        // by throughput: consecutive chunks go to two kernel streams so that their chains overlap
+        cudaStream_t keep = ctx->stream;
+        if (c & 1) ctx->stream = ctx->s_aux;
+        int rc = B200_OK;
+        if (cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0) != cudaSuccess) rc = B200_ERR_CUDA;
+        if (rc == B200_OK) rc = b200_lz77_decode_dev(ctx, variant, d_stream, d_idx + nblocks + b0, d_idx + b0, len, bs, d_out + o);
+        if (rc == B200_OK && cudaEventRecord(ctx->ev_done[c], ctx->stream) != cudaSuccess) rc = B200_ERR_CUDA;
+        ctx->stream = keep;
+        if (rc != B200_OK) { if (rc == B200_ERR_CUDA) B200_SET_ERR("lz77 decompress: stream/event call failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[c], 0));
         CUDA_TRY(cudaMemcpyAsync(h_out + o, d_out + o, len, cudaMemcpyDeviceToHost, ctx->s_out));
     }
     CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_aux));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
