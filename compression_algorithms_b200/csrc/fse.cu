@@ -237,20 +237,39 @@ __global__ void __launch_bounds__(SEG_TILE) fse_decode_kernel(const uint64_t* __
     const uint32_t T = seg_bits[gseg];
     uint8_t* o = out + start;
     if (T < 16) { atomicAdd(bad, 1u); return; }
-    uint64_t pos = T - TLOG;
-    uint32_t u = get_bits(w, pos, TLOG);
+    // the stream is read from its end towards bit 8, as 32-bit words (the u64 words are little endian).
+    // Three of them are held in registers -- the one holding the cursor (wa), the one above (wb) and the
+    // one below (wc, fetched a word ahead) -- so a symbol costs one funnel shift and never waits for memory
+    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(w);
+    const uint32_t last32 = (T - 1) >> 5;
+    uint32_t pos = T - TLOG;
+    uint32_t j = pos >> 5;
+    uint32_t wa = __ldg(w32 + j);
+    uint32_t wb = j + 1 <= last32 ? __ldg(w32 + j + 1) : 0u;
+    uint32_t wc = j > 0 ? __ldg(w32 + j - 1) : 0u;
+    uint32_t u = __funnelshift_r(wa, wb, pos & 31u) & 0xFFu;
     uint32_t i = 0;
     const bool aligned = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
     while (i + 1 < len) {
         uint32_t pack[4] = {0, 0, 0, 0};
         const uint32_t batch = len - 1 - i < 16 ? len - 1 - i : 16;
-        for (uint32_t q = 0; q < batch; ++q) {
-            const uint32_t e = s_tt[u & 0xFF];
-            const uint32_t nb = e >> 24;
-            pack[q >> 2] |= (e & 0xFF) << (8 * (q & 3));
-            if (pos < 8 + nb) { pos = 0; u = 0x100; break; }  // corrupt stream: would read below the raw byte
-            pos -= nb;
-            u = ((e >> 8) & 0xFFFF) + get_bits(w, pos, nb);
+#pragma unroll
+        for (uint32_t q = 0; q < 16; ++q) {                   // fully unrolled: pack[] stays in registers
+            if (q < batch && u != 0x100) {
+                const uint32_t e = s_tt[u & 0xFF];
+                const uint32_t nb = e >> 24;
+                pack[q >> 2] |= (e & 0xFF) << (8 * (q & 3));
+                if (pos < 8 + nb) { pos = 0; u = 0x100; }     // corrupt stream: would read below the raw byte
+                else {
+                    pos -= nb;
+                    if ((pos >> 5) < j) {                     // the cursor moved into the word below
+                        --j;
+                        wb = wa; wa = wc;
+                        wc = j > 0 ? __ldg(w32 + j - 1) : 0u;
+                    }
+                    u = ((e >> 8) & 0xFFFF) + (__funnelshift_r(wa, wb, pos & 31u) & ((1u << nb) - 1u));
+                }
+            }
         }
         if (batch == 16 && aligned) *reinterpret_cast<uint4*>(o + i) = make_uint4(pack[0], pack[1], pack[2], pack[3]);
         else for (uint32_t q = 0; q < batch; ++q) o[i + q] = (uint8_t)(pack[q >> 2] >> (8 * (q & 3)));
