@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(SEG_TILE) fse_encode_kernel(const uint8_t* __r
                                                               uint32_t* __restrict__ seg_bits) {
     __shared__ uint16_t s_norm[256], s_cum[256];
     __shared__ uint8_t  s_enc[256];
+    __shared__ uint32_t s_sym[256];   // per symbol: f | nb0 << 12 | (cum - f + 256) << 16
     const uint64_t b = blockIdx.x / tiles_per_block, tile = blockIdx.x % tiles_per_block;
     for (uint32_t s = threadIdx.x; s < 256; s += blockDim.x) s_norm[s] = norm[b * 256 + s];
     __syncthreads();
@@ -138,6 +139,11 @@ __global__ void __launch_bounds__(SEG_TILE) fse_encode_kernel(const uint8_t* __r
         const uint32_t x = (base + TSIZE) >> nb;
         if (s_norm[s]) s_enc[s_cum[s] + x - s_norm[s]] = (uint8_t)u;
     }
+    for (uint32_t s = threadIdx.x; s < 256; s += blockDim.x) {
+        const uint32_t f = s_norm[s];
+        const uint32_t nb0 = f ? TLOG - (31u - (uint32_t)__clz(f)) : 0u;
+        s_sym[s] = f | (nb0 << 12) | ((uint32_t)(s_cum[s] + 256u - f) << 16);
+    }
     __syncthreads();
     const uint32_t g = (uint32_t)tile * SEG_TILE + threadIdx.x;   // segment inside the block
     if (g >= spb) return;
@@ -146,45 +152,45 @@ __global__ void __launch_bounds__(SEG_TILE) fse_encode_kernel(const uint8_t* __r
     if (start >= blk_end) return;
     const uint32_t len = (uint32_t)(blk_end - start < seg ? blk_end - start : seg);
     const uint64_t gseg = b * spb + g;
-    uint64_t* out = scratch + gseg * stride_words;
+    uint32_t* out = reinterpret_cast<uint32_t*>(scratch + gseg * stride_words);   // the u64 words, written as little-endian u32 halves
     const uint8_t* src = in + start;
 
-    uint64_t acc = src[len - 1];   // last byte raw in the first 8 bits (main.zig:55-56)
+    // bit accumulator: lo holds the next 32 bits of the stream, hi what spills over (a symbol adds <= 8 bits)
+    uint32_t lo = src[len - 1], hi = 0;   // last byte raw in the first 8 bits (main.zig:55-56)
     uint32_t accbits = 8, w = 0;
-    uint32_t X = TSIZE;            // state value 0 (main.zig:52)
-    uint4 cache = make_uint4(0, 0, 0, 0);
-    uint32_t cache_base = 0xFFFFFFFFu;
-    for (int i = (int)len - 2; i >= 0; --i) {
-        const uint32_t cb = (uint32_t)i & ~15u;
-        if (cb != cache_base) {
-            cache_base = cb;
-            if (start + cb + 16 <= n) cache = __ldg(reinterpret_cast<const uint4*>(src + cb));
-            else {
-                uint32_t t[4] = {0, 0, 0, 0};
-                for (uint32_t k = 0; k < 16 && start + cb + k < n; ++k) t[k >> 2] |= (uint32_t)src[cb + k] << (8 * (k & 3));
-                cache = make_uint4(t[0], t[1], t[2], t[3]);
-            }
-        }
-        const uint32_t q = (uint32_t)i & 15u;
-        const uint32_t word = q < 8 ? (q < 4 ? cache.x : cache.y) : (q < 12 ? cache.z : cache.w);
-        const uint32_t s = (word >> (8 * (q & 3))) & 0xFF;
-        const uint32_t f = s_norm[s];
-        uint32_t nb = TLOG - (31u - (uint32_t)__clz(f));
-        if ((X >> nb) < f) --nb;
-        const uint64_t bits = X & ((1u << nb) - 1);
-        acc |= bits << accbits;
+    uint32_t X = TSIZE;                    // state value 0 (main.zig:52)
+    auto put = [&](uint32_t bits, uint32_t nb) {
+        lo |= bits << accbits;
+        hi |= __funnelshift_l(bits, 0u, accbits);        // bits >> (32 - accbits), 0 when accbits == 0
         accbits += nb;
-        if (accbits >= 64) { out[w++] = acc; accbits -= 64; acc = accbits ? bits >> (nb - accbits) : 0; }
-        X = TSIZE + s_enc[s_cum[s] + (X >> nb) - f];
+        if (accbits >= 32) { out[w++] = lo; lo = hi; hi = 0; accbits -= 32; }
+    };
+    auto step = [&](uint32_t s) {
+        const uint32_t e = s_sym[s];
+        const uint32_t f = e & 0xFFFu;
+        uint32_t nb = (e >> 12) & 0xFu;
+        nb -= (X >> nb) < f;
+        put(X & ((1u << nb) - 1u), nb);
+        X = TSIZE + s_enc[(e >> 16) + (X >> nb) - 256u];
+    };
+    int i = (int)len - 2;
+    while (i >= 0 && (((uint32_t)i + 1u) & 15u)) { step(src[i]); --i; }   // down to a 16-byte boundary
+    if (i >= 15) {
+        uint4 nxt = __ldg(reinterpret_cast<const uint4*>(src + i - 15));
+        while (i >= 15) {
+            const uint4 c = nxt;
+            if (i >= 31) nxt = __ldg(reinterpret_cast<const uint4*>(src + i - 31));   // one 16-byte read ahead
+            const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int k = 15; k >= 0; --k) step((cw[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+            i -= 16;
+        }
     }
-    {
-        const uint64_t bits = X - TSIZE;   // final state in TABLE_LOG bits (main.zig:65)
-        acc |= bits << accbits;
-        accbits += TLOG;
-        if (accbits >= 64) { out[w++] = acc; accbits -= 64; acc = accbits ? bits >> (TLOG - accbits) : 0; }
-    }
-    if (accbits) out[w] = acc;
-    seg_bits[gseg] = w * 64 + accbits;
+    put(X - TSIZE, TLOG);                  // final state in TABLE_LOG bits (main.zig:65)
+    const uint32_t total = w * 32 + accbits;
+    if (accbits) { out[w++] = lo; }
+    if (w & 1) out[w] = 0;                 // the upper half of the last u64 word
+    seg_bits[gseg] = total;
 }
 
 // ------------------------------------------------------------ offsets (single CTA) + gather
