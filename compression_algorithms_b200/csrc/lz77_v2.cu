@@ -142,16 +142,21 @@ __device__ __forceinline__ uint32_t walk_groups(const uint16_t* T, uint16_t* B1,
         const uint4* gp = reinterpret_cast<const uint4*>(T + (g << 5));
         const uint4 q0 = gp[0], q1 = gp[1], q2 = gp[2], q3 = gp[3];
         const uint32_t wd[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-        uint32_t dm = 0, mn2 = 0xFFFFFFFFu;
+        // dead flags of the 32 slots, two instructions per word: acc gets the flag of the even slot 2i in bit
+        // 15-i and that of the odd slot 2i+1 in bit 31-i (the walk only needs the first dead slot at/after j0)
+        uint32_t acc = 0, mn2 = 0xFFFFFFFFu;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const uint32_t r = __vsetleu2(wd[i], thr2);             // 1 per halfword that is <= dthr
-            dm |= ((r & 1u) | ((r >> 15) & 2u)) << (2 * i);
+            acc = (acc << 1) + __vsetleu2(wd[i], thr2);             // vset: 1 per halfword that is <= dthr
             mn2 = __vminu2(mn2, wd[i]);
         }
         B1[g] = (uint16_t)min(mn2 & 0xFFFFu, mn2 >> 16);
-        dm &= 0xFFFFFFFFu << j0;
-        const uint32_t stop = dm ? (uint32_t)(__ffs(dm) - 1) : 32u;
+        const uint32_t ev = (acc & 0xFFFFu) & ((1u << (16u - ((j0 + 1u) >> 1))) - 1u);   // even slots 2i >= j0
+        const uint32_t od = (acc >> 16) & ((1u << (16u - (j0 >> 1))) - 1u);              // odd slots 2i+1 >= j0
+        const uint32_t s_ev = ev ? 2u * ((uint32_t)__clz(ev) - 16u) : 64u;
+        const uint32_t s_od = od ? 2u * ((uint32_t)__clz(od) - 16u) + 1u : 64u;
+        const bool dm = (ev | od) != 0u;
+        const uint32_t stop = dm ? min(s_ev, s_od) : 32u;
         if (pend) {
 #pragma unroll 1
             for (uint32_t j = j0; j < stop; ++j) {
