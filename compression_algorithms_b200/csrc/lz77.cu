@@ -356,6 +356,7 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
     uint64_t* block_bytes = misc + 4;
     CUDA_TRY(cudaMemsetAsync(misc, 0, 32, ctx->stream));
     if (use_v2) {
+        if (dbg_tok && bs > 65536) { B200_SET_ERR("lz77: token dump needs blocks <= 65536"); return B200_ERR_ARG; }
         B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
         B200_TRY(lz77_v2_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
         B200_TIMED_END(ctx);

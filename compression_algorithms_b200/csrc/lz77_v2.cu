@@ -42,6 +42,7 @@ constexpr uint32_t PRE_N = BM_WORDS / PRE_CHUNK;             // 4352
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint32_t MAXB = 65536;                             // max block bytes on this path
 constexpr uint32_t NTHREADS = 1024;
+constexpr uint32_t CARRY_BYTES = (MAXB + 64) * 4 + 32768 * 4 + MAXB * 4 + 32768 * 4;
 constexpr uint32_t NR = 32;                                  // ranges == warps
 constexpr uint32_t CROWD_MIN = 12;                           // same-home entries in a batch from which the slot-ordered placement is used
 constexpr uint32_t HOT_MIN_WORDS = 7;                         // fully occupied words (of 8) in a 256-slot chunk from which its chain counts as hot (swept 2..8 on B200)
@@ -73,6 +74,7 @@ struct Misc {
     uint32_t top_start, sp_lo_end, sp_hi_start, pad0;
     uint32_t rstart[NR + 1];
     uint32_t fcut[16], nfcut;    // cuts forced just before / after a hot chain
+    uint32_t ncar, cq_h, cq_t, ecarry;   // slices of a large block: live carried entries, clear-queue cursors, parse carry
     uint32_t cnt[NR][NR];        // [warp][range]
     uint32_t clr[64];            // slot-0 clear times (warp 0)
     uint8_t  sexit[NR][32];      // super-chunk exit functions
@@ -175,6 +177,7 @@ __device__ __forceinline__ uint32_t walk_groups(const uint16_t* T, uint16_t* B1,
 template <int V, bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t bs, uint32_t nblocks,
                                                              uint32_t* __restrict__ lists_all, uint32_t* __restrict__ tok_all,
+                                                             uint8_t* __restrict__ carry_all,
                                                              uint8_t* __restrict__ scratch, uint64_t stride,
                                                              uint64_t* __restrict__ block_sizes, uint64_t* __restrict__ block_bytes,
                                                              uint32_t* __restrict__ dbg_tok) {
@@ -195,31 +198,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t* lists = lists_all + (uint64_t)blockIdx.x * MAXB;
     uint32_t* tokb = tok_all + (uint64_t)blockIdx.x * MAXB;
+    // state handed from one slice of a large block to the next (global, per CTA)
+    uint8_t* carry = carry_all + (uint64_t)blockIdx.x * CARRY_BYTES;
+    uint32_t* rawmap = reinterpret_cast<uint32_t*>(carry);                        // [T_ENTRIES] raw slot of every compact slot
+    uint32_t* raw_carry = rawmap + T_ENTRIES;                                     // [32768] raw slot of every carried position, NONE = cleared
+    uint32_t* cs = raw_carry + 32768;                                             // [MAXB] compact slot every new position was placed in (NONE = wiped); 65535 is a valid slot, hence 32 bits
+    uint32_t* ccar = cs + MAXB;                                                   // [32768] compact slot of every carried position (NONE = none)
 
     uint32_t* dbg_stats = dbg_tok ? dbg_tok + (uint64_t)nblocks * MAXB : nullptr;   // [block][8 phase stamps + 32 warps x 4]
     for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
         const long long t_begin = CLK();
 #define PHASE_STAMP(k) do { if (DBG && dbg_stats && tid == 0) dbg_stats[(uint64_t)b * 136 + (k)] = (uint32_t)(clock64() - t_begin); } while (0)
-        const uint8_t* src = in + (uint64_t)b * bs;
-        const uint32_t len = (uint32_t)(n - (uint64_t)b * bs < bs ? n - (uint64_t)b * bs : bs);
+        const uint8_t* bsrc = in + (uint64_t)b * bs;
+        const uint32_t blen = (uint32_t)(n - (uint64_t)b * bs < bs ? n - (uint64_t)b * bs : bs);
+        // A block larger than 65536 positions is simulated in SLICES so that positions stay 16-bit: a slice
+        // holds the W positions before it (the "carried" entries: still live, already placed, their raw slots
+        // handed over by the previous slice) and up to 65536 - W new positions. Everything below works on
+        // positions relative to the first carried one; a 64 KiB block is a single slice with nothing carried.
+        uint32_t n0 = 0;            // first new position of the slice (absolute in the block)
+        uint64_t out_units = 0;     // bytes (V1) / bits (V0) of the block's tokens written by earlier slices
+        for (;;) {
+        const uint32_t C = n0 ? W : 0u;                       // carried positions: relative [0, C)
+        const uint32_t B0 = n0 - C;                           // absolute position of relative 0
+        const uint32_t avail = blen - B0;                     // bytes of the block from there on
+        const uint32_t len = avail < MAXB ? avail : MAXB;     // new positions: relative [C, len)
+        const bool last_slice = B0 + len >= blen;
+        const uint8_t* src = bsrc + B0;
+        const uint32_t p_start = C + (C ? ms->ecarry : 0u);   // where the greedy parse enters the slice (read before P5 rewrites it)
 
-        // ---------------- P0: block -> shared memory, zero pad, zero bitmap
+        // ---------------- P0: slice -> shared memory (with the real bytes behind it, zero pad behind the block), zero bitmap
         {
             const bool al = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
             for (uint32_t i = tid * 16; i < len + 128 && i < SZ_DATA; i += NTHREADS * 16) {
-                if (al && i + 16 <= len) *reinterpret_cast<uint4*>(data + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
-                else for (uint32_t k = 0; k < 16 && i + k < SZ_DATA; ++k) data[i + k] = (i + k < len) ? __ldg(src + i + k) : 0;
+                if (al && i + 16 <= avail) *reinterpret_cast<uint4*>(data + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
+                else for (uint32_t k = 0; k < 16 && i + k < SZ_DATA; ++k) data[i + k] = (i + k < avail) ? __ldg(src + i + k) : 0;
             }
             for (uint32_t i = tid; i < BM_WORDS; i += NTHREADS) bm[i] = 0;
+            if (tid == 0) ms->ncar = 0;
         }
         __syncthreads();
+        if (C) {   // the carried entries sit where the previous slice left them
+            uint32_t cnt = 0;
+            for (uint32_t i = tid; i < C; i += NTHREADS) {
+                const uint32_t r = raw_carry[i];
+                if (r != NONE) { atomicOr(&bm[r >> 5], 1u << (r & 31)); ++cnt; }
+            }
+            cnt = warp_sum_u32(cnt);
+            if (lane == 0 && cnt) atomicAdd(&ms->ncar, cnt);
+            __syncthreads();
+        }
+        const uint32_t nslots = ms->ncar + (len - C);         // occupied compact slots of the slice
 
         PHASE_STAMP(0);
         // ---------------- P1: no-expiry occupancy (order independent) by atomic linear probing
         // (a per-home "frontier hint" table that lets later walks skip the full words of a hot chain was
         // tried and did not pay: 175 K -> 190 K cycles; the phase is bound by the latency of the
         // dependent hash -> read -> atomicOr chain of the 64 positions each thread owns)
-        for (uint32_t i = tid; i < len; i += NTHREADS) {
+        for (uint32_t i = C + tid; i < len; i += NTHREADS) {
             uint32_t s = lz_hash(sm_word(data, i));
             for (;;) {
                 const uint32_t wi = s >> 5;
@@ -357,8 +392,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
 
         PHASE_STAMP(2);
         // ---------------- P3: compact index + stable partition by range into per-range lists
-        const uint32_t slice = ((len + NTHREADS - 1) / NTHREADS) * 32;   // positions per warp (multiple of 32)
-        const uint32_t p_lo = warp * slice, p_hi = (p_lo + slice < len) ? p_lo + slice : len;
+        const uint32_t slice = ((len - C + NTHREADS - 1) / NTHREADS) * 32;   // new positions per warp (multiple of 32)
+        const uint32_t p_lo = (C + warp * slice < len) ? C + warp * slice : len, p_hi = (p_lo + slice < len) ? p_lo + slice : len;
         const uint32_t top_start = ms->top_start;
         // pass 1: counts per (warp, range)
         for (uint32_t base = p_lo; base < p_hi; base += 32) {
@@ -413,6 +448,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             }
             __syncwarp();
         }
+        if (C) {                   // compact slot of every carried entry (the bitmap is still alive here)
+            for (uint32_t i = tid; i < C; i += NTHREADS) {
+                const uint32_t r = raw_carry[i];
+                ccar[i] = r != NONE ? bm_rank(bm, pre, r) : NONE;
+            }
+        }
+        if (!last_slice) {         // raw slot of every compact slot, for the hand-over at the end of the slice
+            for (uint32_t k = 0; k < 5; ++k) {
+                const uint32_t ch = tid * 5 + k;
+                if (ch >= PRE_N) break;
+                uint32_t r = pre[ch];
+                for (uint32_t wq = 0; wq < PRE_CHUNK; ++wq) {
+                    uint32_t x = bm[ch * PRE_CHUNK + wq];
+                    while (x) { const uint32_t bpos = (uint32_t)(__ffs(x) - 1); x &= x - 1; rawmap[r++] = ((ch * PRE_CHUNK + wq) << 5) + bpos; }
+                }
+            }
+        }
         __syncthreads();
 
         PHASE_STAMP(3);
@@ -421,6 +473,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         uint32_t* S1 = pre;   // rank prefix is dead: per-group pattern-signature filter, u32[2052]
         for (uint32_t i = tid; i < 2052; i += NTHREADS) S1[i] = 0;
         __syncthreads();
+        if (C) {                   // the carried entries: live at the start of the slice, in the slots they were placed in
+            for (uint32_t i = tid; i < C; i += NTHREADS) {
+                const uint32_t c = ccar[i];
+                if (c != NONE) { T[c] = (uint16_t)(i + 1); atomicOr(&S1[c >> 5], 1u << ((sm_word(data, i) * 0x9E3779B1u) >> 27)); }   // and its pattern signature
+            }
+            __syncthreads();
+        }
         {
             const uint32_t sp_lo_end = ms->sp_lo_end, sp_hi_start = ms->sp_hi_start;
             uint32_t cur = ms->rstart[warp];
@@ -428,8 +487,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             const long long t_p4 = CLK();
             uint32_t st_rounds = 0, st_coop = 0, st_entries = end - cur, st_iters = 0;
             long long tq = 0, tc = 0, tm = 0, tl = 0, t_mark;
-            uint32_t qh = 0, qt = 0;                       // slot-0 clear queue (only warp 0 ever uses it)
-            if (warp == 0) { if (lane == 0) ms->clr[0] = W - 1; qt = 1; }
+            // slot-0 clear queue (only warp 0 ever uses it): ABSOLUTE clear times, carried from slice to slice
+            uint32_t qh = 0, qt = 0;
+            if (warp == 0) {
+                if (C == 0) { if (lane == 0) ms->clr[0] = W - 1; qt = 1; }
+                else { qh = ms->cq_h; qt = ms->cq_t; }
+            }
             __syncwarp();
             // the list entries cur .. cur+31 (ent) and cur+32 .. cur+63 (pf) are kept in registers, pf being
             // re-read right after every advance: the L2 latency of the list stays off the critical path
@@ -454,7 +517,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                     // ---- serial path for the cluster that touches slot 0 / the table end: exact reference order
                     const uint32_t q0 = __shfl_sync(0xffffffffu, q, 0), c0 = __shfl_sync(0xffffffffu, kk, 0);
                     if (lane == 0) {
-                        while (qh < qt && ms->clr[qh & 63] < q0) { if (sp_lo_end) { T[0] = 0; B1[0] = 0; } ++qh; }
+                        const uint32_t q0a = B0 + q0;                      // absolute time
+                        auto clear0 = [&]() {                              // the early clear wipes whatever sits in slot 0
+                            if (sp_lo_end) { const uint32_t v0 = T[0]; if (v0 && !last_slice) cs[v0 - 1] = NONE; T[0] = 0; B1[0] = 0; }
+                        };
+                        while (qh < qt && ms->clr[qh & 63] < q0a) { clear0(); ++qh; }
                         const uint32_t dthr = q0 > W ? q0 - W : 0;
                         const uint32_t w = sm_word(data, q0);
                         uint32_t k = c0, m = NONE;
@@ -463,14 +530,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                             const uint32_t v = T[k];
                             if (v <= dthr) break;
                             if (sm_word(data, v - 1) == w) { m = v - 1; break; }
-                            if (k + 1 == len) { ran_off = true; break; }   // find does not wrap (lz77.c:102, deflate/lz77.c:168)
+                            if (k + 1 == nslots) { ran_off = true; break; }   // find does not wrap (lz77.c:102, deflate/lz77.c:168)
                             ++k;
                         }
                         uint32_t e = ran_off ? 0 : k;                      // the wrapping insert continues at slot 0
-                        for (;;) { if (T[e] <= dthr) break; ++e; if (e == len) e = 0; }
+                        for (;;) { if (T[e] <= dthr) break; ++e; if (e == nslots) e = 0; }
                         if (q0 != 65535u) T[e] = (uint16_t)(q0 + 1);
-                        if (e == 0 && sp_lo_end) { ms->clr[qt & 63] = q0 + W; ++qt; }
-                        if (qh < qt && ms->clr[qh & 63] == q0) { if (sp_lo_end) { T[0] = 0; B1[0] = 0; } ++qh; }
+                        if (!last_slice) cs[q0] = e;
+                        if (e == 0 && sp_lo_end) { ms->clr[qt & 63] = q0a + W; ++qt; }
+                        if (qh < qt && ms->clr[qh & 63] == q0a) { clear0(); ++qh; }
                         // token candidate
                         uint32_t tk = 0;
                         const bool reject = (m == NONE) || (V ? (q0 - m >= W - 1) : (q0 - m == W));
@@ -563,7 +631,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                             }
                         }
                         __syncwarp();
-                        if (!done) { if (q != 65535u) T[my_e] = (uint16_t)(q + 1); done = true; }
+                        if (!done) { if (q != 65535u) T[my_e] = (uint16_t)(q + 1); if (!last_slice) cs[q] = my_e; done = true; }
                         __syncwarp();
                         ++st_coop;
                     }
@@ -594,7 +662,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                     const uint32_t cmask = __ballot_sync(0xffffffffu, blocked);
                     const uint32_t firstc = cmask ? (uint32_t)(__ffs(cmask) - 1) : 32u;
                     if (!done && lane < firstc) {
-                        if (q != 65535u) T[kk] = (uint16_t)(q + 1);      // position 65535 is never looked up again
+                        if (q != 65535u) T[kk] = (uint16_t)(q + 1);      // position 65535 is never looked up again within the slice
+                        if (!last_slice) cs[q] = kk;
                         atomicOr(&S1[kk >> 5], 1u << sig);
                         done = true;
                     }
@@ -613,6 +682,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 tl += CLK() - t_mark;
                 advance(L);
             }
+            if (warp == 0 && lane == 0) { ms->cq_h = qh; ms->cq_t = qt; }
             if (DBG && dbg_stats && lane == 0) {
                 uint32_t* o = dbg_stats + (uint64_t)b * 136 + 8 + warp * 4;
                 o[0] = (uint32_t)(clock64() - t_p4); o[1] = st_entries | (st_iters << 16); o[2] = st_rounds | ((uint32_t)(tq >> 10) << 16); o[3] = st_coop | ((uint32_t)(tc >> 10) << 16);
@@ -632,8 +702,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             for (uint32_t k = 0; k < 8; ++k) {
                 const uint32_t i = i0 + k * NTHREADS;
                 if (i < len) {
-                    if (dbg_tok) dbg_tok[(uint64_t)b * MAXB + i] = tv[k];
-                    adv[PADX(i)] = (uint8_t)((tv[k] >> 16) ? (tv[k] >> 16) : 1u);
+                    if (dbg_tok && C == 0) dbg_tok[(uint64_t)b * MAXB + i] = tv[k];
+                    // positions before the parse entry (carried ones, and those covered by the previous slice's last
+                    // token) are stepped over one by one and never emitted
+                    adv[PADX(i)] = (uint8_t)((i >= p_start && (tv[k] >> 16)) ? (tv[k] >> 16) : 1u);
                 }
             }
         }
@@ -672,6 +744,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 centry[ch] = (uint8_t)e;
                 const uint32_t p = (ch << 6) + e;
                 if (ch < nchunks && p < len) e = exitof[PADX(p)];
+                if (ch + 1 == nchunks) ms->ecarry = e;      // positions of the next slice covered by this slice's last token
             }
         }
         __syncthreads();
@@ -688,6 +761,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             const uint32_t cend = (tid << 6) + 64;
             const uint32_t hi = cend < len ? cend : len;
             for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[PADX(p)]) {
+                if (p < p_start) continue;            // (the for's increment still advances by adv[p] == 1)
                 const bool lit = adv[PADX(p)] == 1;   // matches are at least 4 long
                 if (V == 1) orel[PADX(p)] = (uint8_t)(my_units >> 1);
                 my_units += V ? (lit ? 2u : 4u) : (lit ? 9u : 19u);
@@ -708,7 +782,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             my_off = ms->scan[warp] + incl - my_units;
         }
         const uint32_t total_units = ms->scan[32];
-        uint8_t* out = scratch + (uint64_t)b * stride;
+        uint8_t* out = scratch + (uint64_t)b * stride + (V ? out_units : (out_units >> 5) * 4);   // V0: word holding the first bit
 
         PHASE_STAMP(5);
         // ---------------- P6: emission
@@ -735,20 +809,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                     }
                 }
             }
-            if (tid == 0) { block_sizes[b] = total_units; block_bytes[b] = total_units; }
+            if (tid == 0 && last_slice) { block_sizes[b] = out_units + total_units; block_bytes[b] = out_units + total_units; }
         } else {
             // LSB-first bit stream staged in shared memory (exitof is dead now), then stored coalesced
-            const uint32_t nwords = (total_units >> 5) + 2;
+            const uint32_t sh0 = (uint32_t)(out_units & 31);   // bits of the first word that belong to the previous slice
+            const uint32_t nwords = ((sh0 + total_units) >> 5) + 2;
             __syncthreads();
             for (uint32_t i = tid; i < nwords; i += NTHREADS) stage[i] = 0;
             __syncthreads();
             if (tid < nchunks && my_units) {
                 const uint32_t cend = (tid << 6) + 64;
                 const uint32_t hi = cend < len ? cend : len;
-                uint32_t wi = my_off >> 5, have = my_off & 31;
+                uint32_t wi = (sh0 + my_off) >> 5, have = (sh0 + my_off) & 31;
                 bool first = have != 0;
                 uint64_t acc = 0;
                 for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[PADX(p)]) {
+                    if (p < p_start) continue;
                     const uint32_t t = tokb[p];
                     uint32_t v, nb;
                     if (t == 0) { v = (uint32_t)data[p] << 1; nb = 9; }
@@ -763,17 +839,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 if (have) atomicOr(&stage[wi], (uint32_t)acc);
             }
             __syncthreads();
-            for (uint32_t i = tid; i < nwords; i += NTHREADS) reinterpret_cast<uint32_t*>(out)[i] = stage[i];
-            if (tid == 0) { block_sizes[b] = total_units; block_bytes[b] = (uint64_t)total_units / 8 + 1; }
+            for (uint32_t i = tid; i < nwords; i += NTHREADS) {
+                if (i == 0 && sh0) reinterpret_cast<uint32_t*>(out)[0] |= stage[0];   // word shared with the previous slice (same CTA, earlier)
+                else reinterpret_cast<uint32_t*>(out)[i] = stage[i];
+            }
+            if (tid == 0 && last_slice) { block_sizes[b] = out_units + total_units; block_bytes[b] = (out_units + total_units) / 8 + 1; }
         }
-        __syncthreads();   // smem is reused by the next block
+        out_units += total_units;
+        if (!last_slice) {
+            // hand-over: the last W positions of this slice are the next slice's carried entries; their raw slots come
+            // from the compact slot each was placed in (0xFFFF = wiped by the early slot-0 clear)
+            __syncthreads();
+            for (uint32_t i = tid; i < W; i += NTHREADS) {
+                const uint32_t c = cs[len - W + i];
+                raw_carry[i] = c != NONE ? rawmap[c] : NONE;
+            }
+        }
+        __syncthreads();   // smem is reused by the next slice / block
         PHASE_STAMP(6);
+        if (last_slice) break;
+        n0 = B0 + len;
+        }   // slices
     }
 }
 
 }  // namespace
 
-bool lz77_v2_supported(uint64_t bs) { return bs <= MAXB; }
+// blocks above 65536 bytes are simulated in slices (positions stay 16-bit inside a slice)
+bool lz77_v2_supported(uint64_t bs) { return bs <= (1ull << 31); }
 
 // scratch slots: 13 = lists, 14 = tok
 int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
@@ -788,10 +881,11 @@ int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, 
     }
     uint64_t grid = (uint64_t)ctx->sm_count;
     if (grid > nblocks) grid = nblocks;
-    uint32_t *lists, *tok;
+    uint32_t *lists, *tok; uint8_t* carry;
     B200_TRY(b200_scratch(ctx, 13, (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&lists)));
     B200_TRY(b200_scratch(ctx, 14, (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&tok)));
-#define LZ_V2_LAUNCH(V, D) lz77_v2_kernel<V, D><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, lists, tok, scratch, stride, d_block_sizes, block_bytes, dbg_tok)
+    B200_TRY(b200_scratch(ctx, 15, bs > MAXB ? (size_t)grid * CARRY_BYTES + 64 : 64, reinterpret_cast<void**>(&carry)));
+#define LZ_V2_LAUNCH(V, D) lz77_v2_kernel<V, D><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, lists, tok, carry, scratch, stride, d_block_sizes, block_bytes, dbg_tok)
     if (dbg_tok) { if (variant == 0) LZ_V2_LAUNCH(0, true); else LZ_V2_LAUNCH(1, true); }
     else { if (variant == 0) LZ_V2_LAUNCH(0, false); else LZ_V2_LAUNCH(1, false); }
     CUDA_TRY(cudaGetLastError());

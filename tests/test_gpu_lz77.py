@@ -217,3 +217,32 @@ def test_host_pipeline_matches_device(ctx, variant, n, block):
     _lib.check(lib.b200_lz77_decompress_host(ctx.handle, variant, h_out.data_ptr(), tot.value, off.ctypes.data, sizes.ctypes.data,
                                              n, block, h_dec.data_ptr()))
     assert np.array_equal(h_dec.numpy(), data)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("block", [98304, 131072, 1 << 20, 0])
+def test_large_blocks_in_slices(ctx, ob, variant, kind, block):
+    """blocks above 65536 bytes run through the shared-memory emulation in slices (carried entries,
+    parse carry, bit-offset carry of the standalone stream); block 0 = the reference's whole-buffer call"""
+    _encode_check(ctx, ob, _corpus(1_500_000, kind, 13), variant, block)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("block", [131072, 0])
+def test_slot0_exception_across_slices(ctx, ob, variant, block):
+    """U10 with the slot-0 cluster, its clear queue and wiped entries handed from slice to slice"""
+    rng = np.random.default_rng(5)
+    n = 600_000
+    data = rng.integers(97, 123, size=n, dtype=np.uint8)
+    pat = np.array([0x78, 0x15, 0x02, 0x01], dtype=np.uint8)
+    pos = 0
+    while pos + 4 < n:
+        data[pos: pos + 4] = pat
+        pos += int(rng.integers(700, 3000))
+    _encode_check(ctx, ob, data, variant, block)
+
+
+def test_whole_buffer_6mb(ctx, ob):
+    """the drop-in's own call shape (one table sliding over the whole buffer) at a size with ~180 slices"""
+    _encode_check(ctx, ob, _corpus(6_000_000, 0, 7), 1, 0)
