@@ -185,6 +185,20 @@ def detail_codecs(ctx, dv, torch, data100):
     td, _ = timed(lambda: dv.lz77_decode(ctx, st, out=dec), reps=2)
     out["lz77_standalone_64k_blocks"] = {"compress_gbps": n / 1e9 / te, "decompress_gbps": n / 1e9 / td,
                                          "ratio": n / float(st.total_bytes), "roundtrip_ok": bool(torch.equal(dec, data100))}
+    # deflate with the entropy stage (the reference's TODO, deflate/lz77.c:279): LZ77 tokens -> Huffman-coded words
+    ds = dv.deflate_alloc(ctx, n, BLOCK)
+    te, ds = timed(lambda: dv.deflate_compress(ctx, data100, BLOCK, stream=ds, sync=False), reps=2)
+    ds = dv.deflate_compress(ctx, data100, BLOCK, stream=ds)
+    tes, _ = timed(lambda: dv.dfl_encode(ctx, ds.lz, stream=ds, sync=False))
+    dec = torch.empty_like(data100)
+    td, _ = timed(lambda: dv.deflate_decompress(ctx, ds, out=dec), reps=2)
+    tok = torch.empty_like(ds.lz.out)
+    tds, _ = timed(lambda: dv.dfl_decode(ctx, ds, tok))
+    out["deflate_entropy_coded_64k_blocks"] = {
+        "compress_gbps": n / 1e9 / te, "decompress_gbps": n / 1e9 / td, "ratio": n / (ds.total_words * 4.0),
+        "entropy_stage_encode_ms": tes * 1e3, "entropy_stage_decode_ms": tds * 1e3,
+        "token_bytes": int(ds.lz.block_off[-1].item()), "stream_bytes": int(ds.total_words * 4),
+        "roundtrip_ok": bool(torch.equal(dec, data100))}
     return out
 
 

@@ -17,6 +17,13 @@ class HuffLayout(C.Structure):
         "off_meta", "off_block_bits", "off_block_word", "off_chunk_bits", "off_chunk_off", "off_sub_off")]
 
 
+class DflLayout(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "bytes", "nblocks", "nchunks", "chunks_per_block", "off_freq", "off_codes", "off_lens", "off_tree", "off_meta",
+        "off_tok_off", "off_tok_sizes", "off_block_bits", "off_block_word", "off_chunk_state", "off_chunk_bits",
+        "off_chunk_off", "off_sub_off")]
+
+
 class FseLayout(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "bytes", "nblocks", "nsegs", "segs_per_block", "off_freq", "off_norm", "off_tt", "off_seg_bits", "off_seg_word")]
@@ -67,6 +74,13 @@ def core():
         lib.b200_huffman_compress_host.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, u64p, u32p]
         lib.b200_huffman_decompress_host.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
         lib.b200_huffman_decompress_serial_host.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_uint64, u64p]
+        lib.b200_dfl_layout_for.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(DflLayout)]
+        lib.b200_dfl_max_words.restype = C.c_uint64
+        lib.b200_dfl_max_words.argtypes = [C.c_uint64, C.c_uint64]
+        lib.b200_dfl_encode_dev.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, u64p, u32p]
+        lib.b200_dfl_decode_dev.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
+        lib.b200_deflate_compress_dev.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, C.c_uint64, u64p, u32p]
+        lib.b200_deflate_decompress_dev.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]
         if hasattr(lib, "b200_fse_layout_for"):
             lib.b200_fse_layout_for.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(FseLayout)]
             lib.b200_fse_max_words.restype = C.c_uint64

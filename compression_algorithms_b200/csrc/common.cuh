@@ -72,6 +72,8 @@ int b200_pinned(b200_ctx* ctx, size_t bytes, void** out);
 #define B200_K_HUFF_DECODE 3
 #define B200_K_FSE_ENCODE 4
 #define B200_K_FSE_DECODE 5
+#define B200_K_DFL_ENCODE 6
+#define B200_K_DFL_DECODE 7
 void b200_timed_begin(b200_ctx* ctx, int kind);
 void b200_timed_end(b200_ctx* ctx);
 #define B200_TIMED_BEGIN(ctx, kind) do { if ((ctx)->timing) b200_timed_begin((ctx), (kind)); } while (0)

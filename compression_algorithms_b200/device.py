@@ -233,6 +233,108 @@ def lz77_decode(ctx, st, out=None):
     return out
 
 
+# ------------------------------------------------------------------ deflate token entropy stage
+@dataclass
+class DeflateStream:
+    """deflate = LZ77 byte tokens (lz) + their Huffman-coded form (words, side)."""
+    lz: Lz77Stream             # the byte tokens (scratch on the decode side)
+    words: torch.Tensor        # int32 storage of the MSB-first u32 word stream
+    side: torch.Tensor         # uint8 side buffer: frequencies[286], codes, trees, token offsets, decode index
+    layout: _lib.DflLayout
+    n: int
+    block_size: int
+    total_words: int = -1
+    worst_status: int = 0
+
+    def _view(self, off, count, dtype):
+        nbytes = count * torch.empty((), dtype=dtype).element_size()
+        return self.side[off: off + nbytes].view(dtype)
+
+    def freq(self):
+        return self._view(self.layout.off_freq, self.layout.nblocks * 288, torch.int32).view(-1, 288)[:, :286]
+
+    def codes(self):
+        return self._view(self.layout.off_codes, self.layout.nblocks * 288, torch.int32).view(-1, 288)[:, :286]
+
+    def lens(self):
+        return self.side[self.layout.off_lens: self.layout.off_lens + self.layout.nblocks * 288].view(-1, 288)[:, :286]
+
+    def meta(self):
+        return self._view(self.layout.off_meta, self.layout.nblocks * 4, torch.int32).view(-1, 4)
+
+    def block_bits(self):
+        return self._view(self.layout.off_block_bits, self.layout.nblocks, torch.int64)
+
+    def block_word(self):
+        return self._view(self.layout.off_block_word, self.layout.nblocks + 1, torch.int64)
+
+
+def dfl_layout(n, block_size):
+    L = _lib.DflLayout()
+    _lib.check(_lib.core().b200_dfl_layout_for(n, block_size, C.byref(L)))
+    return L
+
+
+def deflate_alloc(ctx, n, block_size, lz=None):
+    L = dfl_layout(n, block_size)
+    cap = int(_lib.core().b200_dfl_max_words(n, block_size))
+    return DeflateStream(lz=lz if lz is not None else lz77_alloc(ctx, n, block_size, LZ_DEFLATE),
+                         words=torch.empty(cap, dtype=torch.int32, device=ctx.device),
+                         side=torch.empty(L.bytes, dtype=torch.uint8, device=ctx.device),
+                         layout=L, n=n, block_size=block_size)
+
+
+def dfl_encode(ctx, lz, stream=None, sync=True):
+    """Entropy stage only: the byte tokens of lz77_encode(variant LZ_DEFLATE) -> frequencies[286],
+    code tables and the packed words (the TODO of algorithms/deflate/lz77.c:279)."""
+    st = stream if stream is not None else deflate_alloc(ctx, lz.n, lz.block_size, lz)
+    tw, ws = C.c_uint64(0), C.c_uint32(0)
+    _lib.check(_lib.core().b200_dfl_encode_dev(
+        ctx.handle, _ptr(lz.out), lz.out.numel(), _ptr(lz.block_off), _ptr(lz.block_sizes), lz.n, lz.block_size,
+        _ptr(st.words), st.words.numel(), _ptr(st.side), st.side.numel(),
+        C.byref(tw) if sync else None, C.byref(ws) if sync else None))
+    if sync:
+        st.total_words, st.worst_status = tw.value, ws.value
+    return st
+
+
+def dfl_decode(ctx, st, tokens_out=None):
+    """packed words -> byte tokens (uint8 tensor as large as the encoder's token buffer)"""
+    if tokens_out is None:
+        tokens_out = torch.zeros_like(st.lz.out)
+    _lib.check(_lib.core().b200_dfl_decode_dev(
+        ctx.handle, _ptr(st.words), max(st.total_words, 0) if st.total_words >= 0 else st.words.numel(),
+        _ptr(st.side), st.side.numel(), st.n, st.block_size, _ptr(tokens_out)))
+    return tokens_out
+
+
+def deflate_compress(ctx, data, block_size=DEFAULT_BLOCK, stream=None, sync=True):
+    """lz77_compress per block (algorithms/deflate/lz77.c:199-277) + the entropy stage."""
+    _check_u8(data)
+    n = data.numel()
+    st = stream if stream is not None else deflate_alloc(ctx, n, block_size)
+    tw, ws = C.c_uint64(0), C.c_uint32(0)
+    _lib.check(_lib.core().b200_deflate_compress_dev(
+        ctx.handle, _ptr(data), n, block_size, _ptr(st.lz.out), st.lz.out.numel(), _ptr(st.lz.block_sizes), _ptr(st.lz.block_off),
+        _ptr(st.words), st.words.numel(), _ptr(st.side), st.side.numel(),
+        C.byref(tw) if sync else None, C.byref(ws) if sync else None))
+    if sync:
+        st.total_words, st.worst_status = tw.value, ws.value
+    return st
+
+
+def deflate_decompress(ctx, st, out=None, tokens=None):
+    """The decoder the reference never wrote (deflate/deflate.c:78-79): words -> tokens -> bytes."""
+    if out is None:
+        out = torch.empty(st.n, dtype=torch.uint8, device=ctx.device)
+    if tokens is None:
+        tokens = st.lz.out
+    _lib.check(_lib.core().b200_deflate_decompress_dev(
+        ctx.handle, _ptr(st.words), max(st.total_words, 0) if st.total_words >= 0 else st.words.numel(),
+        _ptr(st.side), st.side.numel(), st.n, st.block_size, _ptr(tokens), _ptr(out)))
+    return out
+
+
 # ------------------------------------------------------------------ FSE
 DEFAULT_FSE_SEG = 1024
 

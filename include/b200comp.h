@@ -46,7 +46,8 @@ int         b200_ctx_sync(b200_ctx* ctx);
 uint64_t    b200_ctx_launches(b200_ctx* ctx); /* kernels launched so far */
 /* When enabled, every codec call brackets its dominant kernel with CUDA events on
  * the context's stream (kind: 0 LZ77 parse, 1 LZ77 decode, 2 Huffman encode,
- * 3 Huffman decode, 4 FSE encode, 5 FSE decode). Up to 512 entries are kept since the
+ * 3 Huffman decode, 4 FSE encode, 5 FSE decode, 6 deflate entropy encode, 7 deflate entropy
+ * decode). Up to 512 entries are kept since the
  * last b200_ctx_set_timing call; b200_ctx_timing_get waits for entry i. */
 int         b200_ctx_set_timing(b200_ctx* ctx, int enable);
 int         b200_ctx_timing_count(b200_ctx* ctx);
@@ -147,6 +148,58 @@ int b200_lz77_encode_debug_dev(b200_ctx* ctx, int variant, const uint8_t* d_in, 
 int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d_stream,
                          const uint64_t* d_block_off, const uint64_t* d_block_sizes,
                          uint64_t n, uint64_t block_size, uint8_t* d_out);
+
+/* ---- deflate token entropy stage (completes algorithms/deflate/lz77.c:279
+ *      "TODO: Build huffman tree and encode compressed buffer") -----------------
+ * Per LZ block: frequencies[286] exactly as lz77_compress counts them (lz77.c:206,231,273 with
+ * huffman.c:49-62: literal byte, or 256 + clz16(offset) per match), codes by the heap rule of
+ * algorithms/huffman/huffman.c:100-250 over the 286 symbols, MSB-first u32 words as write_bits
+ * (deflate/huffman.c:18-48). literal = code[byte]; match = code[256+k], the 15-k offset bits below
+ * the leading one, the length in 5 bits. The parts the reference only declares are specified by
+ * oracle/port/deflate_huff_port.c (parity unpinned there). */
+#define B200_DFL_NSYM   286u  /* NUM_CODES, algorithms/deflate/huffman.h:6          */
+#define B200_DFL_STRIDE 288u  /* row stride of freq / codes / lens                  */
+#define B200_DFL_CHUNK  4096u /* token bytes per encode chunk (one CTA)             */
+#define B200_DFL_SUB    256u  /* token bytes per decode sub-chunk (one thread)      */
+typedef struct {
+    uint64_t bytes;           /* total size of the side buffer                              */
+    uint64_t nblocks;         /* LZ blocks = table scopes: ceil(n / block_size)             */
+    uint64_t nchunks;         /* nblocks * chunks_per_block chunk slots                     */
+    uint64_t chunks_per_block;/* ceil((2 * block_size + 2) / 4096): worst-case token bytes  */
+    uint64_t off_freq;        /* u32[nblocks][288] frequencies[286] (lz77.c:206)            */
+    uint64_t off_codes;       /* u32[nblocks][288] codes, right-aligned                     */
+    uint64_t off_lens;        /* u8 [nblocks][288] code lengths                             */
+    uint64_t off_tree;        /* i16[nblocks][571][2] children; leaf = {-1, symbol}         */
+    uint64_t off_meta;        /* u32[nblocks][4] = {status, distinct, root, max_len}; status 1 = no tokens, 2 = a code > 32 bits */
+    uint64_t off_tok_off;     /* u64[nblocks+1] byte offset of each block's tokens          */
+    uint64_t off_tok_sizes;   /* u64[nblocks]   token bytes of each block                   */
+    uint64_t off_block_bits;  /* u64[nblocks]   bits of each block's stream                 */
+    uint64_t off_block_word;  /* u64[nblocks+1] first u32 word of each block; [nblocks]=total */
+    uint64_t off_chunk_state; /* u8 [nchunks]   1 = the chunk's first 2-byte unit is the tail of a match */
+    uint64_t off_chunk_bits;  /* u32[nchunks]   bits of each chunk                          */
+    uint64_t off_chunk_off;   /* u64[nchunks+1] absolute bit offset of each chunk           */
+    uint64_t off_sub_off;     /* u32[nchunks*16] bit offset of each sub-chunk in its chunk; bit 31 = starts with a tail unit */
+} b200_dfl_layout;
+/* n / block_size: the UNCOMPRESSED size and LZ block size the tokens came from (0 = one block) */
+int b200_dfl_layout_for(uint64_t n, uint64_t block_size, b200_dfl_layout* out);
+uint64_t b200_dfl_max_words(uint64_t n, uint64_t block_size);
+/* byte tokens (b200_lz77_encode_dev variant 1: d_out, d_block_off, d_block_sizes) -> packed words.
+ * d_tokens must be 16-byte aligned with tokens_capacity bytes allocated. */
+int b200_dfl_encode_dev(b200_ctx* ctx, const uint8_t* d_tokens, uint64_t tokens_capacity,
+                        const uint64_t* d_tok_off, const uint64_t* d_tok_sizes, uint64_t n, uint64_t block_size,
+                        uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
+                        uint64_t* h_total_words, uint32_t* h_worst_status);
+/* packed words -> the byte tokens, placed at the offsets recorded in the side buffer */
+int b200_dfl_decode_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words, const uint8_t* d_side,
+                        uint64_t side_bytes, uint64_t n, uint64_t block_size, uint8_t* d_tokens_out);
+/* both stages: lz77_compress per block + the entropy stage / its inverse + the LZ77 decoder.
+ * d_tokens is a scratch of b200_lz77_max_bytes(1, n, block_size) bytes. */
+int b200_deflate_compress_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
+                              uint8_t* d_tokens, uint64_t tokens_capacity, uint64_t* d_tok_sizes, uint64_t* d_tok_off,
+                              uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
+                              uint64_t* h_total_words, uint32_t* h_worst_status);
+int b200_deflate_decompress_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words, const uint8_t* d_side,
+                                uint64_t side_bytes, uint64_t n, uint64_t block_size, uint8_t* d_tokens, uint8_t* d_out);
 
 /* ---- FSE (C mirror of algorithms/fse/src/main.zig:50-189) ------------------- */
 #define B200_FSE_TABLE_LOG 8u

@@ -192,6 +192,26 @@ def ref_deflate_lz77_compress_blocks(data, block, persistent=False, threads=0):
     return [out[b * stride: b * stride + int(sizes[b])] for b in range(nb)], sizes
 
 
+def ref_deflate_token_frequencies(tokens):
+    """frequencies[286] through the reference's own append_huffman_tree_literal/_pair."""
+    t = _as_u8(tokens)
+    fr = np.zeros(286, dtype=np.uint32)
+    _lib("deflate_ref").orc_ref_deflate_token_frequencies(_p(t, _u8p), C.c_uint64(t.size), _p(fr, _u32p))
+    return fr
+
+
+def ref_deflate_write_bits(values, lengths):
+    """The reference's BitWriter (deflate/huffman.c:9-48) fed with (value, length) pairs -> (words, bits)."""
+    v = np.ascontiguousarray(values, dtype=np.uint32)
+    ln = np.ascontiguousarray(lengths, dtype=np.uint8)
+    cap = int(ln.astype(np.uint64).sum()) // 32 + 4
+    words = np.zeros(cap, dtype=np.uint32)
+    f = _lib("deflate_ref").orc_ref_deflate_write_bits
+    f.restype = C.c_uint64
+    bits = f(_p(v, _u32p), _p(ln, _u8p), C.c_uint64(v.size), _p(words, _u32p), C.c_uint64(cap))
+    return words[: (bits + 31) // 32].copy(), int(bits)
+
+
 def ref_threads():
     f = _lib("deflate_ref").orc_ref_deflate_threads
     return int(f())
@@ -294,6 +314,46 @@ def port_huffman_decompress(words, buffer_size, codes, lens, expect):
     f.restype = C.c_uint64
     n = f(_p(w, _u32p), C.c_uint64(w.size), C.c_uint64(buffer_size), _p(codes, _u32p), _p(lens, _u8p), _p(out, _u8p), C.c_uint64(cap))
     return out[: min(n, cap)].copy(), n
+
+
+def port_dfl_frequencies(tokens):
+    t = _as_u8(tokens)
+    fr = np.zeros(286, dtype=np.uint64)
+    _lib("oracle_port").port_dfl_frequencies(_p(t, _u8p), C.c_uint64(t.size), _p(fr, _u64p))
+    return fr
+
+
+def port_dfl_build(freq):
+    fr = np.ascontiguousarray(freq, dtype=np.uint64)
+    codes = np.zeros(286, dtype=np.uint32)
+    lens = np.zeros(286, dtype=np.uint8)
+    distinct = _lib("oracle_port").port_dfl_build(_p(fr, _u64p), _p(codes, _u32p), _p(lens, _u8p))
+    return codes, lens, distinct
+
+
+def port_dfl_encode(tokens):
+    """One block of byte tokens -> dict(freq, codes, lens, words, bits) of the entropy stage."""
+    t = _as_u8(tokens)
+    fr = port_dfl_frequencies(t)
+    codes, lens, distinct = port_dfl_build(fr)
+    words = np.zeros(t.size // 2 + 8, dtype=np.uint32)   # <= 32 bits per 2-byte unit
+    f = _lib("oracle_port").port_dfl_encode
+    f.restype = C.c_uint64
+    bits = int(f(_p(t, _u8p), C.c_uint64(t.size), _p(codes, _u32p), _p(lens, _u8p), _p(words, _u32p)))
+    return dict(freq=fr, codes=codes, lens=lens, distinct=distinct, words=words[: (bits + 31) // 32].copy(), bits=bits)
+
+
+def port_dfl_decode(words, codes, lens, nbytes):
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    codes = np.ascontiguousarray(codes, dtype=np.uint32)
+    lens = np.ascontiguousarray(lens, dtype=np.uint8)
+    out = np.zeros(nbytes + 8, dtype=np.uint8)
+    used = C.c_uint64(0)
+    rc = _lib("oracle_port").port_dfl_decode(_p(w, _u32p), C.c_uint64(w.size), _p(codes, _u32p), _p(lens, _u8p),
+                                             C.c_uint64(nbytes), _p(out, _u8p), C.byref(used))
+    if rc:
+        raise RuntimeError("deflate entropy stage: corrupt stream")
+    return out[:nbytes].copy(), used.value
 
 
 def port_fse_normalize(freq):

@@ -49,19 +49,20 @@ static int heap_pop(int* heap, int* size, const hnode_t* nd) {
     return top;
 }
 
-/* freq[256] -> codes/lens. The reference sums u32 frequencies in u32
- * (init_node takes uint32_t, huffman.c:165-168,204); inputs < 4 GiB never wrap.
+/* freq[nsym] -> codes/lens (nsym <= PORT_HUFF_MAX_SYMS). The reference sums u32 frequencies
+ * in u32 (init_node takes uint32_t, huffman.c:165-168,204); inputs < 4 GiB never wrap.
  * Returns the number of distinct symbols; 0 or 1 distinct symbols is the
  * reference's exit(1) case (U6) and yields all-zero lengths. nodes_out (optional,
- * 511 entries x 3 ints: left,right,sym) receives the tree, root index returned
- * in *root_out. */
-int port_huffman_build(const uint64_t* freq, uint32_t* codes, uint8_t* lens, int* nodes_out, int* root_out) {
-    hnode_t nd[511];
-    int heap[256];
+ * 2*nsym-1 entries x 3 ints: left,right,sym) receives the tree, root index returned
+ * in *root_out. nsym = 256 is algorithms/huffman; nsym = 286 is the alphabet of the
+ * deflate scaffolding (NUM_CODES, algorithms/deflate/huffman.h:6). */
+int port_huffman_build_n(const uint64_t* freq, int nsym, uint32_t* codes, uint8_t* lens, int* nodes_out, int* root_out) {
+    hnode_t nd[2 * PORT_HUFF_MAX_SYMS - 1];
+    int heap[PORT_HUFF_MAX_SYMS];
     int size = 0, nn = 0;
-    memset(codes, 0, 256 * sizeof(uint32_t));
-    memset(lens, 0, 256);
-    for (int s = 0; s < 256; ++s) {
+    memset(codes, 0, (size_t)nsym * sizeof(uint32_t));
+    memset(lens, 0, (size_t)nsym);
+    for (int s = 0; s < nsym; ++s) {
         if (!freq[s]) continue;
         nd[nn].freq = (uint32_t)freq[s]; nd[nn].left = nd[nn].right = -1; nd[nn].sym = s;
         heap[size++] = nn++;
@@ -80,7 +81,7 @@ int port_huffman_build(const uint64_t* freq, uint32_t* codes, uint8_t* lens, int
     if (root_out) *root_out = root;
     if (nodes_out) for (int i = 0; i < nn; ++i) { nodes_out[3 * i] = nd[i].left; nodes_out[3 * i + 1] = nd[i].right; nodes_out[3 * i + 2] = nd[i].sym; }
     /* iterative DFS, code is kept in 64 bits only to detect >32-bit depth (U7) */
-    struct { int node; uint32_t code; int len; } st[512];
+    struct { int node; uint32_t code; int len; } st[2 * PORT_HUFF_MAX_SYMS];
     int sp = 0;
     st[sp].node = root; st[sp].code = 0; st[sp].len = 0; ++sp;
     while (sp) {
@@ -92,6 +93,10 @@ int port_huffman_build(const uint64_t* freq, uint32_t* codes, uint8_t* lens, int
         st[sp].node = nd[v].left;  st[sp].code = c;     st[sp].len = l + 1; ++sp;
     }
     return distinct;
+}
+
+int port_huffman_build(const uint64_t* freq, uint32_t* codes, uint8_t* lens, int* nodes_out, int* root_out) {
+    return port_huffman_build_n(freq, 256, codes, lens, nodes_out, root_out);
 }
 
 void port_histogram(const uint8_t* in, uint64_t n, uint64_t* freq) {

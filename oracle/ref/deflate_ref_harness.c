@@ -104,3 +104,34 @@ int orc_ref_deflate_lz77_compress_blocks(const uint8_t* in, uint64_t n, uint64_t
 }
 
 int orc_ref_deflate_threads(void) { return omp_get_max_threads(); }
+
+/* frequencies[286] as lz77_compress counts them (deflate/lz77.c:206,231,273): the harness walks a
+ * token stream and calls the reference's own append_huffman_tree_literal / _pair
+ * (deflate/huffman.c:49-62) for every token. freq: 286 entries, zeroed here. */
+void orc_ref_deflate_token_frequencies(const uint8_t* tok, uint64_t nbytes, uint32_t* freq) {
+    memset(freq, 0, NUM_CODES * sizeof(uint32_t));
+    uint64_t i = 0;
+    while (i + 1 < nbytes) {
+        if (tok[i] == 1 && i + 3 < nbytes) {
+            append_huffman_tree_pair(freq, (uint16_t)(tok[i + 1] | (tok[i + 2] << 8)));
+            i += 4;
+        } else {
+            append_huffman_tree_literal(freq, (char)tok[i + 1]);
+            i += 2;
+        }
+    }
+}
+
+/* the reference's bit writer (deflate/huffman.c:9-48) fed with a list of (value, length) pairs;
+ * values are pre-masked to their length as the code tables of gather_codes are. Returns the
+ * number of bits; words must hold nbits/32 + 2 entries. */
+uint64_t orc_ref_deflate_write_bits(const uint32_t* values, const uint8_t* lengths, uint64_t count,
+                                    uint32_t* words, uint64_t words_cap) {
+    orc_arena_reserve((size_t)words_cap * 4 + 4096);
+    BitWriter w;
+    init_bitwriter(&w, words_cap * 4);
+    for (uint64_t i = 0; i < count; ++i) if (lengths[i]) write_bits(&w, values[i], lengths[i]);
+    const uint64_t nw = w.word_idx + (w.bit_idx ? 1 : 0);
+    memcpy(words, w.buffer, (size_t)(nw < words_cap ? nw : words_cap) * 4);
+    return w.word_idx * 32 + w.bit_idx;
+}

@@ -47,6 +47,14 @@ def main():
         c["lz77"] = {"bit_index": bits, "fnv": "%016x" % fnv1a64(bytes(s))}
         t = ob.ref_deflate_lz77_compress(data)
         c["deflate"] = {"bytes": int(t.size), "fnv": "%016x" % fnv1a64(bytes(t))}
+        # frequencies[286] of the token stream through the reference's own append_huffman_tree_literal/_pair
+        # (deflate/lz77.c:231,273; deflate/huffman.c:49-62): pinned. The entropy-coded stream is the
+        # oracle port's (the reference stops at its TODO, lz77.c:279): "port" marks it as unpinned.
+        fr = ob.ref_deflate_token_frequencies(t)
+        e = ob.port_dfl_encode(t)
+        c["deflate_freq"] = {"nonzero": {str(i): int(fr[i]) for i in np.nonzero(fr)[0]}}
+        c["deflate_huff_port"] = {"bits": int(e["bits"]), "words_fnv": "%016x" % fnv1a64(e["words"].tobytes()),
+                                  "lens": bytes(e["lens"]).hex()}
         if len(data) <= 100:
             c["lz77"]["hex"] = bytes(s).hex()
             c["deflate"]["hex"] = bytes(t).hex()

@@ -189,3 +189,82 @@ def test_huffman_heap_ties(ob):
         c1, l1 = ob.ref_huffman_tables(data)
         c2, l2, _ = ob.port_huffman_build(f)
         assert np.array_equal(c1, c2) and np.array_equal(l1, l2)
+
+
+# ----------------------------------------------------------------- deflate token entropy stage
+def _token_pieces(tok, codes, lens):
+    """(value, length) list of the entropy stage, built independently of the port in plain Python"""
+    vals, ls = [], []
+    i = 0
+    while i + 1 < len(tok):
+        if tok[i] == 1:
+            off = int(tok[i + 1]) | int(tok[i + 2]) << 8
+            k = 16 - off.bit_length()
+            vals.append(int(codes[256 + k])); ls.append(int(lens[256 + k]))
+            if k < 15:
+                vals.append(off & ((1 << (15 - k)) - 1)); ls.append(15 - k)
+            vals.append(int(tok[i + 3])); ls.append(5)
+            i += 4
+        else:
+            vals.append(int(codes[tok[i + 1]])); ls.append(int(lens[tok[i + 1]]))
+            i += 2
+    return vals, ls
+
+
+def test_deflate_frequencies_vs_golden(ob, cases, golden):
+    """frequencies[286] (deflate/lz77.c:206,231,273) — golden values come from the reference's own
+    append_huffman_tree_literal/_pair; the entropy-coded stream is pinned to the port's spec vector"""
+    for name, data in cases.items():
+        g = golden["cases"][name]
+        tok = ob.port_deflate_lz77_compress(data)
+        tok = tok[0] if isinstance(tok, tuple) else tok
+        fr = ob.port_dfl_frequencies(tok)
+        want = np.zeros(286, dtype=np.uint64)
+        for k, v in g["deflate_freq"]["nonzero"].items():
+            want[int(k)] = v
+        assert np.array_equal(fr, want), name
+        e = ob.port_dfl_encode(tok)
+        gp = g["deflate_huff_port"]
+        assert e["bits"] == gp["bits"] and "%016x" % fnv1a64(e["words"].tobytes()) == gp["words_fnv"], name
+        assert bytes(e["lens"]).hex() == gp["lens"], name
+        back, used = ob.port_dfl_decode(e["words"], e["codes"], e["lens"], len(tok))
+        assert used == e["bits"] and np.array_equal(back, tok), name
+
+
+def test_deflate_entropy_stage_vs_compiled_reference(ob):
+    """the pieces the reference does define: frequencies through its append_* functions, the packed
+    words through its write_bits (deflate/huffman.c:18-48), and for a literal-only stream the code
+    table of algorithms/huffman (same heap rule over 256 symbols)"""
+    if not ob.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from compression_algorithms_b200 import corpus
+    for kind in (0, 1, 3):
+        d = corpus.generate(70000, kind, 31)
+        tok = ob.ref_deflate_lz77_compress(d)
+        e = ob.port_dfl_encode(tok)
+        assert np.array_equal(ob.ref_deflate_token_frequencies(tok).astype(np.uint64), e["freq"])
+        vals, ls = _token_pieces(tok, e["codes"], e["lens"])
+        w, bits = ob.ref_deflate_write_bits(vals, ls)
+        assert bits == e["bits"] and np.array_equal(w, e["words"])
+    # literal-only token stream over bytes: the 286-symbol build must agree with the reference's
+    # 256-symbol tables (symbols 256.. are absent)
+    d = corpus.generate(20000, 0, 2)
+    tok = np.zeros(2 * d.size, dtype=np.uint8)
+    tok[1::2] = d
+    tok[0::2] = 0
+    e = ob.port_dfl_encode(tok)
+    c1, l1 = ob.ref_huffman_tables(d)
+    assert np.array_equal(e["codes"][:256], c1) and np.array_equal(e["lens"][:256], l1)
+    r = ob.ref_huffman_compress(d)
+    assert np.array_equal(e["words"], r["words"])
+
+
+def test_deflate_entropy_stage_degenerate(ob):
+    for data in (b"a", b"ab", b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa", bytes([7]) * 5000):
+        tok = ob.port_deflate_lz77_compress(data)
+        tok = tok[0] if isinstance(tok, tuple) else tok
+        e = ob.port_dfl_encode(tok)
+        back, used = ob.port_dfl_decode(e["words"], e["codes"], e["lens"], len(tok))
+        assert used == e["bits"] and np.array_equal(back, tok)
+        if e["distinct"] == 1:
+            assert e["lens"].max() == 1 and e["bits"] >= 1
