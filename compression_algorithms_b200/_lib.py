@@ -81,6 +81,8 @@ def core():
         lib.b200_dfl_decode_dev.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
         lib.b200_deflate_compress_dev.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, C.c_uint64, u64p, u32p]
         lib.b200_deflate_decompress_dev.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]
+        lib.b200_deflate_compress_host.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, u64p, u32p]
+        lib.b200_deflate_decompress_host.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
         if hasattr(lib, "b200_fse_layout_for"):
             lib.b200_fse_layout_for.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(FseLayout)]
             lib.b200_fse_max_words.restype = C.c_uint64

@@ -349,3 +349,56 @@ extern "C" int b200_fse_normalize_host(b200_ctx* ctx, const uint8_t* h_in, uint6
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
+
+// deflate with the entropy stage from / to HOST buffers (what a completed deflate.c compress() /
+// decompress() pair would call): H2D -> lz77_compress per block -> entropy stage -> D2H of the words
+// and the side buffer (tables + decode index; like Huffman's it is not part of the compressed words).
+extern "C" int b200_deflate_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
+                                          uint32_t* h_words, uint64_t words_capacity, uint8_t* h_side, uint64_t side_bytes,
+                                          uint64_t* h_total_words, uint32_t* h_worst_status) {
+    if (n == 0) { if (h_total_words) *h_total_words = 0; if (h_worst_status) *h_worst_status = 0; return B200_OK; }
+    b200_dfl_layout L;
+    B200_TRY(b200_dfl_layout_for(n, block_size, &L));
+    if (!h_side || side_bytes < L.bytes) { B200_SET_ERR("deflate: host side buffer too small (%llu needed)", (unsigned long long)L.bytes); return B200_ERR_CAPACITY; }
+    const uint64_t cap = b200_dfl_max_words(n, block_size);
+    const uint64_t tok_cap = lz_cap(B200_LZ_DEFLATE, n, L.nblocks);
+    uint8_t *d_in, *d_tok, *d_side; uint32_t* d_words; uint64_t* d_idx;
+    B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
+    B200_TRY(b200_scratch(ctx, 9, tok_cap, reinterpret_cast<void**>(&d_tok)));
+    B200_TRY(b200_scratch(ctx, 10, (2 * L.nblocks + 2) * 8, reinterpret_cast<void**>(&d_idx)));
+    B200_TRY(b200_scratch(ctx, 11, cap * 4, reinterpret_cast<void**>(&d_words)));
+    B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
+    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t total = 0; uint32_t worst = 0;
+    B200_TRY(b200_deflate_compress_dev(ctx, d_in, n, block_size, d_tok, tok_cap, d_idx, d_idx + L.nblocks, d_words, cap,
+                                       d_side, L.bytes, &total, &worst));
+    if (h_total_words) *h_total_words = total;
+    if (h_worst_status) *h_worst_status = worst;
+    if (worst) { B200_SET_ERR("deflate: a block needs a code longer than 32 bits (status %u)", worst); return B200_ERR_DOMAIN; }
+    if (total > words_capacity) { B200_SET_ERR("deflate: output needs %llu words, buffer has %llu", (unsigned long long)total, (unsigned long long)words_capacity); return B200_ERR_CAPACITY; }
+    CUDA_TRY(cudaMemcpyAsync(h_words, d_words, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h_side, d_side, L.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_deflate_decompress_host(b200_ctx* ctx, const uint32_t* h_words, uint64_t total_words,
+                                            const uint8_t* h_side, uint64_t side_bytes, uint64_t n, uint64_t block_size,
+                                            uint8_t* h_out) {
+    if (n == 0) return B200_OK;
+    b200_dfl_layout L;
+    B200_TRY(b200_dfl_layout_for(n, block_size, &L));
+    if (side_bytes < L.bytes) { B200_SET_ERR("deflate: host side buffer too small"); return B200_ERR_CAPACITY; }
+    const uint64_t tok_cap = lz_cap(B200_LZ_DEFLATE, n, L.nblocks);
+    uint8_t *d_out, *d_tok, *d_side; uint32_t* d_words;
+    B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_out)));
+    B200_TRY(b200_scratch(ctx, 9, tok_cap, reinterpret_cast<void**>(&d_tok)));
+    B200_TRY(b200_scratch(ctx, 11, (total_words + 4) * 4, reinterpret_cast<void**>(&d_words)));
+    B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
+    CUDA_TRY(cudaMemcpyAsync(d_words, h_words, total_words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_side, h_side, L.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_deflate_decompress_dev(ctx, d_words, total_words, d_side, L.bytes, n, block_size, d_tok, d_out));
+    CUDA_TRY(cudaMemcpyAsync(h_out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}

@@ -40,6 +40,7 @@ constexpr uint32_t BM_WORDS = (SLOTS + GUARD_BITS) / 32;     // 34816
 constexpr uint32_t PRE_CHUNK = 8;                            // words per rank-prefix entry
 constexpr uint32_t PRE_N = BM_WORDS / PRE_CHUNK;             // 4352
 constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t LONER = 0xFFFFFFFFu;                      // P3 marker: entry alone in its cluster (not a valid hash | range << 21)
 constexpr uint32_t MAXB = 65536;                             // max block bytes on this path
 constexpr uint32_t NTHREADS = 1024;
 constexpr uint32_t CARRY_BYTES = (MAXB + 64) * 4 + 32768 * 4 + MAXB * 4 + 32768 * 4;
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 else for (uint32_t k = 0; k < 16 && i + k < SZ_DATA; ++k) data[i + k] = (i + k < avail) ? __ldg(src + i + k) : 0;
             }
             for (uint32_t i = tid; i < BM_WORDS; i += NTHREADS) bm[i] = 0;
+            for (uint32_t i = tid; i < BM_WORDS / 32; i += NTHREADS) pre[i] = 0;   // P1's "word is full" summary (pre is free until P2)
             if (tid == 0) ms->ncar = 0;
         }
         __syncthreads();
@@ -254,6 +256,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         // (a per-home "frontier hint" table that lets later walks skip the full words of a hot chain was
         // tried and did not pay: 175 K -> 190 K cycles; the phase is bound by the latency of the
         // dependent hash -> read -> atomicOr chain of the 64 positions each thread owns)
+        // The k-th occurrence of a hot 4-gram would walk k/32 words of its chain; a summary bit per bitmap
+        // word ("known to be full", set by whoever takes its last free bit; bits are never cleared in this
+        // phase, so a set summary bit is always right) lets a walk jump to the first word that may have room.
+        uint32_t* summ = pre;
         for (uint32_t i = C + tid; i < len; i += NTHREADS) {
             uint32_t s = lz_hash(sm_word(data, i));
             for (;;) {
@@ -261,10 +267,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 const uint32_t free_bits = ~bm[wi] & (0xFFFFFFFFu << (s & 31));
                 if (free_bits) {
                     const uint32_t bit = 1u << (__ffs(free_bits) - 1);
-                    if (!(atomicOr(&bm[wi], bit) & bit)) break;
+                    const uint32_t old = atomicOr(&bm[wi], bit);
+                    if (!(old & bit)) {
+                        if ((old | bit) == 0xFFFFFFFFu) atomicOr(&summ[wi >> 5], 1u << (wi & 31));
+                        break;
+                    }
                     continue;  // lost the race for that bit: look again in the same word
                 }
-                s = (wi + 1) << 5;
+                uint32_t nw = wi + 1;
+                uint32_t open = ~summ[nw >> 5] & (0xFFFFFFFFu << (nw & 31));
+                while (!open) { nw = ((nw >> 5) + 1) << 5; open = ~summ[nw >> 5]; }   // the guard words behind the table never fill up
+                s = ((nw & ~31u) + (uint32_t)(__ffs(open) - 1)) << 5;
                 if (V == 1 && s >= SLOTS) s = 0;   // the deflate insert wraps (deflate/lz77.c:99-101)
             }
         }
@@ -400,12 +413,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             const uint32_t i = base + lane;
             if (i < p_hi) {
                 const uint32_t h = lz_hash(sm_word(data, i));
+                // A position whose home slot is a cluster of its own (both neighbours free in the no-expiry
+                // occupancy) is the only entry that ever touches that slot: it lands there, its find sees a slot
+                // that was never used (-> literal candidate) and no other probe walk reaches it. Such entries
+                // (a third of enwik-shaped text) skip the partition and the simulation altogether. Not on a
+                // slice that hands its slots over (cs[] would be missing).
+                const uint32_t wi = h >> 5, bi = h & 31u, wv = bm[wi];
+                const uint32_t below = bi ? (wv >> (bi - 1u)) & 1u : (wi ? bm[wi - 1] >> 31 : 1u);
+                const uint32_t above = bi != 31u ? (wv >> (bi + 1u)) & 1u : (bm[wi + 1] & 1u);
+                if (last_slice && !below && !above && h != SLOTS - 1u) tokb[i] = LONER;
+                else {
                 uint32_t r = 0;             // largest r with cut[r] <= h (0 also for the cluster below cut[0])
 #pragma unroll
                 for (uint32_t st = 16; st > 0; st >>= 1) if (ms->cut[r + st] <= h) r += st;
                 if (V == 1 && h >= top_start) r = 0;
                 tokb[i] = h | (r << 21);    // kept for pass 2 (the token array is free until P4)
                 atomicAdd(&ms->cnt[warp][r], 1u);
+                }
             }
         }
         __syncthreads();
@@ -432,10 +456,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         uint32_t hr_next = p_lo + lane < p_hi ? tokb[p_lo + lane] : 0u;
         for (uint32_t base = p_lo; base < p_hi; base += 32) {
             const uint32_t i = base + lane;
-            const bool valid = i < p_hi;
+            const bool in_range = i < p_hi;
             const uint32_t hr = hr_next;
             if (i + 32 < p_hi) hr_next = tokb[i + 32];       // prefetch
             uint32_t r = 0xFFu, c = 0;
+            const bool loner = in_range && hr == LONER;
+            // (a loner keeps its LONER mark in tokb: P5 / P6 read it as "literal candidate")
+            const bool valid = in_range && !loner;
             if (valid) { r = hr >> 21; c = bm_rank(bm, pre, hr & 0x1FFFFFu); }
             const uint32_t peers = __match_any_sync(0xffffffffu, r);
             const uint32_t myrank = __popc(peers & lt_mask);
@@ -594,7 +621,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                                 if (d < tv) lo += st;
                             }
                             const uint32_t qmask = lo >= 32 ? 0u : (0xFFFFFFFFu << lo);
-                            uint32_t cm = __ballot_sync(0xffffffffu, tv <= dmax && sl >= hmin && (qmask & unplaced) != 0u);
+                            const bool cand = tv <= dmax && sl >= hmin && (qmask & unplaced) != 0u;
+                            uint32_t cm = __ballot_sync(0xffffffffu, cand);
+                            // Fast path: when no unplaced entry has its home strictly inside this group (so the same set
+                            // E of entries may take any of its slots) and the candidates' release indices lo are
+                            // non-decreasing in slot order (slots of a chain die in the order they were filled), the
+                            // slot-by-slot greedy has a closed form: the k-th candidate takes the entry of E-rank
+                            // rho_k = max(rank_E(lo_k), rho_{k-1} + 1) = k + max_{i <= k}(rank_E(lo_i) - i), one prefix
+                            // maximum for the whole group instead of one ballot + shuffle round per slot.
+                            if (cm & (cm - 1u)) {                                           // two or more candidates
+                                const uint32_t gs = g << 5;
+                                const uint32_t am_g = __ballot_sync(0xffffffffu, home_s <= gs);
+                                const uint32_t inside = __ballot_sync(0xffffffffu, home_s > gs && home_s < gs + 32u) & unplaced;
+                                uint32_t lom = cand ? lo : 0u;                              // inclusive prefix maximum of lo over the candidates
+#pragma unroll
+                                for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, lom, d); if (lane >= d) lom = max(lom, t); }
+                                const uint32_t lom_prev = __shfl_up_sync(0xffffffffu, lom, 1);
+                                const bool viol = cand && lane > 0 && lo < lom_prev;
+                                if (!inside && !__ballot_sync(0xffffffffu, viol)) {
+                                    const uint32_t E = unplaced & am_g;
+                                    const int k = (int)__popc(cm & lt_mask);
+                                    int v = cand ? (int)__popc(E & ((1u << lo) - 1u)) - k : -64;    // cand implies lo < 32
+#pragma unroll
+                                    for (uint32_t d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, t); }
+                                    uint32_t rho = (uint32_t)(v + k);
+                                    const bool take = cand && rho < (uint32_t)__popc(E);
+                                    uint32_t e = 0;
+                                    if (take) {                                             // position of the rho-th set bit of E
+                                        uint32_t mk = E, c;
+                                        c = __popc(mk & 0xFFFFu); if (rho >= c) { rho -= c; e = 16; mk >>= 16; }
+                                        c = __popc(mk & 0xFFu);   if (rho >= c) { rho -= c; e += 8; mk >>= 8; }
+                                        c = __popc(mk & 0xFu);    if (rho >= c) { rho -= c; e += 4; mk >>= 4; }
+                                        c = __popc(mk & 0x3u);    if (rho >= c) { rho -= c; e += 2; mk >>= 2; }
+                                        if (rho >= (mk & 1u)) e += 1;
+                                        aslot[e] = (uint16_t)sl;
+                                    }
+                                    const uint32_t assigned = __reduce_or_sync(0xffffffffu, take ? (1u << e) : 0u);
+                                    __syncwarp();
+                                    if ((assigned >> lane) & 1u) my_e = aslot[lane];
+                                    unplaced &= ~assigned;
+                                    cm = 0;
+                                }
+                            }
                             while (cm && unplaced) {
                                 const int j = __ffs(cm) - 1;
                                 cm &= cm - 1;
@@ -697,7 +765,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         for (uint32_t i0 = tid; i0 < len; i0 += 8 * NTHREADS) {   // eight independent reads in flight per thread
             uint32_t tv[8];
 #pragma unroll
-            for (uint32_t k = 0; k < 8; ++k) { const uint32_t i = i0 + k * NTHREADS; tv[k] = i < len ? tokb[i] : 0u; }
+            for (uint32_t k = 0; k < 8; ++k) { const uint32_t i = i0 + k * NTHREADS; tv[k] = i < len ? tokb[i] : 0u; if (tv[k] == LONER) tv[k] = 0u; }
 #pragma unroll
             for (uint32_t k = 0; k < 8; ++k) {
                 const uint32_t i = i0 + k * NTHREADS;
@@ -793,7 +861,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             for (uint32_t p0 = tid; p0 < len; p0 += 4 * NTHREADS) {
                 uint32_t tk[4];
 #pragma unroll
-                for (uint32_t k = 0; k < 4; ++k) { const uint32_t p = p0 + k * NTHREADS; tk[k] = p < len ? tokb[p] : 0u; }
+                for (uint32_t k = 0; k < 4; ++k) { const uint32_t p = p0 + k * NTHREADS; tk[k] = p < len ? tokb[p] : 0u; if (tk[k] == LONER) tk[k] = 0u; }
 #pragma unroll
                 for (uint32_t k = 0; k < 4; ++k) {
                     const uint32_t p = p0 + k * NTHREADS;
@@ -825,7 +893,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 uint64_t acc = 0;
                 for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[PADX(p)]) {
                     if (p < p_start) continue;
-                    const uint32_t t = tokb[p];
+                    uint32_t t = tokb[p];
+                    if (t == LONER) t = 0u;
                     uint32_t v, nb;
                     if (t == 0) { v = (uint32_t)data[p] << 1; nb = 9; }
                     else { v = 1u | ((t & 0xFFFFu) << 1) | ((t >> 16) << 15); nb = 19; }

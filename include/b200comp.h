@@ -250,6 +250,15 @@ int b200_huffman_decompress_serial_host(b200_ctx* ctx, const uint32_t* h_words, 
                                         uint64_t buffer_size, const uint32_t* h_codes, const uint8_t* h_lens,
                                         uint8_t* h_out, uint64_t out_capacity, uint64_t* h_count);
 
+/* deflate with the entropy stage (lz77_compress per block + the Huffman-coded token stream);
+ * h_side receives b200_dfl_layout.bytes of tables and decode index */
+int b200_deflate_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
+                               uint32_t* h_words, uint64_t words_capacity, uint8_t* h_side, uint64_t side_bytes,
+                               uint64_t* h_total_words, uint32_t* h_worst_status);
+int b200_deflate_decompress_host(b200_ctx* ctx, const uint32_t* h_words, uint64_t total_words,
+                                 const uint8_t* h_side, uint64_t side_bytes, uint64_t n, uint64_t block_size,
+                                 uint8_t* h_out);
+
 int b200_huffman_tables_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
                              uint8_t* h_side, uint64_t side_bytes);
 int b200_huffman_compress_codes_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n,

@@ -133,3 +133,26 @@ def test_roundtrip_32mb(ctx, ob):
     for b in (0, 17, 255, 511):
         t = st.lz.out[int(off[b]): int(off[b + 1])].cpu().numpy()
         assert ob.port_dfl_encode(t)["bits"] == int(bb[b])
+
+
+def test_host_buffer_entry_points(ctx, ob):
+    """b200_deflate_compress_host / _decompress_host: same words as the device-resident path, round trip"""
+    import ctypes as C
+    from compression_algorithms_b200 import _lib, device as dv
+    data = _corpus(5 * 65536 + 999, seed=21)
+    n = data.size
+    lib = _lib.core()
+    L = dv.dfl_layout(n, 65536)
+    cap = int(lib.b200_dfl_max_words(n, 65536))
+    words = np.zeros(cap, dtype=np.uint32)
+    side = np.zeros(L.bytes, dtype=np.uint8)
+    tw, ws = C.c_uint64(0), C.c_uint32(0)
+    _lib.check(lib.b200_deflate_compress_host(ctx.handle, data.ctypes.data, n, 65536, words.ctypes.data, cap,
+                                              side.ctypes.data, side.size, C.byref(tw), C.byref(ws)))
+    st = dv.deflate_compress(ctx, _to_dev(ctx, data), 65536)
+    assert tw.value == st.total_words and ws.value == 0
+    assert np.array_equal(words[: tw.value], u32(st.words[: st.total_words]))
+    out = np.zeros(n, dtype=np.uint8)
+    _lib.check(lib.b200_deflate_decompress_host(ctx.handle, words.ctypes.data, tw.value, side.ctypes.data, side.size,
+                                                n, 65536, out.ctypes.data))
+    assert first_diff(out, data) == -1
