@@ -320,6 +320,101 @@ __global__ void __launch_bounds__(128) lz77_decode_kernel(const uint8_t* __restr
     }
 }
 
+// Deflate-variant decoder, token-parallel: one warp per block, 32 two-byte units of the token stream per
+// step, one unit per lane. Tokens are 2 or 4 bytes, so every token starts on a unit; a unit whose first
+// byte is non-zero is a match head unless it is the tail (offset high byte, length) of the match before
+// it, and a unit is a tail iff the run of "first byte non-zero" units that ends just before it has odd
+// length (see deflate_huff.cu) -- one ballot classifies the 32 units. An exclusive scan of the output
+// lengths places every token; literals are stored at once; a match is copied by its own lane as soon
+// as all of its source bytes lie below the first byte that is not final yet (matches whose source was
+// written in an earlier step -- nearly all of them in text -- go together in the first round; a match
+// that reads the output of a neighbour in the same step waits a round). Source bytes are read with
+// ld.cg because other lanes wrote them a moment ago.
+__global__ void __launch_bounds__(128) lz77_decode_units_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ block_off,
+                                                               const uint64_t* __restrict__ block_sizes, uint64_t n, uint64_t bs,
+                                                               uint64_t nblocks, uint8_t* __restrict__ out) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t b = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= nblocks) return;
+    const uint32_t len = (uint32_t)(n - b * bs < bs ? n - b * bs : bs);
+    const uint16_t* tk = reinterpret_cast<const uint16_t*>(stream + block_off[b]);   // block offsets are even (tokens are 2 or 4 bytes)
+    const uint32_t nunits = (uint32_t)(block_sizes[b] >> 1);
+    uint8_t* gout = out + b * bs;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t o = 0;        // output bytes produced by the units before this step
+    uint32_t s0 = 0;       // 1 = the first unit of this step is the tail of a match
+    uint32_t nextv = lane < nunits ? __ldg(tk + lane) : 0u;
+    for (uint32_t base = 0; base < nunits; base += 32) {
+        const uint32_t u = base + lane;
+        const bool valid = u < nunits;
+        const uint32_t cur = nextv;
+        nextv = u + 32 < nunits ? __ldg(tk + u + 32) : 0u;                 // next step's unit, in flight during this one
+        uint32_t nxt = __shfl_down_sync(0xffffffffu, cur, 1);
+        const uint32_t nv0 = __shfl_sync(0xffffffffu, nextv, 0);
+        if (lane == 31) nxt = nv0;
+        const bool h = valid && (cur & 0xFFu) != 0u;
+        const uint32_t m = __ballot_sync(0xffffffffu, h);
+        if (m == 0u && s0 == 0u) {                                         // 32 literals (incompressible stretches): no scan, no copies
+            if (valid && o + lane < len) gout[o + lane] = (uint8_t)(cur >> 8);
+            o += nunits - base < 32u ? nunits - base : 32u;
+            continue;
+        }
+        // run of h-units that ends just before this lane
+        const uint32_t zeros_below = ~m & lt_mask;
+        const uint32_t tail = zeros_below ? ((lane - 32u + (uint32_t)__clz((int)zeros_below)) & 1u)   // lane - 1 - (31 - clz)
+                                          : (s0 ^ (lane & 1u));
+        const uint32_t z32 = ~m;
+        s0 = z32 ? ((uint32_t)__clz((int)z32) & 1u) : s0;                  // state of the unit after lane 31: run = 31 - (31 - clz)
+        const bool is_lit = valid && !tail && !h, is_head = valid && !tail && h;
+        const uint32_t ml = is_head ? (nxt >> 8) & 0xFFu : 0u;
+        const uint32_t off = is_head ? ((cur >> 8) | ((nxt & 0xFFu) << 8)) : 0u;
+        const uint32_t outlen = is_lit ? 1u : ml;
+        const uint32_t incl = warp_incl_scan_u32(outlen);
+        const uint32_t myo = o + incl - outlen;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (is_lit && myo < len) gout[myo] = (uint8_t)(cur >> 8);
+        const bool copy = is_head && ml != 0u && off != 0u && off <= myo;   // an offset of 0 or beyond the start copies nothing (as lz77_decode_kernel)
+        bool pending = copy;
+        const uint32_t need = copy ? myo - off + (ml < off ? ml : off) : 0u;   // end of the source bytes this match reads
+        for (;;) {
+            const uint32_t pm = __ballot_sync(0xffffffffu, pending);
+            if (!pm) break;
+            const uint32_t wm = __shfl_sync(0xffffffffu, myo, __ffs(pm) - 1);  // every byte below the first unfinished match is final
+            __syncwarp();                                                      // ... and visible
+            if (pending && need <= wm) {
+                const uint8_t* src = gout + (myo - off);
+                uint8_t* dst = gout + myo;
+                const uint32_t cnt = myo + ml <= len ? ml : (myo < len ? len - myo : 0u);
+                if (off >= 8u) {                                               // eight independent reads per batch
+                    for (uint32_t k0 = 0; k0 < cnt; k0 += 8) {
+                        uint8_t c[8];
+#pragma unroll
+                        for (uint32_t q = 0; q < 8; ++q) c[q] = k0 + q < cnt ? __ldcg(src + k0 + q) : (uint8_t)0;
+#pragma unroll
+                        for (uint32_t q = 0; q < 8; ++q) if (k0 + q < cnt) dst[k0 + q] = c[q];
+                    }
+                } else {                                                       // short period: out[o+k] = out[o-off + k % off]
+                    uint8_t c[8];
+#pragma unroll
+                    for (uint32_t q = 0; q < 8; ++q) c[q] = q < off ? __ldcg(src + q) : (uint8_t)0;
+                    uint32_t si = 0;
+                    for (uint32_t k = 0; k < cnt; ++k) {
+                        uint8_t v = c[0];
+#pragma unroll
+                        for (uint32_t q = 1; q < 8; ++q) if (si == q) v = c[q];
+                        dst[k] = v;
+                        if (++si == off) si = 0;
+                    }
+                }
+                pending = false;
+            }
+            __syncwarp();
+        }
+        o += total;
+        __syncwarp();
+    }
+}
+
 inline uint64_t round16(uint64_t x) { return (x + 15) & ~(uint64_t)15; }
 
 }  // namespace
@@ -447,6 +542,15 @@ extern "C" int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d
     // 300 MB 23.5 vs 27.4 ms/GB, 1 GB 18.9 vs 15.2 ms/GB
     uint32_t G = nblocks * 32 > (uint64_t)ctx->sm_count * 2048 ? 16u : 32u;
     if (const char* e = getenv("B200_LZ_DEC_G")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) G = (uint32_t)v; }
+    const char* seq = getenv("B200_LZ_DEC_SERIAL");     // keep the token-serial decoder reachable for comparison
+    if (variant == 1 && !(seq && seq[0] == '1')) {
+        B200_TIMED_BEGIN(ctx, B200_K_LZ_DECODE);
+        lz77_decode_units_kernel<<<(unsigned)((nblocks + 3) / 4), 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
+        B200_TIMED_END(ctx);
+        ctx->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        return B200_OK;
+    }
     const unsigned grid = (unsigned)((nblocks * G + 127) / 128);   // 128 / G blocks per CTA
     B200_TIMED_BEGIN(ctx, B200_K_LZ_DECODE);
 #define LZ_DEC(V, GG) lz77_decode_kernel<V, GG><<<grid, 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out)
