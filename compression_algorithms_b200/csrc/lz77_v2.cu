@@ -363,13 +363,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             }
             if (tid < nforced) ms->cut[nq + tid] = ms->fcut[tid];
             __syncthreads();
-            if (tid == 0) {                                                      // 31 cuts from two sources: sort them
-                for (uint32_t i = 2; i < NR; ++i) {
-                    const uint32_t v = ms->cut[i];
-                    uint32_t j = i;
-                    while (j > 1 && ms->cut[j - 1] > v) { ms->cut[j] = ms->cut[j - 1]; --j; }
-                    ms->cut[j] = v;
+            {                                                                    // 31 cuts from two sources: rank-sort them (one thread each)
+                uint32_t v = 0, rk = 0;
+                if (tid >= 1 && tid < NR) {
+                    v = ms->cut[tid];
+                    rk = 1;
+                    for (uint32_t j = 1; j < NR; ++j) { const uint32_t o = ms->cut[j]; rk += (o < v || (o == v && j < tid)) ? 1u : 0u; }
                 }
+                __syncthreads();
+                if (tid >= 1 && tid < NR) ms->cut[rk] = v;
             }
             if (tid == 0) {
                 uint32_t s = 0;   // cut[0]: end of the cluster that touches slot 0
