@@ -3,12 +3,13 @@ sys.path.insert(0, '.')
 from compression_algorithms_b200 import corpus, device as dv
 ctx = dv.Context(0)
 kind = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-data = corpus.generate(148 * 65536, kind, 5)
+mult = int(sys.argv[2]) if len(sys.argv) > 2 else 1   # blocks per CTA; statistics are taken over the last 148 blocks
+data = corpus.generate(148 * mult * 65536, kind, 5)
 d = torch.from_numpy(data).to(ctx.device)
 for variant in (1,):
     st, tok = dv.lz77_encode_debug(ctx, d, variant, 65536)
     st, tok = dv.lz77_encode_debug(ctx, d, variant, 65536)
-    s = st.debug_stats.cpu().numpy().astype(np.int64)
+    s = st.debug_stats.cpu().numpy().astype(np.int64)[-148:]
     ph = s[:, :7]
     names = ["P0 load", "P1 bitmap", "P2 prefix", "P3 partition", "P4 sim", "P5 parse", "P6 emit"]
     prev = np.zeros(len(s), dtype=np.int64)

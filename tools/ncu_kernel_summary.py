@@ -32,8 +32,9 @@ def f(r, name, default=0.0):
 def scale(name, v, want):
     """convert v from the column's unit to `want` (ns / byte based)"""
     u = units[col[name]] if name in col else ""
-    m = {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    return v * m.get(u, 1.0)
+    m = {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9, "byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}
+    u = u.split("/")[0]
+    return v * m.get(u if u in m else u.lower(), 1.0)
 
 
 stall_cols = [h for h in hdr if re.match(r"smsp__average_warps_issue_stalled_(.*)_per_issue_active\.ratio", h)]

@@ -2,7 +2,9 @@
 usage: python tools/ncu_lines.py report.ncu-rep [top]"""
 import csv, subprocess, sys, collections
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+import os
+KFILTER = (["-k", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else [])
+out = subprocess.run(["ncu", "-i", rep] + KFILTER + ["--page", "source", "--print-source", "cuda,sass", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 agg = collections.OrderedDict(); stall = collections.defaultdict(lambda: collections.Counter())
 fname = ""

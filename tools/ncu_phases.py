@@ -12,7 +12,9 @@ def phase(ln):
     for i, nm in marks:
         if ln >= i: name = nm
     return name
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+import os
+KFILTER = (["-k", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else [])
+out = subprocess.run(["ncu", "-i", rep] + KFILTER + ["--page", "source", "--print-source", "cuda,sass", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = None; agg = collections.OrderedDict()
 for r in rows:
