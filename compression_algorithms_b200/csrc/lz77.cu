@@ -343,12 +343,18 @@ __global__ void __launch_bounds__(128) lz77_decode_units_kernel(const uint8_t* _
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t o = 0;        // output bytes produced by the units before this step
     uint32_t s0 = 0;       // 1 = the first unit of this step is the tail of a match
+    // the units of this step and of the next three are held in registers: four loads of the token stream
+    // are always in flight (ncu: with one step of look-ahead the kernel waited on this load)
     uint32_t nextv = lane < nunits ? __ldg(tk + lane) : 0u;
+    uint32_t pf1 = lane + 32 < nunits ? __ldg(tk + lane + 32) : 0u;
+    uint32_t pf2 = lane + 64 < nunits ? __ldg(tk + lane + 64) : 0u;
+    uint32_t pf3 = lane + 96 < nunits ? __ldg(tk + lane + 96) : 0u;
     for (uint32_t base = 0; base < nunits; base += 32) {
         const uint32_t u = base + lane;
         const bool valid = u < nunits;
         const uint32_t cur = nextv;
-        nextv = u + 32 < nunits ? __ldg(tk + u + 32) : 0u;                 // next step's unit, in flight during this one
+        nextv = pf1; pf1 = pf2; pf2 = pf3;
+        pf3 = u + 128 < nunits ? __ldg(tk + u + 128) : 0u;
         uint32_t nxt = __shfl_down_sync(0xffffffffu, cur, 1);
         const uint32_t nv0 = __shfl_sync(0xffffffffu, nextv, 0);
         if (lane == 31) nxt = nv0;
