@@ -246,3 +246,54 @@ def test_slot0_exception_across_slices(ctx, ob, variant, block):
 def test_whole_buffer_6mb(ctx, ob):
     """the drop-in's own call shape (one table sliding over the whole buffer) at a size with ~180 slices"""
     _encode_check(ctx, ob, _corpus(6_000_000, 0, 7), 1, 0)
+
+
+def _random_token_block(rng, out_len, style):
+    """A VALID deflate-variant token stream (write_literal / write_length_distance, deflate/lz77.c:176-197)
+    producing exactly out_len bytes, built directly (not by the match finder) so that offsets, lengths and
+    token alignments the parser rarely produces are covered: overlapping copies (offset < length, offset 1),
+    offsets whose high byte is non-zero (long runs of units with a non-zero first byte), length 0 .. 255."""
+    tok = bytearray()
+    o = 0
+    while o < out_len:
+        r = rng.random()
+        if o == 0 or r < (0.15 if style == "matches" else 0.6):
+            tok += bytes((0, int(rng.integers(0, 256)))); o += 1
+            continue
+        if style == "rle":
+            off = int(rng.integers(1, min(o, 4) + 1))
+        elif style == "far":
+            off = int(rng.integers(max(1, min(o, 256)), min(o, 32766) + 1))
+        else:
+            off = int(rng.integers(1, min(o, 32766) + 1))
+        ln = int(rng.integers(0, 256)) if rng.random() < 0.1 else int(rng.integers(4, 32))
+        ln = min(ln, out_len - o)
+        tok += bytes((1, off & 0xFF, off >> 8, ln)); o += ln
+    return bytes(tok)
+
+
+@pytest.mark.parametrize("style", ["mixed", "matches", "rle", "far"])
+def test_decoder_on_handmade_streams(ctx, ob, style, monkeypatch):
+    """both deflate-variant decoders (token-parallel units, token-serial) against the oracle's byte-serial decoder"""
+    import torch
+    from compression_algorithms_b200 import device as dv
+    rng = np.random.default_rng({"mixed": 1, "matches": 2, "rle": 3, "far": 4}[style])
+    block = 4096
+    lens = [block] * 6 + [1, 2, 33, 777]
+    n = sum(lens)
+    # the decoder derives block lengths from (n, block): all blocks full except the last -> lay the ragged ones out as separate calls
+    for blens in ([block] * 6 + [777], [1], [2], [33]):
+        nn = sum(blens)
+        toks = [_random_token_block(rng, L, style) for L in blens]
+        stream = np.frombuffer(b"".join(toks), dtype=np.uint8)
+        sizes = np.array([len(t) for t in toks], dtype=np.int64)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        want = np.concatenate([ob.port_deflate_lz77_decompress(np.frombuffer(t, dtype=np.uint8), L)[:L] for t, L in zip(toks, blens)])
+        pad = np.zeros(64, dtype=np.uint8)
+        st = dv.Lz77Stream(variant=dv.LZ_DEFLATE, out=_to_dev(ctx, np.concatenate([stream, pad])), block_sizes=_to_dev(ctx, sizes),
+                           block_off=_to_dev(ctx, off), n=nn, block_size=block, total_bytes=int(off[-1]))
+        for serial in ("0", "1"):
+            monkeypatch.setenv("B200_LZ_DEC_SERIAL", serial)
+            got = dv.lz77_decode(ctx, st, out=torch.zeros(nn, dtype=torch.uint8, device=ctx.device)).cpu().numpy()
+            d = first_diff(got, want)
+            assert d == -1, "%s decoder (%s) differs at byte %d" % ("serial" if serial == "1" else "unit", style, d)
