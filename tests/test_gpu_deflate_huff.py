@@ -156,3 +156,30 @@ def test_host_buffer_entry_points(ctx, ob):
     _lib.check(lib.b200_deflate_decompress_host(ctx.handle, words.ctypes.data, tw.value, side.ctypes.data, side.size,
                                                 n, 65536, out.ctypes.data))
     assert first_diff(out, data) == -1
+
+
+def test_error_paths(ctx, ob):
+    """capacity errors are reported, not written past: side buffer too small, word buffer too small"""
+    import ctypes as C
+    import torch
+    from compression_algorithms_b200 import _lib, device as dv
+    data = _corpus(2 * 65536 + 5, seed=4)
+    d = _to_dev(ctx, data)
+    lz = dv.lz77_encode(ctx, d, dv.LZ_DEFLATE, 65536)
+    st = dv.deflate_alloc(ctx, lz.n, 65536, lz)
+    lib = _lib.core()
+    tw, ws = C.c_uint64(0), C.c_uint32(0)
+    rc = lib.b200_dfl_encode_dev(ctx.handle, C.c_void_p(lz.out.data_ptr()), lz.out.numel(), C.c_void_p(lz.block_off.data_ptr()),
+                                 C.c_void_p(lz.block_sizes.data_ptr()), lz.n, 65536, C.c_void_p(st.words.data_ptr()), st.words.numel(),
+                                 C.c_void_p(st.side.data_ptr()), st.side.numel() - 8, C.byref(tw), C.byref(ws))
+    assert rc == 3 and b"side buffer" in lib.b200_last_error()
+    guard = torch.full((64,), 0x5A, dtype=torch.int32, device=ctx.device)
+    small = torch.cat([torch.zeros(100, dtype=torch.int32, device=ctx.device), guard])
+    rc = lib.b200_dfl_encode_dev(ctx.handle, C.c_void_p(lz.out.data_ptr()), lz.out.numel(), C.c_void_p(lz.block_off.data_ptr()),
+                                 C.c_void_p(lz.block_sizes.data_ptr()), lz.n, 65536, C.c_void_p(small.data_ptr()), 100,
+                                 C.c_void_p(st.side.data_ptr()), st.side.numel(), C.byref(tw), C.byref(ws))
+    assert rc == 3 and tw.value > 100            # needed size is reported
+    assert bool((small[100:] == 0x5A).all())     # nothing written past the capacity
+    # a good call afterwards still works (no sticky state)
+    st = dv.dfl_encode(ctx, lz, stream=st)
+    assert torch.equal(dv.deflate_decompress(ctx, st, tokens=torch.zeros_like(lz.out)), d)
