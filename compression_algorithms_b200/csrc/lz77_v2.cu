@@ -82,6 +82,7 @@ struct Misc {
     uint8_t  sentry[NR + 1];
     uint32_t scan[34];
     uint32_t entry_pad;
+    uint8_t  rtab[(SLOTS + GUARD_BITS) >> 12];   // range of the first slot of every 4096-slot bin (P3 starts its search there)
 };
 static_assert(sizeof(Misc) <= SZ_MISC, "misc region too small");
 
@@ -109,16 +110,16 @@ __device__ __forceinline__ uint32_t match_len(const uint8_t* data, uint32_t m, u
     return l < MAXLEN ? l : MAXLEN;
 }
 
-__device__ __forceinline__ uint32_t bm_rank(const uint32_t* bm, const uint32_t* pre, uint32_t s) {
-    // set bits below slot s: prefix of the 8-word chunk + masked popcounts of the chunk (two 16-byte reads)
-    const uint32_t wi = s >> 5, j = wi & (PRE_CHUNK - 1);
-    const uint4* cp = reinterpret_cast<const uint4*>(bm + (wi & ~(PRE_CHUNK - 1)));
-    const uint4 lo = cp[0], hi = cp[1];
-    const uint32_t wd[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    uint32_t r = pre[wi / PRE_CHUNK];
+__device__ __forceinline__ uint32_t bm_rank(const uint32_t* bm, const uint16_t* pre16, uint32_t s) {
+    // set bits below slot s: prefix of the 4-word half chunk (u16: a slice has at most 65536 occupied slots, and the
+    // prefix of an occupied slot is below that) + masked popcounts of the half chunk (one 16-byte read)
+    const uint32_t wi = s >> 5, j = wi & 3u;
+    const uint4 q = *reinterpret_cast<const uint4*>(bm + (wi & ~3u));
+    const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+    uint32_t r = pre16[wi >> 2];
     const uint32_t below = (1u << (s & 31)) - 1u;
 #pragma unroll
-    for (uint32_t k = 0; k < 8; ++k) r += __popc(wd[k] & (k < j ? 0xFFFFFFFFu : (k == j ? below : 0u)));
+    for (uint32_t k = 0; k < 4; ++k) r += __popc(wd[k] & (k < j ? 0xFFFFFFFFu : (k == j ? below : 0u)));
     return r;
 }
 
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
     uint8_t* big = smem + OFF_BIG;
     uint32_t* bm = reinterpret_cast<uint32_t*>(big);
     uint32_t* pre = reinterpret_cast<uint32_t*>(smem + OFF_PRE);
+    uint16_t* pre16 = reinterpret_cast<uint16_t*>(smem + OFF_PRE);   // P2/P3: rank prefix per 4-word half chunk
     Misc* ms = reinterpret_cast<Misc*>(smem + OFF_MISC);
     uint16_t* T = reinterpret_cast<uint16_t*>(big + OFF_T);
     uint16_t* B1 = reinterpret_cast<uint16_t*>(big + OFF_B1);
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         uint32_t* summ = pre;
         for (uint32_t i = C + tid; i < len; i += NTHREADS) {
             uint32_t s = lz_hash(sm_word(data, i));
+            tokb[i] = s;                                   // P3 reads the hash back instead of computing it again
             for (;;) {
                 const uint32_t wi = s >> 5;
                 const uint32_t free_bits = ~bm[wi] & (0xFFFFFFFFu << (s & 31));
@@ -288,14 +291,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         {
             // thread t owns chunks [5t, 5t+5)
             uint32_t c0 = tid * 5, mine = 0, mine_cost = 0;
-            uint32_t part[5], cost[5], fullw[7];   // fullw[j]: fully occupied words of chunk c0 - 1 + j
+            uint32_t part[5], half[5], cost[5], fullw[7];   // fullw[j]: fully occupied words of chunk c0 - 1 + j; half: first four words
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
                 const uint32_t ch = c0 + j - 1;     // wraps for c0 == 0, j == 0: out of range, counts 0
-                uint32_t s = 0, full = 0;
-                if (ch < PRE_N) for (uint32_t w = 0; w < PRE_CHUNK; ++w) { const uint32_t x = bm[ch * PRE_CHUNK + w]; s += __popc(x); full += x == 0xFFFFFFFFu; }
+                uint32_t s = 0, s4 = 0, full = 0;
+                if (ch < PRE_N) for (uint32_t w = 0; w < PRE_CHUNK; ++w) { const uint32_t x = bm[ch * PRE_CHUNK + w]; s += __popc(x); if (w == 3) s4 = s; full += x == 0xFFFFFFFFu; }
                 fullw[j] = full;
-                if (j >= 1 && j <= 5) { part[j - 1] = s; mine += s; }
+                if (j >= 1 && j <= 5) { part[j - 1] = s; half[j - 1] = s4; mine += s; }
             }
             // Range cuts. A chunk with HOT_MIN_WORDS fully occupied bitmap words belongs to the chain of a hot
             // 4-gram: such a chain gets a cut just before and just after it, so that it sits (almost) alone in a
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             __syncthreads();
             uint32_t run = ms->scan[warp] + incl - mine;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) { if (c0 + k < PRE_N) pre[c0 + k] = run; run += part[k]; }
+            for (int k = 0; k < 5; ++k) { if (c0 + k < PRE_N) { pre16[2 * (c0 + k)] = (uint16_t)run; pre16[2 * (c0 + k) + 1] = (uint16_t)(run + half[k]); } run += part[k]; }
             const uint32_t cincl = warp_incl_scan_u32(mine_cost);
             __syncthreads();
             if (lane == 31) ms->scan[warp] = cincl;
@@ -398,9 +401,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             }
         }
         __syncthreads();
+        if (tid < ((SLOTS + GUARD_BITS) >> 12)) {
+            const uint32_t slot = tid << 12;
+            uint32_t r = 0;
+#pragma unroll
+            for (uint32_t st = 16; st > 0; st >>= 1) if (ms->cut[r + st] <= slot) r += st;
+            ms->rtab[tid] = (uint8_t)r;
+        }
         if (tid == 0) {
-            ms->sp_lo_end = bm_rank(bm, pre, ms->cut[0]);
-            ms->sp_hi_start = ms->top_start < SLOTS ? bm_rank(bm, pre, ms->top_start) : 0xFFFFFFFFu;
+            ms->sp_lo_end = bm_rank(bm, pre16, ms->cut[0]);
+            ms->sp_hi_start = ms->top_start < SLOTS ? bm_rank(bm, pre16, ms->top_start) : 0xFFFFFFFFu;
         }
         for (uint32_t i = tid; i < NR * NR; i += NTHREADS) (&ms->cnt[0][0])[i] = 0;
         __syncthreads();
@@ -411,10 +421,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         const uint32_t p_lo = (C + warp * slice < len) ? C + warp * slice : len, p_hi = (p_lo + slice < len) ? p_lo + slice : len;
         const uint32_t top_start = ms->top_start;
         // pass 1: counts per (warp, range)
+        uint32_t h_next = p_lo + lane < p_hi ? tokb[p_lo + lane] : 0u;
         for (uint32_t base = p_lo; base < p_hi; base += 32) {
             const uint32_t i = base + lane;
+            const uint32_t h = h_next;
+            if (i + 32 < p_hi) h_next = tokb[i + 32];        // prefetch
             if (i < p_hi) {
-                const uint32_t h = lz_hash(sm_word(data, i));
                 // A position whose home slot is a cluster of its own (both neighbours free in the no-expiry
                 // occupancy) is the only entry that ever touches that slot: it lands there, its find sees a slot
                 // that was never used (-> literal candidate) and no other probe walk reaches it. Such entries
@@ -425,9 +437,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 const uint32_t above = bi != 31u ? (wv >> (bi + 1u)) & 1u : (bm[wi + 1] & 1u);
                 if (last_slice && !below && !above && h != SLOTS - 1u) tokb[i] = LONER;
                 else {
-                uint32_t r = 0;             // largest r with cut[r] <= h (0 also for the cluster below cut[0])
-#pragma unroll
-                for (uint32_t st = 16; st > 0; st >>= 1) if (ms->cut[r + st] <= h) r += st;
+                uint32_t r = ms->rtab[h >> 12];   // largest r with cut[r] <= h (0 also for the cluster below cut[0])
+                while (ms->cut[r + 1] <= h) ++r;  // (cut[NR] lies beyond every slot)
                 if (V == 1 && h >= top_start) r = 0;
                 tokb[i] = h | (r << 21);    // kept for pass 2 (the token array is free until P4)
                 atomicAdd(&ms->cnt[warp][r], 1u);
@@ -465,7 +476,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             const bool loner = in_range && hr == LONER;
             // (a loner keeps its LONER mark in tokb: P5 / P6 read it as "literal candidate")
             const bool valid = in_range && !loner;
-            if (valid) { r = hr >> 21; c = bm_rank(bm, pre, hr & 0x1FFFFFu); }
+            if (valid) { r = hr >> 21; c = bm_rank(bm, pre16, hr & 0x1FFFFFu); }
             const uint32_t peers = __match_any_sync(0xffffffffu, r);
             const uint32_t myrank = __popc(peers & lt_mask);
             uint32_t basepos = 0;
@@ -480,14 +491,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         if (C) {                   // compact slot of every carried entry (the bitmap is still alive here)
             for (uint32_t i = tid; i < C; i += NTHREADS) {
                 const uint32_t r = raw_carry[i];
-                ccar[i] = r != NONE ? bm_rank(bm, pre, r) : NONE;
+                ccar[i] = r != NONE ? bm_rank(bm, pre16, r) : NONE;
             }
         }
         if (!last_slice) {         // raw slot of every compact slot, for the hand-over at the end of the slice
             for (uint32_t k = 0; k < 5; ++k) {
                 const uint32_t ch = tid * 5 + k;
                 if (ch >= PRE_N) break;
-                uint32_t r = pre[ch];
+                uint32_t r = pre16[2 * ch];
                 for (uint32_t wq = 0; wq < PRE_CHUNK; ++wq) {
                     uint32_t x = bm[ch * PRE_CHUNK + wq];
                     while (x) { const uint32_t bpos = (uint32_t)(__ffs(x) - 1); x &= x - 1; rawmap[r++] = ((ch * PRE_CHUNK + wq) << 5) + bpos; }
