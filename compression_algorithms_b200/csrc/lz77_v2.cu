@@ -82,6 +82,7 @@ struct Misc {
     uint8_t  sentry[NR + 1];
     uint32_t scan[34];
     uint32_t entry_pad;
+    uint32_t p1_next;                            // P1: next row of 32 positions to hand out
     uint8_t  rtab[(SLOTS + GUARD_BITS) >> 12];   // range of the first slot of every 4096-slot bin (P3 starts its search there)
 };
 static_assert(sizeof(Misc) <= SZ_MISC, "misc region too small");
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             }
             for (uint32_t i = tid; i < BM_WORDS; i += NTHREADS) bm[i] = 0;
             for (uint32_t i = tid; i < BM_WORDS / 32; i += NTHREADS) pre[i] = 0;   // P1's "word is full" summary (pre is free until P2)
-            if (tid == 0) ms->ncar = 0;
+            if (tid == 0) { ms->ncar = 0; ms->p1_next = C; }
         }
         __syncthreads();
         if (C) {   // the carried entries sit where the previous slice left them
@@ -262,7 +263,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         // word ("known to be full", set by whoever takes its last free bit; bits are never cleared in this
         // phase, so a set summary bit is always right) lets a walk jump to the first word that may have room.
         uint32_t* summ = pre;
-        for (uint32_t i = C + tid; i < len; i += NTHREADS) {
+        for (;;) {
+            // 32 positions at a time from a shared counter: the warps that hold many occurrences of a hot 4-gram
+            // (long probe walks, lost races) take fewer rows, and all warps reach the barrier together
+            uint32_t row = 0;
+            if (lane == 0) row = atomicAdd(&ms->p1_next, 32u);
+            row = __shfl_sync(0xffffffffu, row, 0);
+            if (row >= len) break;
+            const uint32_t i = row + lane;
+            if (i >= len) continue;
             uint32_t s = lz_hash(sm_word(data, i));
             tokb[i] = s;                                   // P3 reads the hash back instead of computing it again
             for (;;) {
@@ -472,12 +481,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             const bool in_range = i < p_hi;
             const uint32_t hr = hr_next;
             if (i + 32 < p_hi) hr_next = tokb[i + 32];       // prefetch
-            uint32_t r = 0xFFu, c = 0;
             const bool loner = in_range && hr == LONER;
             // (a loner keeps its LONER mark in tokb: P5 / P6 read it as "literal candidate")
             const bool valid = in_range && !loner;
-            if (valid) { r = hr >> 21; c = bm_rank(bm, pre16, hr & 0x1FFFFFu); }
-            const uint32_t peers = __match_any_sync(0xffffffffu, r);
+            const uint32_t r = valid ? hr >> 21 : 0xFFu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, r);   // issued first: its latency overlaps the rank below
+            uint32_t c = 0;
+            if (valid) c = bm_rank(bm, pre16, hr & 0x1FFFFFu);
             const uint32_t myrank = __popc(peers & lt_mask);
             uint32_t basepos = 0;
             if (valid) basepos = ms->cnt[warp][r];
