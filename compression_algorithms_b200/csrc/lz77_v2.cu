@@ -46,6 +46,7 @@ constexpr uint32_t NTHREADS = 1024;
 constexpr uint32_t CARRY_BYTES = (MAXB + 64) * 4 + 32768 * 4 + MAXB * 4 + 32768 * 4;
 constexpr uint32_t NR = 32;                                  // ranges == warps
 constexpr uint32_t CROWD_MIN = 12;                           // same-home entries in a batch from which the slot-ordered placement is used
+constexpr uint32_t FULL_WORD_WEIGHT = 6;                      // extra cost units per slot of a fully occupied bitmap word (range balancing, P2)
 constexpr uint32_t HOT_MIN_WORDS = 7;                         // fully occupied words (of 8) in a 256-slot chunk from which its chain counts as hot (swept 2..8 on B200)
 
 // shared memory layout (bytes)
@@ -328,7 +329,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 const bool hot = fullw[k + 1] >= HOT_MIN_WORDS, hot_prev = fullw[k] >= HOT_MIN_WORDS, hot_next = fullw[k + 2] >= HOT_MIN_WORDS;
-                cost[k] = (c0 + k < PRE_N && !hot) ? part[k] : 0u;
+                // An entry of a medium-hot chain (a run of occupied slots too short to be cut out, 32 .. 223 slots)
+                // costs a whole commit round of its warp, an ordinary entry a thirty-second of a batch: slots in
+                // fully occupied bitmap words are weighted accordingly
+                cost[k] = (c0 + k < PRE_N && !hot) ? part[k] + FULL_WORD_WEIGHT * 32u * fullw[k + 1] : 0u;
                 mine_cost += cost[k];
                 if (hot && c0 + k < PRE_N) {
                     if (!hot_prev && c0 + k >= 1) { const uint32_t i = atomicAdd(&ms->nfcut, 1u); if (i < 16) ms->fcut[i] = free_at_or_after((c0 + k - 1) * PRE_CHUNK * 32); }
