@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                             uint32_t k2 = home;
 #pragma unroll 1
                             while (k2 < my_e) {
-                                if ((k2 & 31u) == 0 && k2 + 32u <= my_e && !((S1[k2 >> 5] >> sig) & 1u)) { k2 += 32; continue; }
+                                if (!((S1[k2 >> 5] >> sig) & 1u)) { k2 = (k2 | 31u) + 1u; continue; }   // nothing with this signature in the (rest of the) group
                                 const uint32_t v = T[k2];
                                 if (v > dthr) { if (sm_word(data, v - 1) == w) { fm = v - 1; break; } }
                                 else {
