@@ -47,6 +47,7 @@ constexpr uint32_t CARRY_BYTES = (MAXB + 64) * 4 + 32768 * 4 + MAXB * 4 + 32768 
 constexpr uint32_t NR = 32;                                  // ranges == warps
 constexpr uint32_t CROWD_MIN = 12;                           // same-home entries in a batch from which the slot-ordered placement is used
 constexpr uint32_t FULL_WORD_WEIGHT = 6;                      // extra cost units per slot of a fully occupied bitmap word (range balancing, P2)
+constexpr uint32_t RUN8_WEIGHT = 4;                           // extra cost units per slot beyond the seventh of a run of occupied slots
 constexpr uint32_t HOT_MIN_WORDS = 7;                         // fully occupied words (of 8) in a 256-slot chunk from which its chain counts as hot (swept 2..8 on B200)
 
 // shared memory layout (bytes)
@@ -301,14 +302,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
         {
             // thread t owns chunks [5t, 5t+5)
             uint32_t c0 = tid * 5, mine = 0, mine_cost = 0;
-            uint32_t part[5], half[5], cost[5], fullw[7];   // fullw[j]: fully occupied words of chunk c0 - 1 + j; half: first four words
+            uint32_t part[5], half[5], cost[5], run8[5], fullw[7];   // fullw[j]: fully occupied words of chunk c0 - 1 + j; half: first four words
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
                 const uint32_t ch = c0 + j - 1;     // wraps for c0 == 0, j == 0: out of range, counts 0
-                uint32_t s = 0, s4 = 0, full = 0;
-                if (ch < PRE_N) for (uint32_t w = 0; w < PRE_CHUNK; ++w) { const uint32_t x = bm[ch * PRE_CHUNK + w]; s += __popc(x); if (w == 3) s4 = s; full += x == 0xFFFFFFFFu; }
+                uint32_t s = 0, s4 = 0, full = 0, r8 = 0;
+                if (ch < PRE_N) for (uint32_t w = 0; w < PRE_CHUNK; ++w) {
+                    const uint32_t x = bm[ch * PRE_CHUNK + w];
+                    s += __popc(x); if (w == 3) s4 = s; full += x == 0xFFFFFFFFu;
+                    uint32_t y = x & (x >> 1); y &= y >> 2; y &= y >> 4;   // slots that end a run of eight or more (inside the word)
+                    r8 += __popc(y);
+                }
                 fullw[j] = full;
-                if (j >= 1 && j <= 5) { part[j - 1] = s; half[j - 1] = s4; mine += s; }
+                if (j >= 1 && j <= 5) { part[j - 1] = s; half[j - 1] = s4; run8[j - 1] = r8; mine += s; }
             }
             // Range cuts. A chunk with HOT_MIN_WORDS fully occupied bitmap words belongs to the chain of a hot
             // 4-gram: such a chain gets a cut just before and just after it, so that it sits (almost) alone in a
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 // An entry of a medium-hot chain (a run of occupied slots too short to be cut out, 32 .. 223 slots)
                 // costs a whole commit round of its warp, an ordinary entry a thirty-second of a batch: slots in
                 // fully occupied bitmap words are weighted accordingly
-                cost[k] = (c0 + k < PRE_N && !hot) ? part[k] + FULL_WORD_WEIGHT * 32u * fullw[k + 1] : 0u;
+                cost[k] = (c0 + k < PRE_N && !hot) ? part[k] + RUN8_WEIGHT * run8[k] + FULL_WORD_WEIGHT * 32u * fullw[k + 1] : 0u;
                 mine_cost += cost[k];
                 if (hot && c0 + k < PRE_N) {
                     if (!hot_prev && c0 + k >= 1) { const uint32_t i = atomicAdd(&ms->nfcut, 1u); if (i < 16) ms->fcut[i] = free_at_or_after((c0 + k - 1) * PRE_CHUNK * 32); }
