@@ -56,26 +56,43 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        """Started before the warm-up steps (nvidia-smi takes a few hundred ms to print its first row); only rows
+        that arrive between mark_begin() and stop() are used."""
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.t_begin = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_end = time.perf_counter()
+        time.sleep(0.12)
         self.proc.terminate()
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        rows = [r for t, r in self.rows if t0 <= t <= t_end + 0.06]
+        window = "timed region"
+        if not rows:   # a timed region shorter than the sampling period: fall back to every row taken under load
+            rows, window = [r for _, r in self.rows], "warm-up + timed region"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -84,7 +101,7 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def cpu_baseline(data_np, sample_bytes, threads=0):
@@ -255,15 +272,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first()
     for _ in range(args.warmup):
         step()
     barrier()
     launches0 = ctx.launches
     ctx.set_timing(True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step()

@@ -57,6 +57,9 @@ def core():
         lib.b200_huffman_max_words.argtypes = [C.c_uint64, C.c_uint64]
         lib.b200_huffman_encode_dev.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, u64p, u32p]
         lib.b200_huffman_tables_dev.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64]
+        lib.b200_huffman_histogram_dev.argtypes = [vp, vp, C.c_uint64, vp]
+        lib.b200_huffman_encode_with_freq_dev.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint64, vp, C.c_uint64, u64p, u64p, u32p]
+        lib.b200_huffman_splice_dev.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64]
         lib.b200_huffman_decode_dev.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
         lib.b200_huffman_decode_serial_dev.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_uint64, u64p]
         lib.b200_lz77_block_stride.restype = C.c_uint64

@@ -8,6 +8,7 @@
 // Data layout in HBM: input bytes; output = host-endian u32 words, MSB-first, each
 // table scope ("block") starting on a word boundary; a side buffer (b200_huff_layout)
 // with per-block tables and the chunk/sub-chunk bit index used for parallel decode.
+#include <algorithm>
 #include "common.cuh"
 #include "hist.cuh"
 #include "huff_shared.cuh"
@@ -441,6 +442,109 @@ extern "C" int b200_huffman_encode_with_codes_dev(b200_ctx* ctx, const uint8_t* 
     const int rc = huff_pack(ctx, d_in, n, L, d_words, words_capacity, d_side, h_total_words, &worst);
     if (h_worst_status) *h_worst_status = worst;
     return rc;
+}
+
+// ---------------------------------------------------------------- one table over several shards
+// The reference builds ONE tree over the whole input (huffman.c:184-211). When the input is sharded over ranks the
+// shard histograms are summed (all-reduce of 256 x u64 by the caller), every rank builds the same table from the sum
+// and packs its own shard from bit 0 of its own words; the shard streams are then spliced bit-granularly at the
+// exclusive prefix of the shard bit counts, which yields the words huffman_compress writes for the whole buffer.
+__global__ void __launch_bounds__(256) huff_widen_freq_kernel(const uint32_t* __restrict__ f32, uint64_t* __restrict__ f64) {
+    f64[threadIdx.x] = f32[threadIdx.x];
+}
+__global__ void __launch_bounds__(256) huff_narrow_freq_kernel(const uint64_t* __restrict__ f64, uint32_t* __restrict__ f32) {
+    f32[threadIdx.x] = (uint32_t)f64[threadIdx.x];   // `uint32_t frequencies[256]` (huffman.c:184) wraps the same way
+}
+
+extern "C" int b200_huffman_histogram_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t* d_freq64) {
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_freq64) & 7)) {
+        B200_SET_ERR("huffman: d_in must be 16-byte and d_freq64 8-byte aligned"); return B200_ERR_ARG;
+    }
+    if (n >> 32) { B200_SET_ERR("huffman histogram: a shard must be below 4 GiB (u32 bins)"); return B200_ERR_ARG; }
+    uint32_t* f32; B200_TRY(b200_scratch(ctx, 0, 1024, reinterpret_cast<void**>(&f32)));
+    CUDA_TRY(cudaMemsetAsync(f32, 0, 1024, ctx->stream));
+    if (n) {
+        const uint64_t bs = eff_block(n, 0);
+        const uint32_t tpb = (uint32_t)((bs / CHUNK + TILE_CHUNKS - 1) / TILE_CHUNKS);
+        byte_hist_kernel<<<tpb, 256, 0, ctx->stream>>>(d_in, n, bs, tpb, f32);
+        ctx->launches += 1;
+    }
+    huff_widen_freq_kernel<<<1, 256, 0, ctx->stream>>>(f32, d_freq64);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_huffman_encode_with_freq_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, const uint64_t* d_freq64,
+                                                 uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
+                                                 uint64_t* h_total_words, uint64_t* h_total_bits, uint32_t* h_worst_status) {
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_side) & 7)) {
+        B200_SET_ERR("huffman: d_in must be 16-byte and d_side 8-byte aligned"); return B200_ERR_ARG;
+    }
+    b200_huff_layout L;
+    B200_TRY(b200_huffman_layout(n, 0, &L));
+    if (side_bytes < L.bytes) { B200_SET_ERR("huffman: side buffer %llu < %llu", (unsigned long long)side_bytes, (unsigned long long)L.bytes); return B200_ERR_CAPACITY; }
+    CUDA_TRY(cudaMemsetAsync(d_side, 0, L.off_tree, ctx->stream));
+    huff_narrow_freq_kernel<<<1, 256, 0, ctx->stream>>>(d_freq64, reinterpret_cast<uint32_t*>(d_side + L.off_freq));
+    huff_build_kernel<256, 256, false><<<1, 32, 0, ctx->stream>>>(
+        reinterpret_cast<const uint32_t*>(d_side + L.off_freq), reinterpret_cast<uint32_t*>(d_side + L.off_codes),
+        d_side + L.off_lens, reinterpret_cast<int16_t*>(d_side + L.off_tree), reinterpret_cast<uint32_t*>(d_side + L.off_meta));
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    if (n == 0) {   // an empty shard (more ranks than data): the table is there, the stream is empty
+        CUDA_TRY(cudaMemsetAsync(d_side + L.off_block_bits, 0, L.bytes - L.off_block_bits, ctx->stream));
+        if (h_total_words || h_total_bits || h_worst_status) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (h_total_words) *h_total_words = 0;
+        if (h_total_bits) *h_total_bits = 0;
+        if (h_worst_status) {
+            uint32_t* pin; B200_TRY(b200_pinned(ctx, 16, reinterpret_cast<void**>(&pin)));
+            CUDA_TRY(cudaMemcpyAsync(pin, d_side + L.off_meta, 16, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            *h_worst_status = pin[0];
+        }
+        return B200_OK;
+    }
+    B200_TRY(huff_pack(ctx, d_in, n, L, d_words, words_capacity, d_side, h_total_words, h_worst_status));
+    if (h_total_bits) {
+        uint64_t* pin; B200_TRY(b200_pinned(ctx, 16, reinterpret_cast<void**>(&pin)));
+        CUDA_TRY(cudaMemcpyAsync(pin, d_side + L.off_block_bits, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        *h_total_bits = pin[0];
+    }
+    return B200_OK;
+}
+
+// dst word j of the piece holds source bits [32 j - s, 32 j - s + 32), s = dst_bit % 32, MSB first (bit k of a stream
+// is bit 31 - k % 32 of word k / 32, write_bits huffman.c:18-48). The first and the last word of the piece are shared
+// with the neighbouring shards and are OR-ed atomically into the zeroed destination; the rest are plain stores.
+__global__ void __launch_bounds__(256) huff_splice_kernel(uint32_t* __restrict__ dst, uint64_t dst_bit, const uint32_t* __restrict__ src,
+                                                          uint64_t src_bits, uint64_t nwords) {
+    const uint32_t s = (uint32_t)(dst_bit & 31);
+    const uint64_t w0 = dst_bit >> 5, src_words = (src_bits + 31) >> 5;
+    for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < nwords; j += (uint64_t)gridDim.x * 256) {
+        const uint32_t hi = (j >= 1 && j - 1 < src_words) ? __ldg(src + j - 1) : 0u;
+        const uint32_t lo = j < src_words ? __ldg(src + j) : 0u;
+        uint32_t v = s ? __funnelshift_r(lo, hi, s) : lo;   // (hi:lo) >> s, low word
+        // keep only source bits below src_bits: piece bit t = 32 j + q is source bit 32 j + q - s
+        const int64_t first = (int64_t)(j * 32) - (int64_t)s;                 // source bit index of this word's MSB
+        const int64_t over = first + 32 - (int64_t)src_bits;                  // bits of this word past the end
+        if (over > 0) v = over >= 32 ? 0u : (v & (0xFFFFFFFFu << over));
+        if (first < 0) v &= 0xFFFFFFFFu >> (uint32_t)(-first);
+        if (j == 0 || j + 1 == nwords) { if (v) atomicOr(dst + w0 + j, v); }
+        else dst[w0 + j] = v;
+    }
+}
+
+extern "C" int b200_huffman_splice_dev(b200_ctx* ctx, uint32_t* d_dst, uint64_t dst_words_capacity, uint64_t dst_bit,
+                                       const uint32_t* d_src, uint64_t src_bits) {
+    if (src_bits == 0) return B200_OK;
+    const uint64_t nwords = ((dst_bit & 31) + src_bits + 31) >> 5;
+    if ((dst_bit >> 5) + nwords > dst_words_capacity) { B200_SET_ERR("huffman splice: destination too small"); return B200_ERR_CAPACITY; }
+    const unsigned grid = (unsigned)std::min<uint64_t>((nwords + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    huff_splice_kernel<<<grid, 256, 0, ctx->stream>>>(d_dst, dst_bit, d_src, src_bits, nwords);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
 }
 
 extern "C" int b200_huffman_decode_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words, const uint8_t* d_side,

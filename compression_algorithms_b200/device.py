@@ -149,6 +149,33 @@ def huffman_tables(ctx, data, block_size=0):
     return st
 
 
+def huffman_histogram(ctx, data):
+    """Shard histogram as int64[256] on the device (huffman.c:184-187), ready for an all-reduce."""
+    _check_u8(data)
+    freq = torch.empty(256, dtype=torch.int64, device=ctx.device)
+    _lib.check(_lib.core().b200_huffman_histogram_dev(ctx.handle, _ptr(data), data.numel(), _ptr(freq)))
+    return freq
+
+
+def huffman_encode_with_freq(ctx, data, freq64):
+    """Table from the given (global) int64[256] histogram, this shard packed from bit 0 of its own words.
+    -> (HuffmanStream with block_size 0, bits of the shard's stream)."""
+    _check_u8(data)
+    n = data.numel()
+    st = huffman_alloc(ctx, n, 0)
+    tw, tb, ws = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+    _lib.check(_lib.core().b200_huffman_encode_with_freq_dev(
+        ctx.handle, _ptr(data), n, _ptr(freq64), _ptr(st.words), st.words.numel(), _ptr(st.side), st.side.numel(),
+        C.byref(tw), C.byref(tb), C.byref(ws)))
+    st.total_words, st.worst_status = tw.value, ws.value
+    return st, tb.value
+
+
+def huffman_splice(ctx, dst_words, dst_bit, src_words, src_bits):
+    """OR `src_bits` bits of src_words (MSB first) into the zeroed dst_words at bit `dst_bit`."""
+    _lib.check(_lib.core().b200_huffman_splice_dev(ctx.handle, _ptr(dst_words), dst_words.numel(), dst_bit, _ptr(src_words), src_bits))
+
+
 def huffman_decode(ctx, st, out=None):
     """Table-lookup decoder (replaces huffman_decompress, huffman.c:330-364)."""
     if out is None:

@@ -7,6 +7,11 @@ derives the global byte offset of its shard in the final stream; an optional sec
 all-gather of the per-block sizes gives the global block index. Payload stays sharded
 (decode needs nothing else) or is placed at its offset with `gather_stream`.
 
+Whole-buffer Huffman (ONE tree for all the data, what the reference's huffman_compress does)
+is the one mode with a second exchange: an all-reduce of the 256-bin histogram before the
+table build, then an all-gather of the shard BIT counts; the shard streams are spliced
+bit-granularly (`huffman_whole_compress_sharded`, `huffman_whole_gather`).
+
 The functions take any torch.distributed backend: `nccl` on the GPUs, `gloo` in the CPU
 tests (world_size 2), where `compress_fn` is supplied by the test.
 """
@@ -144,3 +149,72 @@ def lz77_decompress_sharded(ctx, sh, variant):
     st = dv.Lz77Stream(variant=variant, out=sh.stream, block_sizes=sh.block_sizes, block_off=sh.block_off, n=n,
                        block_size=sh.block_size, total_bytes=int(sh.block_off[-1].item()))
     return dv.lz77_decode(ctx, st)
+
+
+# ------------------------------------------------------------------ whole-buffer Huffman over ranks
+@dataclass
+class HuffmanShardedStream:
+    rank: int
+    world: int
+    stream: object             # device.HuffmanStream of this rank's shard (own words from bit 0, own decode index)
+    bits: int                  # bits of this rank's stream
+    freq: torch.Tensor         # int64[256] global histogram (identical on every rank)
+    shard_bits: torch.Tensor   # int64[world]
+    bit_off: torch.Tensor      # int64[world + 1] exclusive prefix: where every shard starts in the whole stream
+
+
+def reduce_histogram(freq64, group=None):
+    """Sum of the shard histograms over the ranks (in place; the all-reduce of SURVEY.md §8e)."""
+    rank, world = _world(group)
+    if world > 1:
+        dist.all_reduce(freq64, op=dist.ReduceOp.SUM, group=group)
+    return freq64
+
+
+def whole_stream_size(total_bits):
+    """(u32 words, buffer_size in bytes) of a whole stream of `total_bits` bits: the reference's
+    `4*word_idx + ceil(bit_idx/8)` (/root/reference/algorithms/huffman/huffman.c:318-320)."""
+    word_idx, bit_idx = divmod(int(total_bits), 32)
+    return word_idx + (1 if bit_idx else 0), 4 * word_idx + (bit_idx + 7) // 8
+
+
+def huffman_whole_compress_sharded(data_shard, hist_fn, encode_fn, group=None):
+    """One Huffman table for the data of all ranks. hist_fn(shard) -> int64[256] on the shard's device;
+    encode_fn(shard, freq64) -> (stream, bits). On the GPUs these are device.huffman_histogram and
+    device.huffman_encode_with_freq (see `huffman_fns`); the gloo CPU tests supply their own."""
+    rank, world = _world(group)
+    freq = reduce_histogram(hist_fn(data_shard), group)
+    stream, bits = encode_fn(data_shard, freq)
+    sizes, off = exchange_sizes(int(bits), freq.device, group)
+    return HuffmanShardedStream(rank, world, stream, int(bits), freq, sizes, off)
+
+
+def huffman_whole_gather(sh, words, splice_fn, group=None):
+    """All ranks end up with the whole-buffer word stream (what huffman_compress writes for the concatenated
+    input): all-gather of the shard words padded to the largest shard, then every shard is spliced at its bit
+    offset by splice_fn(dst_words, dst_bit, src_words, src_bits). words: this rank's int32 word tensor.
+    -> (int32 words, buffer_size bytes)."""
+    nwords, nbytes = whole_stream_size(int(sh.bit_off[-1].item()))
+    out = torch.zeros(nwords + 1, dtype=torch.int32, device=words.device)
+    mxw = (int(sh.shard_bits.max().item()) + 31) // 32
+    mine = torch.zeros(max(mxw, 1), dtype=torch.int32, device=words.device)
+    myw = (sh.bits + 31) // 32
+    mine[:myw] = words[:myw]
+    if sh.world > 1:
+        allw = torch.empty(sh.world * mine.numel(), dtype=torch.int32, device=words.device)
+        dist.all_gather_into_tensor(allw, mine, group=group)
+    else:
+        allw = mine
+    for r in range(sh.world):
+        b = int(sh.shard_bits[r].item())
+        if b:
+            splice_fn(out, int(sh.bit_off[r].item()), allw[r * mine.numel(): (r + 1) * mine.numel()], b)
+    return out[:nwords], nbytes
+
+
+def huffman_fns(ctx):
+    """(hist_fn, encode_fn, splice_fn) of the GPU path for the two functions above."""
+    from . import device as dv
+    return (lambda shard: dv.huffman_histogram(ctx, shard),
+            lambda shard, freq: dv.huffman_encode_with_freq(ctx, shard, freq),
+            lambda dst, bit, src, nbits: dv.huffman_splice(ctx, dst, bit, src, nbits))

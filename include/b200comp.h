@@ -110,6 +110,20 @@ int b200_huffman_encode_with_codes_dev(b200_ctx* ctx, const uint8_t* d_in, uint6
                                        const uint32_t* h_codes, const uint8_t* h_lens,
                                        uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
                                        uint64_t* h_total_words, uint32_t* h_worst_status);
+/* One table over several shards (the reference builds one tree over the whole
+ * input, huffman.c:184-211). Per rank: b200_huffman_histogram_dev -> the caller sums the
+ * 256 x u64 bins over the ranks (all-reduce) -> b200_huffman_encode_with_freq_dev builds the
+ * table from the sum (bins truncated to the reference's uint32_t) and packs this shard from
+ * bit 0 of d_words (side layout = b200_huffman_layout(n, 0); an empty shard is allowed) ->
+ * the caller all-gathers the shard bit counts -> b200_huffman_splice_dev ORs a shard stream
+ * into a ZEROED destination at the exclusive prefix of the bit counts. The spliced words equal
+ * huffman_compress on the concatenated input. Decoding stays per shard (own side index). */
+int b200_huffman_histogram_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t* d_freq64);
+int b200_huffman_encode_with_freq_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, const uint64_t* d_freq64,
+                                      uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
+                                      uint64_t* h_total_words, uint64_t* h_total_bits, uint32_t* h_worst_status);
+int b200_huffman_splice_dev(b200_ctx* ctx, uint32_t* d_dst, uint64_t dst_words_capacity, uint64_t dst_bit,
+                            const uint32_t* d_src, uint64_t src_bits);
 /* table-lookup decoder driven by the side index written by the encoder */
 int b200_huffman_decode_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words,
                             const uint8_t* d_side, uint64_t side_bytes,

@@ -304,6 +304,17 @@ def port_huffman_compress(data):
     return dict(words=words[:nw].copy(), word_idx=wi.value, bit_idx=bi.value, buffer_size=bs.value, codes=codes, lens=lens)
 
 
+def port_huffman_encode(data, codes, lens):
+    """_huffman_compress with a given table (huffman.c:267-285) -> (u32 words, bits)."""
+    d = _as_u8(data)
+    words = np.zeros(d.size + 2, dtype=np.uint32)
+    f = _lib("oracle_port").port_huffman_encode
+    f.restype = C.c_uint64
+    bits = f(_p(d, _u8p), C.c_uint64(d.size), _p(np.ascontiguousarray(codes, dtype=np.uint32), _u32p),
+             _p(np.ascontiguousarray(lens, dtype=np.uint8), _u8p), _p(words, _u32p))
+    return words[: (bits + 31) // 32].copy(), int(bits)
+
+
 def port_huffman_decompress(words, buffer_size, codes, lens, expect):
     w = np.ascontiguousarray(words, dtype=np.uint32)
     cap = expect + 64

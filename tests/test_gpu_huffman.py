@@ -141,3 +141,51 @@ def test_full_size_roundtrip(ctx):
         assert torch.all((bb + 31) // 32 == bw[1:] - bw[:-1])
         dec = dv.huffman_decode(ctx, st)
         assert torch.equal(dec, data)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 3])
+@pytest.mark.parametrize("cuts", [(500_001,), (1, 4097, 4097, 700_000), (0, 333_333, 1_000_003)])
+def test_one_table_over_shards(ctx, ob, kind, cuts):
+    """SURVEY.md §8e whole-buffer mode over ranks, with the ranks played by one GPU: shard histograms summed
+    (the all-reduce), every shard packed with the table of the sum, streams spliced at the prefix of the bit
+    counts == huffman_compress on the whole buffer (huffman.c:288-328); every shard decodes on its own.
+    Cuts at odd byte positions, repeated cuts (empty shards) and a 1-byte shard included."""
+    import torch
+    from compression_algorithms_b200 import device as dv, sharding
+    n = 1_000_003
+    data = _corpus(n, kind, 11)
+    exp = ob.port_huffman_compress(data)
+    edges = [0] + list(cuts) + [n]
+    shards = [_to_dev(ctx, data[a:b]) for a, b in zip(edges[:-1], edges[1:])]
+    freq = torch.stack([dv.huffman_histogram(ctx, s) for s in shards]).sum(0)
+    assert np.array_equal(freq.cpu().numpy(), np.bincount(data, minlength=256))
+    enc = [dv.huffman_encode_with_freq(ctx, s, freq) for s in shards]
+    for st, _ in enc:
+        assert st.worst_status == 0
+        assert np.array_equal(u32(st.codes()[0]), exp["codes"]) and np.array_equal(st.lens()[0].cpu().numpy(), exp["lens"])
+    bits = [b for _, b in enc]
+    off = np.concatenate([[0], np.cumsum(bits)])
+    assert off[-1] == 32 * exp["word_idx"] + exp["bit_idx"]
+    nwords, nbytes = sharding.whole_stream_size(int(off[-1]))
+    assert nbytes == exp["buffer_size"] and nwords == len(exp["words"])
+    out = torch.zeros(nwords, dtype=torch.int32, device=ctx.device)
+    for (st, b), o in reversed(list(zip(enc, off[:-1]))):      # any order: boundary words are OR-ed atomically
+        dv.huffman_splice(ctx, out, int(o), st.words, b)
+    ctx.sync()
+    got = u32(out)
+    assert first_diff(got, exp["words"]) == -1, "spliced stream differs at word %d" % first_diff(got, exp["words"])
+    for (st, _), s in zip(enc, shards):
+        if s.numel():
+            assert torch.equal(dv.huffman_decode(ctx, st), s)
+
+
+def test_splice_rejects_small_destination(ctx):
+    import torch
+    from compression_algorithms_b200 import device as dv
+    src = torch.full((4,), -1, dtype=torch.int32, device=ctx.device)
+    dst = torch.zeros(4, dtype=torch.int32, device=ctx.device)
+    with pytest.raises(RuntimeError):
+        dv.huffman_splice(ctx, dst, 1, src, 128)
+    dv.huffman_splice(ctx, dst, 3, src, 100)
+    ctx.sync()
+    assert u32(dst).tolist() == [0x1FFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFE000000]
