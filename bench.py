@@ -380,4 +380,11 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries the ONE JSON line and nothing else: libraries that print to fd 1 (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, for one) are sent to stderr, the line goes to the saved descriptor.
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     main()
+    _real_stdout.flush()
