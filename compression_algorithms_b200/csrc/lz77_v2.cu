@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                     tq += CLK() - t_mark; t_mark = CLK();
                     __syncwarp();
                     tc += CLK() - t_mark; t_mark = CLK();
-                    const uint32_t key = done ? (0x80000000u | lane) : kk;
+                    const uint32_t key = done ? 0xFFFFFFFFu : kk;   // the finished lanes share one key: MATCH.ANY takes one step per distinct value
                     const uint32_t peers = __match_any_sync(0xffffffffu, key);
                     const bool blocked = !done && (peers & lt_mask) != 0;
                     const uint32_t cmask = __ballot_sync(0xffffffffu, blocked);
