@@ -495,7 +495,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             // (a loner keeps its LONER mark in tokb: P5 / P6 read it as "literal candidate")
             const bool valid = in_range && !loner;
             const uint32_t r = valid ? hr >> 21 : 0xFFu;
-            const uint32_t peers = __match_any_sync(0xffffffffu, r);   // issued first: its latency overlaps the rank below
+            // MATCH.ANY takes one step per distinct value: two matches on the halves of the range id (8 + 4 values, the
+            // invalid lanes share the ninth) instead of one on up to 33 values; issued first, their latency overlaps the rank below
+            const uint32_t peers = __match_any_sync(0xffffffffu, r >> 2) & __match_any_sync(0xffffffffu, r & 3u);
             uint32_t c = 0;
             if (valid) c = bm_rank(bm, pre16, hr & 0x1FFFFFu);
             const uint32_t myrank = __popc(peers & lt_mask);
