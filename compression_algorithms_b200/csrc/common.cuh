@@ -55,7 +55,7 @@ struct b200_ctx {
     int          ev_created, ev_used;
     // copy streams + events of the host-buffer entry points (host_api.cu): input chunks are copied
     // in on s_in, results copied out on s_out, while the codec kernels run on `stream`
-    static const int kPipe = 16;
+    static const int kPipe = 32;
     cudaStream_t s_in, s_out, s_aux;   // s_aux: second kernel stream, so that latency-bound chunk kernels overlap
     cudaEvent_t  ev_in[kPipe], ev_done[kPipe];
     bool         pipe_ready;

@@ -1,6 +1,7 @@
 // Host-buffer entry points: H2D -> *_dev -> D2H on the context's stream. These are
 // what the reference-named shims (csrc/shims/*.c) and bench.py's end-to-end leg call.
 // Device staging buffers live in the context's scratch slots 8..13 and are reused.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/b200comp.h"
 
@@ -22,7 +23,8 @@ extern "C" uint64_t b200_lz77_max_bytes(int variant, uint64_t n, uint64_t block_
 static uint64_t lz_chunk_blocks(const b200_ctx* ctx, uint64_t nblocks) {
     const uint64_t sms = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
     if (nblocks < 4 * sms) return nblocks;                       // too small to be worth splitting
-    uint64_t per = (nblocks + 7) / 8;                            // aim at 8 chunks
+    static const uint64_t target = [] { const char* e = getenv("B200_LZ_CHUNKS"); const long v = e ? atol(e) : 0; return (uint64_t)(v > 0 ? v : 12); }();
+    uint64_t per = (nblocks + target - 1) / target;              // aim at 12 chunks (swept 8 .. 32 on B200 with 1 GB: 78.8 / 76.0 / 76.1 / 75.9 / 76.9 ms for compress + decompress at 8 / 12 / 16 / 24 / 32; B200_LZ_CHUNKS overrides, at most kPipe)
     per = (per + sms - 1) / sms * sms;
     while ((nblocks + per - 1) / per > (uint64_t)b200_ctx::kPipe) per += sms;
     return per;
