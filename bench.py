@@ -245,6 +245,18 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
+    numa = None
+    if world > 1 and os.environ.get("B200_BENCH_NO_AFFINITY") != "1":
+        # one process per GPU: run (and first-touch the pinned host buffers) on the CPUs next to this rank's GPU, so that
+        # the host-buffer leg does not cross the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            numa = sorted(os.sched_getaffinity(0))
+            numa = "cpus %d-%d (%d)" % (numa[0], numa[-1], len(numa))
+        except Exception as e:   # affinity is an optimisation, never a requirement
+            numa = "unchanged (%s)" % type(e).__name__
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -362,7 +374,7 @@ def main():
                                    "compaction) compress + decompress of an enwik9-shaped buffer, BASELINE.json configs[3]",
                        "bytes_per_gpu": n, "block_size": BLOCK, "blocks_per_gpu": nblocks, "token_bytes_per_gpu": int(T),
                        "l2_policy": "input (1 GB) and token stream are far larger than the 126 MB L2; no flush needed",
-                       "sharding": "contiguous block ranges per rank; all-gather of shard sizes only"},
+                       "sharding": "contiguous block ranges per rank; all-gather of shard sizes only", "cpu_affinity_rank0": numa},
             "roundtrip_ok": ok, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu:
