@@ -111,7 +111,12 @@ def cpu_baseline(data_np, sample_bytes, threads=0):
     from oracle import bindings as ob
     n = min(sample_bytes, data_np.size)
     sample = np.ascontiguousarray(data_np[:n])
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0)) or 1
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    if threads <= 0:
+        threads = cores     # explicit: torchrun exports OMP_NUM_THREADS=1, which would leave the harness on one thread
     kind = "reference" if ob.have_ref() else "port"
     t0 = time.perf_counter()
     if kind == "reference":
@@ -127,10 +132,10 @@ def cpu_baseline(data_np, sample_bytes, threads=0):
     t3 = time.perf_counter()
     ok = bad == 0 and np.array_equal(dec, sample)
     tc, td = t1 - t0, t3 - t2
-    return {"value": n / 1e9 / (tc + td), "unit": UNIT, "cores": cores, "kind": kind,
+    return {"value": n / 1e9 / (tc + td), "unit": UNIT, "cores": threads, "kind": kind,
             "sample": "first %d MiB of the workload, %d blocks of 64 KiB, one %s lz77_compress call per block on a fresh table "
                       "spread over %d threads; decode by the oracle port (the reference has no deflate decoder)"
-                      % (n >> 20, len(sizes), "reference" if kind == "reference" else "oracle-port", cores),
+                      % (n >> 20, len(sizes), "reference" if kind == "reference" else "oracle-port", threads),
             "compress_gbps": n / 1e9 / tc, "decompress_gbps": n / 1e9 / td, "roundtrip_ok": bool(ok),
             "token_bytes": int(stream.size)}
 
