@@ -189,3 +189,17 @@ def test_splice_rejects_small_destination(ctx):
     dv.huffman_splice(ctx, dst, 3, src, 100)
     ctx.sync()
     assert u32(dst).tolist() == [0x1FFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFE000000]
+
+
+def test_one_table_argument_errors(ctx):
+    """misaligned input pointer and an empty shard through the sharded whole-buffer entry points"""
+    import torch
+    from compression_algorithms_b200 import device as dv
+    buf = torch.zeros(4096 + 16, dtype=torch.uint8, device=ctx.device)
+    with pytest.raises(RuntimeError):
+        dv.huffman_histogram(ctx, buf[1:4097])          # d_in must be 16-byte aligned
+    freq = dv.huffman_histogram(ctx, torch.tensor(list(b"abracadabra" * 100), dtype=torch.uint8, device=ctx.device))
+    assert int(freq.sum().item()) == 1100 and int(freq[ord("a")].item()) == 500
+    st, bits = dv.huffman_encode_with_freq(ctx, torch.empty(0, dtype=torch.uint8, device=ctx.device), freq)
+    assert bits == 0 and st.total_words == 0 and st.worst_status == 0
+    assert int(st.lens()[0][ord("a")].item()) == 1    # the table of the global histogram is there all the same
