@@ -38,7 +38,8 @@ struct b200_ctx {
     bool         own_stream;
     int          sm_count;
     // named scratch buffers, grown on demand and kept
-    static const int kSlots = 16;
+    static const int kSlots = 32;   // two banks of 16: the host compress path runs consecutive chunks on two kernel streams
+    int          bank = 0;         // 0 or 1: which bank B200_SLOT() names (only host_api.cu switches it)
     void*        buf[kSlots];
     size_t       cap[kSlots];
     // pinned host staging for small results
@@ -62,6 +63,7 @@ struct b200_ctx {
 };
 int b200_pipe_init(b200_ctx* ctx);
 
+#define B200_SLOT(ctx, s) ((s) + 16 * (ctx)->bank)
 int b200_scratch(b200_ctx* ctx, int slot, size_t bytes, void** out);
 int b200_pinned(b200_ctx* ctx, size_t bytes, void** out);
 

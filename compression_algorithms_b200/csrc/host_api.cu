@@ -23,8 +23,8 @@ extern "C" uint64_t b200_lz77_max_bytes(int variant, uint64_t n, uint64_t block_
 static uint64_t lz_chunk_blocks(const b200_ctx* ctx, uint64_t nblocks) {
     const uint64_t sms = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
     if (nblocks < 4 * sms) return nblocks;                       // too small to be worth splitting
-    static const uint64_t target = [] { const char* e = getenv("B200_LZ_CHUNKS"); const long v = e ? atol(e) : 0; return (uint64_t)(v > 0 ? v : 12); }();
-    uint64_t per = (nblocks + target - 1) / target;              // aim at 12 chunks (swept 8 .. 32 on B200 with 1 GB: 78.8 / 76.0 / 76.1 / 75.9 / 76.9 ms for compress + decompress at 8 / 12 / 16 / 24 / 32; B200_LZ_CHUNKS overrides, at most kPipe)
+    static const uint64_t target = [] { const char* e = getenv("B200_LZ_CHUNKS"); const long v = e ? atol(e) : 0; return (uint64_t)(v > 0 ? v : 24); }();
+    uint64_t per = (nblocks + target - 1) / target;              // aim at 24 chunks (swept on B200 with 1 GB, compress + decompress, chunks alternating between two kernel streams: 75.8 / 74.9 / 75.2 / 73.8 / 74.3 ms at 12 / 16 / 20 / 24 / 32; one stream: 78.8 / 76.0 / 76.1 / 75.9 / 76.9 at 8 / 12 / 16 / 24 / 32; B200_LZ_CHUNKS overrides, at most kPipe)
     per = (per + sms - 1) / sms * sms;
     while ((nblocks + per - 1) / per > (uint64_t)b200_ctx::kPipe) per += sms;
     return per;
@@ -63,11 +63,18 @@ extern "C" int b200_lz77_compress_host(b200_ctx* ctx, int variant, const uint8_t
         const uint64_t b0 = c * per, nb = b0 + per < nblocks ? per : nblocks - b0;
         const uint64_t o = b0 * bs, len = o + nb * bs < n ? nb * bs : n - o;
         const uint64_t slot = lz_cap(variant, b0 * bs, b0) + 128 * c;  // worst cases are additive over chunks; 128 covers the rounding
-        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0));
-        B200_TRY(b200_lz77_encode_dev(ctx, variant, d_in + o, len, bs, d_out + slot, lz_cap(variant, len, nb), d_sizes + b0,
-                                      d_boff + b0 + c, nullptr));
-        CUDA_TRY(cudaMemcpyAsync(pin + 8 + c, d_boff + b0 + c + nb, 8, cudaMemcpyDeviceToHost, ctx->stream));   // chunk total
-        CUDA_TRY(cudaEventRecord(ctx->ev_done[c], ctx->stream));
+        // consecutive chunks alternate between two kernel streams, each with its own bank of work arrays: the next chunk's
+        // match finder fills the SMs that the drain of this chunk's last wave (and its scan + compaction) leave idle
+        cudaStream_t keep = ctx->stream;
+        if (c & 1) { ctx->stream = ctx->s_aux; ctx->bank = 1; }
+        int rc2 = B200_OK;
+        if (cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0) != cudaSuccess) rc2 = B200_ERR_CUDA;
+        if (rc2 == B200_OK) rc2 = b200_lz77_encode_dev(ctx, variant, d_in + o, len, bs, d_out + slot, lz_cap(variant, len, nb), d_sizes + b0,
+                                                       d_boff + b0 + c, nullptr);
+        if (rc2 == B200_OK && cudaMemcpyAsync(pin + 8 + c, d_boff + b0 + c + nb, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc2 = B200_ERR_CUDA;   // chunk total
+        if (rc2 == B200_OK && cudaEventRecord(ctx->ev_done[c], ctx->stream) != cudaSuccess) rc2 = B200_ERR_CUDA;
+        ctx->stream = keep; ctx->bank = 0;
+        if (rc2 != B200_OK) { if (rc2 == B200_ERR_CUDA) B200_SET_ERR("lz77 compress: stream/event call failed: %s", cudaGetErrorString(cudaGetLastError())); return rc2; }
     }
     // 3. as each chunk finishes, its tokens go home while later chunks are still being compressed
     uint64_t total = 0;
@@ -86,6 +93,7 @@ extern "C" int b200_lz77_compress_host(b200_ctx* ctx, int variant, const uint8_t
         total += tc;
     }
     CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_aux));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (h_total_bytes) *h_total_bytes = total;
     if (rc != B200_OK) { B200_SET_ERR("lz77: output needs %llu bytes, buffer has %llu", (unsigned long long)total, (unsigned long long)out_capacity); return rc; }

@@ -450,8 +450,8 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
     // v2: whole table in one SM's shared memory (blocks <= 64 KiB); v1: table in HBM (any block <= 4 MiB)
     const bool use_v2 = lz77_v2_supported(bs) && !getenv("B200_LZ_FORCE_V1");
     uint8_t* scratch; uint64_t* misc;
-    B200_TRY(b200_scratch(ctx, 3, (size_t)(nblocks * stride + 64), reinterpret_cast<void**>(&scratch)));
-    B200_TRY(b200_scratch(ctx, 4, (size_t)(nblocks * 8 + 64), reinterpret_cast<void**>(&misc)));
+    B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 3), (size_t)(nblocks * stride + 64), reinterpret_cast<void**>(&scratch)));
+    B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 4), (size_t)(nblocks * 8 + 64), reinterpret_cast<void**>(&misc)));
     uint64_t* info = misc;                       // [0] total, [1] overflow
     uint32_t* err = reinterpret_cast<uint32_t*>(misc + 2);
     uint64_t* block_bytes = misc + 4;
@@ -472,9 +472,9 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
         const uint64_t per_warp = (nblocks + nwarps - 1) / nwarps;
         const size_t table_bytes = (size_t)nwarps * (TABLE_SLOTS + GUARD) * sizeof(uint2);
         uint2* tables; uint32_t* clrq;
-        const bool fresh = ctx->cap[1] < table_bytes;
-        B200_TRY(b200_scratch(ctx, 1, table_bytes, reinterpret_cast<void**>(&tables)));
-        B200_TRY(b200_scratch(ctx, 2, (size_t)nwarps * CLRQ * 4, reinterpret_cast<void**>(&clrq)));
+        const bool fresh = ctx->cap[B200_SLOT(ctx, 1)] < table_bytes;
+        B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 1), table_bytes, reinterpret_cast<void**>(&tables)));
+        B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 2), (size_t)nwarps * CLRQ * 4, reinterpret_cast<void**>(&clrq)));
         uint32_t& ep = ctx->lz_epoch;
         const unsigned grid = (unsigned)(nwarps / 4);
         if (big) {

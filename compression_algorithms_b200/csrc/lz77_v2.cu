@@ -986,9 +986,9 @@ int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, 
     uint64_t grid = (uint64_t)ctx->sm_count;
     if (grid > nblocks) grid = nblocks;
     uint32_t *lists, *tok; uint8_t* carry;
-    B200_TRY(b200_scratch(ctx, 13, (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&lists)));
-    B200_TRY(b200_scratch(ctx, 14, (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&tok)));
-    B200_TRY(b200_scratch(ctx, 15, bs > MAXB ? (size_t)grid * CARRY_BYTES + 64 : 64, reinterpret_cast<void**>(&carry)));
+    B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 13), (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&lists)));
+    B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 14), (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&tok)));
+    B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 15), bs > MAXB ? (size_t)grid * CARRY_BYTES + 64 : 64, reinterpret_cast<void**>(&carry)));
 #define LZ_V2_LAUNCH(V, D) lz77_v2_kernel<V, D><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, lists, tok, carry, scratch, stride, d_block_sizes, block_bytes, dbg_tok)
     if (dbg_tok) { if (variant == 0) LZ_V2_LAUNCH(0, true); else LZ_V2_LAUNCH(1, true); }
     else { if (variant == 0) LZ_V2_LAUNCH(0, false); else LZ_V2_LAUNCH(1, false); }
