@@ -495,9 +495,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
             // (a loner keeps its LONER mark in tokb: P5 / P6 read it as "literal candidate")
             const bool valid = in_range && !loner;
             const uint32_t r = valid ? hr >> 21 : 0xFFu;
-            // MATCH.ANY takes one step per distinct value: two matches on the halves of the range id (8 + 4 values, the
-            // invalid lanes share the ninth) instead of one on up to 33 values; issued first, their latency overlaps the rank below
-            const uint32_t peers = __match_any_sync(0xffffffffu, r >> 2) & __match_any_sync(0xffffffffu, r & 3u);
+            // MATCH.ANY takes one step per distinct value: three matches on pieces of the range id (4 + 4 + 2 values, the
+            // invalid lanes share a fifth in the first) instead of one on up to 33 values (two matches, 8 + 4: 44.6 ms per
+            // GB, three: 44.2); issued first, their latency overlaps the rank below
+            const uint32_t peers = __match_any_sync(0xffffffffu, r >> 3) & __match_any_sync(0xffffffffu, (r >> 1) & 3u) & __match_any_sync(0xffffffffu, r & 1u);
             uint32_t c = 0;
             if (valid) c = bm_rank(bm, pre16, hr & 0x1FFFFFu);
             const uint32_t myrank = __popc(peers & lt_mask);
