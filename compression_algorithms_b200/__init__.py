@@ -4,8 +4,7 @@ the C entry points of jdm365/Compression_Algorithms.
 Layout:
   csrc/        hand-written CUDA kernels + the C-ABI (include/b200comp.h)
   device.py    device-resident Python mirror of the C-ABI (torch = memory + streams)
-  host.py      host-buffer mirror of the reference's own functions (names, argument
-               meaning and error behaviour of the reference headers)
+  csrc/shims/  the reference's own function names (one C library per reference directory)
   corpus.py    seeded synthetic inputs
   sharding.py  block-range sharding across ranks + all-gather of shard sizes
 """

@@ -38,7 +38,7 @@ struct b200_ctx {
     bool         own_stream;
     int          sm_count;
     // named scratch buffers, grown on demand and kept
-    static const int kSlots = 32;   // two banks of 16: the host compress path runs consecutive chunks on two kernel streams
+    static const int kSlots = 40;   // two banks of 20: the host compress path runs consecutive chunks on two kernel streams
     int          bank = 0;         // 0 or 1: which bank B200_SLOT() names (only host_api.cu switches it)
     void*        buf[kSlots];
     size_t       cap[kSlots];
@@ -46,7 +46,7 @@ struct b200_ctx {
     void*        pinned;
     size_t       pinned_cap;
     uint64_t     launches;  // kernels launched through this context (bench "gpu_launches")
-    uint32_t     lz_epoch;  // last epoch tag used in this context's LZ77 table arena
+    uint32_t     lz_epoch[2];  // last epoch tag used in each bank's LZ77 table arena (v1 path)
     // optional timing of the dominant kernel of every codec call (bench.py roofline):
     // a pool of event pairs recorded in-stream, read back after the timed region
     bool         timing;
@@ -63,7 +63,7 @@ struct b200_ctx {
 };
 int b200_pipe_init(b200_ctx* ctx);
 
-#define B200_SLOT(ctx, s) ((s) + 16 * (ctx)->bank)
+#define B200_SLOT(ctx, s) ((s) + 20 * (ctx)->bank)
 int b200_scratch(b200_ctx* ctx, int slot, size_t bytes, void** out);
 int b200_pinned(b200_ctx* ctx, size_t bytes, void** out);
 

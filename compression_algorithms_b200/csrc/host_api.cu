@@ -8,7 +8,7 @@
 namespace {
 inline uint64_t lz_bs(uint64_t n, uint64_t block_size) { return (block_size == 0 || block_size > n) ? n : block_size; }
 inline uint64_t lz_cap(int variant, uint64_t n, uint64_t nblocks) {
-    return (variant == B200_LZ_DEFLATE ? 2 * n : n + n / 8 + 8 * nblocks) + 64;
+    return (variant == B200_LZ_DEFLATE ? 2 * n + 2 * nblocks : n + n / 8 + 8 * nblocks) + 64;
 }
 }  // namespace
 
@@ -114,6 +114,17 @@ extern "C" int b200_lz77_decompress_host(b200_ctx* ctx, int variant, const uint8
     if (n == 0) return B200_OK;
     const uint64_t bs = lz_bs(n, block_size);
     const uint64_t nblocks = (n + bs - 1) / bs;
+    if (variant != 0 && variant != 1) { B200_SET_ERR("lz77: variant must be 0 or 1"); return B200_ERR_ARG; }
+    // the index comes from the caller: every block must lie inside the stream and carry the size its extent implies
+    for (uint64_t b = 0; b < nblocks; ++b) {
+        const uint64_t o0 = h_block_off[b], o1 = b + 1 < nblocks ? h_block_off[b + 1] : stream_bytes;
+        const uint64_t need = variant == B200_LZ_DEFLATE ? h_block_sizes[b] : h_block_sizes[b] / 8 + 1;
+        if (o0 > o1 || o1 > stream_bytes || need > o1 - o0) {
+            B200_SET_ERR("lz77: block %llu of the index does not fit the stream (offset %llu, next %llu, size %llu, stream %llu)",
+                         (unsigned long long)b, (unsigned long long)o0, (unsigned long long)o1, (unsigned long long)h_block_sizes[b], (unsigned long long)stream_bytes);
+            return B200_ERR_FORMAT;
+        }
+    }
     B200_TRY(b200_pipe_init(ctx));
     const uint64_t per = lz_chunk_blocks(ctx, nblocks);
     const uint64_t nchunks = (nblocks + per - 1) / per;
@@ -325,6 +336,21 @@ extern "C" int b200_fse_decompress_host(b200_ctx* ctx, const uint64_t* h_contain
     const uint64_t o_norm = 8, o_bits = o_norm + w8(nblocks * 512), o_stream = o_bits + w8(nsegs * 4);
     if (o_stream + total > words) { B200_SET_ERR("fse: truncated container"); return B200_ERR_FORMAT; }
     if (n > out_capacity) { B200_SET_ERR("fse: output needs %llu bytes, buffer has %llu", (unsigned long long)n, (unsigned long long)out_capacity); return B200_ERR_CAPACITY; }
+    {   // the tables and the index are read from the container: check them before any kernel trusts them
+        const uint16_t* norm = reinterpret_cast<const uint16_t*>(h_container + o_norm);
+        for (uint64_t b = 0; b < nblocks; ++b) {
+            uint32_t sum = 0;
+            for (int k = 0; k < 256; ++k) sum += norm[b * 256 + k];
+            if (sum != 256) { B200_SET_ERR("fse: normalised counts of block %llu sum to %u, not 256", (unsigned long long)b, sum); return B200_ERR_FORMAT; }
+        }
+        const uint32_t* sb = reinterpret_cast<const uint32_t*>(h_container + o_bits);
+        uint64_t words_needed = 0;
+        for (uint64_t g = 0; g < nsegs; ++g) {
+            if (sb[g] < 16 || sb[g] > 64ull * (seg + 8)) { B200_SET_ERR("fse: segment %llu claims %u bits", (unsigned long long)g, sb[g]); return B200_ERR_FORMAT; }
+            words_needed += ((uint64_t)sb[g] + 63) >> 6;
+        }
+        if (words_needed != total) { B200_SET_ERR("fse: segment index covers %llu words, the stream has %llu", (unsigned long long)words_needed, (unsigned long long)total); return B200_ERR_FORMAT; }
+    }
     uint8_t *d_out, *d_side; uint64_t* d_words;
     B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_out)));
     B200_TRY(b200_scratch(ctx, 11, (total + 4) * 8, reinterpret_cast<void**>(&d_words)));

@@ -428,6 +428,9 @@ inline uint64_t round16(uint64_t x) { return (x + 15) & ~(uint64_t)15; }
 bool lz77_v2_supported(uint64_t bs);
 int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
                    uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok);
+// blocks of at most 65536 bytes: occupancy-decided finds + lane-serial simulation of the mixed clusters (lz77_v3.cu)
+int lz77_v3_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
+                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok);
 
 extern "C" uint64_t b200_lz77_block_stride(uint64_t block_size) { return round16(2 * block_size + 16); }
 
@@ -459,7 +462,8 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
     if (use_v2) {
         if (dbg_tok && bs > 65536) { B200_SET_ERR("lz77: token dump needs blocks <= 65536"); return B200_ERR_ARG; }
         B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
-        B200_TRY(lz77_v2_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
+        if (bs <= 65536 && getenv("B200_LZ_V3")) B200_TRY(lz77_v3_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
+        else B200_TRY(lz77_v2_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
         B200_TIMED_END(ctx);
     } else {
         if (dbg_tok) { B200_SET_ERR("lz77: token dump needs the shared-memory path (block <= 65536)"); return B200_ERR_ARG; }
@@ -475,7 +479,7 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
         const bool fresh = ctx->cap[B200_SLOT(ctx, 1)] < table_bytes;
         B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 1), table_bytes, reinterpret_cast<void**>(&tables)));
         B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 2), (size_t)nwarps * CLRQ * 4, reinterpret_cast<void**>(&clrq)));
-        uint32_t& ep = ctx->lz_epoch;
+        uint32_t& ep = ctx->lz_epoch[ctx->bank & 1];   // one table arena (and epoch counter) per bank
         const unsigned grid = (unsigned)(nwarps / 4);
         if (big) {
             // waves of nwarps blocks; the epoch tags of earlier calls are wiped, so restart them
@@ -494,7 +498,7 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
             ep = MAX_EPOCH;   // forces a clear before the next epoch-tagged call
         } else {
             if (fresh || ep + per_warp > MAX_EPOCH) {
-                CUDA_TRY(cudaMemsetAsync(tables, 0, ctx->cap[1], ctx->stream));
+                CUDA_TRY(cudaMemsetAsync(tables, 0, ctx->cap[B200_SLOT(ctx, 1)], ctx->stream));
                 ep = 0;
             }
             B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);

@@ -14,6 +14,40 @@ uint32_t hash(uint32_t k) {
     return h % (1u << (WINDOW_BITS + 6));
 }
 
+/* table helpers of lz77.h:33-37. A guard tail behind the 2^20 slots takes the probes that run past
+ * the end (the reference indexes out of bounds there). */
+#define SHIM_GUARD (1u << WINDOW_BITS)
+void init_hash_table(HashTableArray* t) {
+    t->buckets = (ArrayNode*)calloc((size_t)TABLE_SIZE + SHIM_GUARD, sizeof(ArrayNode));
+    memset(t->bucket_indices, 0, sizeof(t->bucket_indices));
+    t->current_idx = 0;
+    t->is_full = false;
+}
+
+void insert_hash_table(HashTableArray* t, uint32_t pattern, uint64_t index) {
+    uint32_t s = hash(pattern);
+    while (t->buckets[s].is_set) ++s;                      /* no wrap (lz77.c:61) */
+    t->buckets[s].pattern = pattern; t->buckets[s].index = index; t->buckets[s].is_set = true;
+    if (t->is_full) {   /* evict the slot recorded one window ago (flips one insert early: SURVEY.md U10) */
+        ArrayNode* old = &t->buckets[t->bucket_indices[t->current_idx]];
+        old->pattern = 0; old->index = 0; old->is_set = false;
+    }
+    t->bucket_indices[t->current_idx++] = s;
+    if (t->current_idx >= (1u << WINDOW_BITS) - 1) t->is_full = true;
+    t->current_idx %= (1u << WINDOW_BITS);
+}
+
+uint64_t find(HashTableArray* t, uint32_t pattern) {
+    uint32_t s = hash(pattern);
+    while (t->buckets[s].is_set && t->buckets[s].pattern != pattern) ++s;
+    return t->buckets[s].is_set ? t->buckets[s].index : UINT64_MAX;
+}
+
+void print_bit_string(const char* buffer, uint64_t size) {
+    for (uint64_t i = 0; i < size; ++i) for (int b = 7; b >= 0; --b) putchar(((unsigned char)buffer[i] >> b) & 1 ? '1' : '0');
+    putchar('\n');
+}
+
 char* read_input_buffer(const char* filename, uint64_t* size) {
     FILE* f = fopen(filename, "rb");
     if (!f) { printf("ERROR: cannot open %s\n", filename); exit(1); }

@@ -211,7 +211,7 @@ def lz77_alloc(ctx, n, block_size, variant):
     bs = n if (block_size == 0 or block_size > n) else block_size
     nblocks = max(1, (n + bs - 1) // max(bs, 1))
     # variant 0 worst case 9 bits/byte + 1 byte/block; variant 1 worst case 2 bytes/byte
-    cap = (2 * n if variant == LZ_DEFLATE else n + n // 8 + 8 * nblocks) + 64
+    cap = (2 * n + 2 * nblocks if variant == LZ_DEFLATE else n + n // 8 + 8 * nblocks) + 64
     return Lz77Stream(variant=variant,
                       out=torch.empty(cap, dtype=torch.uint8, device=ctx.device),
                       block_sizes=torch.empty(nblocks, dtype=torch.int64, device=ctx.device),

@@ -25,6 +25,28 @@ typedef struct {        /* lz77.h:14-17 */
     uint64_t bit_index;
 } BitStream;
 
+#define TABLE_SIZE (1 << (WINDOW_BITS + 6))   /* lz77.h:8 */
+
+typedef struct ArrayNode {   /* lz77.h:19-23 */
+    uint32_t pattern;
+    uint64_t index;
+    bool is_set;
+} ArrayNode;
+
+typedef struct {             /* lz77.h:25-30 */
+    ArrayNode* buckets;
+    uint32_t bucket_indices[1 << WINDOW_BITS];
+    uint32_t current_idx;
+    bool is_full;
+} HashTableArray;
+
+/* host-side table helpers of lz77.h:33-37 (the drivers do not call them; exported so that every
+ * public name of the header resolves). They run on the host: one table, one caller. */
+void     init_hash_table(HashTableArray* table);                                    /* lz77.c:43-53  */
+void     insert_hash_table(HashTableArray* table, uint32_t pattern, uint64_t index); /* lz77.c:55-86  */
+uint64_t find(HashTableArray* table, uint32_t pattern);                             /* lz77.c:94-108 */
+void     print_bit_string(const char* buffer, uint64_t size);                       /* lz77.c:111-119 */
+
 uint64_t min(uint64_t a, uint64_t b);                      /* lz77.c:9  */
 uint64_t max(uint64_t a, uint64_t b);                      /* lz77.c:10 */
 uint32_t hash(uint32_t pattern);                           /* lz77.c:13-41 */
