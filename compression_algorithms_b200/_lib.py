@@ -93,6 +93,10 @@ def core():
             lib.b200_fse_encode_dev.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, u64p]
             lib.b200_fse_decode_dev.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, vp, u32p]
             lib.b200_fse_normalize_dev.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64]
+            lib.b200_fse_container_max_words.restype = C.c_uint64
+            lib.b200_fse_container_max_words.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+            lib.b200_fse_compress_host.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.c_uint64, u64p]
+            lib.b200_fse_decompress_host.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p]
         _core = lib
     return _core
 
@@ -106,6 +110,7 @@ def corpus():
             raise RuntimeError("%s is missing: run `python -m compression_algorithms_b200.build`" % p)
         lib = C.CDLL(p)
         lib.b200_corpus_generate.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint64]
+        lib.b200_corpus_generate_range.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64]
         _corpus = lib
     return _corpus
 

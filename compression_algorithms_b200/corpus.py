@@ -20,3 +20,14 @@ def generate(n, kind=ENWIK, seed=DEFAULT_SEED, out=None):
     if rc:
         raise ValueError("b200_corpus_generate failed: %d" % rc)
     return a[:n]
+
+
+def generate_range(start, length, kind=ENWIK, seed=DEFAULT_SEED, out=None):
+    """Bytes [start, start + length) of the buffer generate(N, kind, seed) gives for any N >= start + length:
+    every rank of a multi-GPU run materialises only its own shard of one global buffer."""
+    a = np.empty(length, dtype=np.uint8) if out is None else out
+    assert a.dtype == np.uint8 and a.size >= length and a.flags["C_CONTIGUOUS"]
+    rc = _lib.corpus().b200_corpus_generate_range(a.ctypes.data_as(C.c_void_p), start, length, kind, seed)
+    if rc:
+        raise ValueError("b200_corpus_generate_range failed: %d" % rc)
+    return a[:length]

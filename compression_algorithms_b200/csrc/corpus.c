@@ -200,3 +200,47 @@ int b200_corpus_generate(uint8_t* out, uint64_t n, int kind, uint64_t seed) {
     free(v);
     return 0;
 }
+
+/* Bytes [start, start + len) of the buffer b200_corpus_generate(out, N, kind, seed) would produce for any
+ * N >= start + len (chunks are independent), without generating what lies before: lets every rank of a
+ * multi-GPU run materialise only its own shard of ONE global buffer. */
+int b200_corpus_generate_range(uint8_t* out, uint64_t start, uint64_t len, int kind, uint64_t seed) {
+    if (kind < 0 || kind > 3) return 1;
+    if (len == 0) return 0;
+    vocab_t* v = NULL;
+    if (kind == 0) {
+        v = (vocab_t*)malloc(sizeof(vocab_t));
+        if (!v) return 2;
+        build_vocab(v, seed);
+    }
+    const uint64_t c0 = start / CHUNK, c1 = (start + len - 1) / CHUNK;
+    int rc = 0;
+#pragma omp parallel
+    {
+        uint8_t* tmp = (uint8_t*)malloc(CHUNK);
+        if (!tmp) {
+#pragma omp atomic write
+            rc = 2;
+        }
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t c = (int64_t)c0; c <= (int64_t)c1; ++c) {
+            if (!tmp) continue;
+            const uint64_t off = (uint64_t)c * CHUNK;
+            const uint64_t lo = off > start ? off : start, hi = off + CHUNK < start + len ? off + CHUNK : start + len;
+            if (lo == off && hi == off + CHUNK) {   /* whole chunk: straight into place */
+                if (kind == 0) gen_enwik_chunk(out + (lo - start), CHUNK, v, seed, (uint64_t)c);
+                else gen_simple_chunk(out + (lo - start), CHUNK, kind, seed, (uint64_t)c);
+            } else {
+                /* a chunk's bytes do not depend on how much of it is asked for beyond the prefix property, so
+                 * generate the chunk up to `hi` and keep the tail */
+                const size_t want = (size_t)(hi - off);
+                if (kind == 0) gen_enwik_chunk(tmp, want, v, seed, (uint64_t)c);
+                else gen_simple_chunk(tmp, want, kind, seed, (uint64_t)c);
+                memcpy(out + (lo - start), tmp + (lo - off), (size_t)(hi - lo));
+            }
+        }
+        free(tmp);
+    }
+    free(v);
+    return rc;
+}

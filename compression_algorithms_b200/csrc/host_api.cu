@@ -10,6 +10,28 @@ inline uint64_t lz_bs(uint64_t n, uint64_t block_size) { return (block_size == 0
 inline uint64_t lz_cap(int variant, uint64_t n, uint64_t nblocks) {
     return (variant == B200_LZ_DEFLATE ? 2 * n + 2 * nblocks : n + n / 8 + 8 * nblocks) + 64;
 }
+
+// A caller's malloc'd (pageable) buffer is copied by the driver through small bounce buffers at a few GB/s. Large
+// pageable buffers are page-locked for the duration of the call instead (cudaHostRegister), so that the chunked
+// copies run at PCIe speed and really overlap the kernels; pinned buffers (b200_host_alloc) are left alone.
+struct HostPin {
+    void* p = nullptr;
+    explicit HostPin(const void* ptr, uint64_t bytes, bool read_only) {
+        static const uint64_t min_bytes = [] { const char* e = getenv("B200_PIN_MIN_BYTES"); return e ? (uint64_t)atoll(e) : (16ull << 20); }();
+        if (!ptr || bytes < min_bytes) return;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return; }
+        if (a.type != cudaMemoryTypeUnregistered) return;
+        unsigned flags = cudaHostRegisterDefault;
+        if (read_only) flags |= cudaHostRegisterReadOnly;
+        cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, flags);
+        if (e != cudaSuccess && read_only) { cudaGetLastError(); e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault); }
+        if (e == cudaSuccess) p = const_cast<void*>(ptr); else cudaGetLastError();   // not fatal: the copy just stays pageable
+    }
+    ~HostPin() { if (p) cudaHostUnregister(p); }
+    HostPin(const HostPin&) = delete;
+    HostPin& operator=(const HostPin&) = delete;
+};
 }  // namespace
 
 extern "C" uint64_t b200_lz77_max_bytes(int variant, uint64_t n, uint64_t block_size) {
@@ -42,6 +64,7 @@ extern "C" int b200_lz77_compress_host(b200_ctx* ctx, int variant, const uint8_t
     const uint64_t nblocks = (n + bs - 1) / bs;
     const uint64_t cap = lz_cap(variant, n, nblocks);
     B200_TRY(b200_pipe_init(ctx));
+    HostPin pin_in(h_in, n, true), pin_out(h_out, out_capacity < cap ? out_capacity : cap, false);
     const uint64_t per = lz_chunk_blocks(ctx, nblocks);
     const uint64_t nchunks = (nblocks + per - 1) / per;
     uint8_t *d_in, *d_out; uint64_t* d_idx; uint64_t* pin;
@@ -126,6 +149,7 @@ extern "C" int b200_lz77_decompress_host(b200_ctx* ctx, int variant, const uint8
         }
     }
     B200_TRY(b200_pipe_init(ctx));
+    HostPin pin_in(h_stream, stream_bytes, true), pin_out(h_out, n, false);
     const uint64_t per = lz_chunk_blocks(ctx, nblocks);
     const uint64_t nchunks = (nblocks + per - 1) / per;
     uint8_t *d_stream, *d_out; uint64_t* d_idx;
@@ -346,7 +370,8 @@ extern "C" int b200_fse_decompress_host(b200_ctx* ctx, const uint64_t* h_contain
         const uint32_t* sb = reinterpret_cast<const uint32_t*>(h_container + o_bits);
         uint64_t words_needed = 0;
         for (uint64_t g = 0; g < nsegs; ++g) {
-            if (sb[g] < 16 || sb[g] > 64ull * (seg + 8)) { B200_SET_ERR("fse: segment %llu claims %u bits", (unsigned long long)g, sb[g]); return B200_ERR_FORMAT; }
+            // (0 bits = a segment behind the end of the input)
+            if (sb[g] > 64ull * (seg + 8)) { B200_SET_ERR("fse: segment %llu claims %u bits", (unsigned long long)g, sb[g]); return B200_ERR_FORMAT; }
             words_needed += ((uint64_t)sb[g] + 63) >> 6;
         }
         if (words_needed != total) { B200_SET_ERR("fse: segment index covers %llu words, the stream has %llu", (unsigned long long)words_needed, (unsigned long long)total); return B200_ERR_FORMAT; }

@@ -163,6 +163,9 @@ def huffman_encode_with_freq(ctx, data, freq64):
     _check_u8(data)
     n = data.numel()
     st = huffman_alloc(ctx, n, 0)
+    # the table comes from the GLOBAL histogram: a shard whose own distribution differs (binary data on one rank,
+    # text on the others) can need up to the reference's 32 bits per symbol, not the 8 of a self-built table
+    st.words = torch.empty(n + 8, dtype=torch.int32, device=ctx.device)
     tw, tb, ws = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
     _lib.check(_lib.core().b200_huffman_encode_with_freq_dev(
         ctx.handle, _ptr(data), n, _ptr(freq64), _ptr(st.words), st.words.numel(), _ptr(st.side), st.side.numel(),

@@ -117,7 +117,8 @@ int b200_huffman_encode_with_codes_dev(b200_ctx* ctx, const uint8_t* d_in, uint6
  * bit 0 of d_words (side layout = b200_huffman_layout(n, 0); an empty shard is allowed) ->
  * the caller all-gathers the shard bit counts -> b200_huffman_splice_dev ORs a shard stream
  * into a ZEROED destination at the exclusive prefix of the bit counts. The spliced words equal
- * huffman_compress on the concatenated input. Decoding stays per shard (own side index). */
+ * huffman_compress on the concatenated input. Decoding stays per shard (own side index).
+ * words_capacity: the table is not the shard's own, so allow the reference's 32 bits per symbol (n + 4 words). */
 int b200_huffman_histogram_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t* d_freq64);
 int b200_huffman_encode_with_freq_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, const uint64_t* d_freq64,
                                       uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,

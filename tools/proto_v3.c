@@ -159,20 +159,24 @@ static void v3_block(const uint8_t* d, uint32_t n, int variant, uint32_t* F, sta
         const uint32_t lo = start[b], hi = start[b + 1];
         if (hi - lo > st->maxlane) st->maxlane = hi - lo;
         uint32_t ei = lo;
-        uint32_t hint_c = NONE, hint_w = 0;
+        uint32_t hint_c = NONE, hint_w = 0, hw = 0;
         for (uint32_t i = lo; i < hi; ++i) {
             const uint32_t p = lpos[i], c = cc[p];
             ++st->simsteps;
             /* FIFO expiry: entry j is live at time p iff j + W >= p */
             while (ei < i && lpos[ei] + W < p) {
-                const uint32_t s = lslot[ei];
-                M[s >> 5] &= ~(1u << (s & 31));
-                if (hint_c != NONE && s >= hint_c && (s >> 5) < hint_w) hint_w = s >> 5;
+                const uint32_t s = lslot[ei], sw = s >> 5, sbit = 1u << (s & 31);
+                M[sw] &= ~sbit;
+                if (s >= hint_c) {
+                    if (sw < hint_w) { hint_w = sw; hw = ~sbit; }
+                    else if (sw == hint_w) hw &= ~sbit;
+                }
                 ++ei;
             }
             const int need_find = cls[p] == 2 || NONUNI[cca[p]];
-            uint32_t s = c;
+            const int is_head = cls[p] == 1;
             if (need_find) {
+                uint32_t s = c;
                 const uint32_t w = word_at(d, n, p);
                 uint32_t m = NONE;
                 while ((M[s >> 5] >> (s & 31)) & 1u) {
@@ -182,14 +186,19 @@ static void v3_block(const uint8_t* d, uint32_t n, int variant, uint32_t* F, sta
                 }
                 F[p] = m;
             }
-            /* first-fit: first dead slot at/after c (never leaves the cluster) */
             uint32_t wi, z;
-            if (c == hint_c && hint_w > (c >> 5)) { wi = hint_w; z = ~M[wi]; }
+            if (c == hint_c) { wi = hint_w; z = ~hw; if (wi == (c >> 5)) z &= 0xFFFFFFFFu << (c & 31); }
             else { wi = c >> 5; z = ~M[wi] & (0xFFFFFFFFu << (c & 31)); }
             while (!z) { ++wi; z = ~M[wi]; }
             const uint32_t e = (wi << 5) + (uint32_t)__builtin_ctz(z);
-            if (cls[p] == 1) { hint_c = c; hint_w = wi; }
-            M[e >> 5] |= 1u << (e & 31);
+            const uint32_t ebit = 1u << (e & 31);
+            /* check against the plain search */
+            { uint32_t s2 = c; while ((M[s2 >> 5] >> (s2 & 31)) & 1u) ++s2; if (s2 != e) { printf("HINT MISMATCH p %u c %u: %u vs %u\n", p, c, e, s2); exit(3); } }
+            if (is_head) {
+                if (c != hint_c || wi != hint_w) { hw = ~z; if (wi == (c >> 5)) hw |= ~(0xFFFFFFFFu << (c & 31)); }
+                hint_c = c; hint_w = wi; hw |= ebit;
+            } else if (e >= hint_c && (e >> 5) == hint_w) hw |= ebit;
+            M[e >> 5] |= ebit;
             T[e] = (uint16_t)p;
             lslot[i] = e;
         }
