@@ -86,6 +86,14 @@ def core():
         lib.b200_deflate_decompress_dev.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]
         lib.b200_deflate_compress_host.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, u64p, u32p]
         lib.b200_deflate_decompress_host.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
+        for name in ("b200_huffman_container_max_bytes", "b200_deflate_container_max_bytes"):
+            getattr(lib, name).restype = C.c_uint64
+            getattr(lib, name).argtypes = [C.c_uint64, C.c_uint64]
+        lib.b200_container_info.argtypes = [vp, C.c_uint64, u32p, u64p, u64p]
+        for name in ("b200_huffman_compress_container_host", "b200_deflate_compress_container_host"):
+            getattr(lib, name).argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, u64p]
+        for name in ("b200_huffman_decompress_container_host", "b200_deflate_decompress_container_host"):
+            getattr(lib, name).argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p]
         if hasattr(lib, "b200_fse_layout_for"):
             lib.b200_fse_layout_for.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(FseLayout)]
             lib.b200_fse_max_words.restype = C.c_uint64

@@ -458,6 +458,19 @@ extern "C" int b200_dfl_encode_dev(b200_ctx* ctx, const uint8_t* d_tokens, uint6
     return B200_OK;
 }
 
+// decoder side of a stored stream (container.cu): frequencies[286] of every block -> codes, lengths, trees, meta
+extern "C" int b200_dfl_tables_from_freq_dev(b200_ctx* ctx, uint8_t* d_side, uint64_t side_bytes, uint64_t n, uint64_t block_size) {
+    b200_dfl_layout L;
+    B200_TRY(b200_dfl_layout_for(n, block_size, &L));
+    if (side_bytes < L.bytes) { B200_SET_ERR("deflate entropy stage: side buffer too small"); return B200_ERR_CAPACITY; }
+    huff_build_kernel<NSYM, STR, true><<<(unsigned)L.nblocks, 32, 0, ctx->stream>>>(
+        reinterpret_cast<const uint32_t*>(d_side + L.off_freq), reinterpret_cast<uint32_t*>(d_side + L.off_codes),
+        d_side + L.off_lens, reinterpret_cast<int16_t*>(d_side + L.off_tree), reinterpret_cast<uint32_t*>(d_side + L.off_meta));
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
 extern "C" int b200_dfl_decode_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words, const uint8_t* d_side,
                                    uint64_t side_bytes, uint64_t n, uint64_t block_size, uint8_t* d_tokens_out) {
     if (n == 0) return B200_OK;

@@ -335,6 +335,20 @@ extern "C" int b200_huffman_tables_dev(b200_ctx* ctx, const uint8_t* d_in, uint6
     return huff_tables(ctx, d_in, n, block_size, d_side, side_bytes, &L, &bs);
 }
 
+// decoder side of a stored stream (container.cu): with freq[] of every block already in d_side, rebuild codes, lengths,
+// trees and meta with the same heap replay the encoder ran
+extern "C" int b200_huffman_tables_from_freq_dev(b200_ctx* ctx, uint8_t* d_side, uint64_t side_bytes, uint64_t n, uint64_t block_size) {
+    b200_huff_layout L;
+    B200_TRY(b200_huffman_layout(n, block_size, &L));
+    if (side_bytes < L.bytes) { B200_SET_ERR("huffman: side buffer too small"); return B200_ERR_CAPACITY; }
+    huff_build_kernel<256, 256, false><<<(unsigned)L.nblocks, 32, 0, ctx->stream>>>(
+        reinterpret_cast<const uint32_t*>(d_side + L.off_freq), reinterpret_cast<uint32_t*>(d_side + L.off_codes),
+        d_side + L.off_lens, reinterpret_cast<int16_t*>(d_side + L.off_tree), reinterpret_cast<uint32_t*>(d_side + L.off_meta));
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
 // chunk bit counts -> offsets -> bit packing, with the tables already in the side buffer
 static int huff_pack(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, const b200_huff_layout& L, uint32_t* d_words,
                      uint64_t words_capacity, uint8_t* d_side, uint64_t* h_total_words, uint32_t* h_worst_status) {

@@ -247,3 +247,36 @@ void decompress(StateData* state_data, const char* input_filename) {
     fclose(f);
     free(out_name); free(out); free(off); free(tokens);
 }
+
+/* ---- the completed pipeline the reference sketches (deflate/lz77.c:279 "TODO: Build huffman tree and encode
+ * compressed buffer"): <name>.dfl = ONE self-describing stream (b200comp.h "containers": frequencies[286] of every
+ * block, token sizes, decode index, Huffman-coded words). Nothing else is needed to decode it. */
+uint64_t compress_entropy(const char* input_filename, const char* output_filename) {
+    b200_ctx* ctx = shim_ctx();
+    uint64_t size = 0, total = 0;
+    char* in = slurp(input_filename, &size);
+    if (!in) DIE("Error: could not open file %s\n", input_filename);
+    const uint64_t cap = b200_deflate_container_max_bytes(size, BUFFER_SIZE);
+    void* out = malloc(cap);
+    SHIM_CHECK(b200_deflate_compress_container_host(ctx, (const uint8_t*)in, size, BUFFER_SIZE, out, cap, &total));
+    FILE* f = fopen(output_filename, "wb");
+    if (!f || fwrite(out, 1, total, f) != total) DIE("Error: could not write file %s\n", output_filename);
+    fclose(f);
+    free(out); free(in);
+    return total;
+}
+
+uint64_t decompress_entropy(const char* input_filename, const char* output_filename) {
+    b200_ctx* ctx = shim_ctx();
+    uint64_t bytes = 0, n = 0, bs = 0; uint32_t codec = 0;
+    char* c = slurp(input_filename, &bytes);
+    if (!c) DIE("Error: could not open file %s\n", input_filename);
+    SHIM_CHECK(b200_container_info(c, bytes, &codec, &n, &bs));
+    uint8_t* out = (uint8_t*)malloc(n + 64);
+    SHIM_CHECK(b200_deflate_decompress_container_host(ctx, c, bytes, out, n, &n));
+    FILE* f = fopen(output_filename, "wb");
+    if (!f || fwrite(out, 1, n, f) != n) DIE("Error: could not write file %s\n", output_filename);
+    fclose(f);
+    free(out); free(c);
+    return n;
+}

@@ -115,14 +115,39 @@ void print_codes(uint32_t* codes, uint8_t* code_lengths) {
 
 /* ---- GPU-backed entry points ------------------------------------------------------------ */
 
-/* the bit-offset index of the last stream this library produced (not part of the words the
- * reference compares): lets huffman_decompress use the parallel decoder */
-static struct { const uint32_t* buffer; uint64_t n, total_words, total_bits; uint8_t* side; uint64_t side_bytes; } g_last;
+/* The decode index (bit offsets of the 256-symbol sub-chunks) is not part of the words the reference compares and
+ * huffman_decompress(writer, root, ...) has no parameter that could carry it, so the library keeps it for every
+ * stream it produced, keyed by the words pointer and the exact bit count, behind a mutex: any number of live
+ * streams, from any thread. A stream that is not in the registry (e.g. words written by the reference itself) is
+ * decoded without an index. Streams that leave the process go through the container calls below instead. */
+#include <pthread.h>
+typedef struct Stream { struct Stream* next; const uint32_t* buffer; uint64_t n, total_words, total_bits; uint8_t* side; uint64_t side_bytes; } Stream;
+static Stream* g_streams = NULL;
+static pthread_mutex_t g_streams_mu = PTHREAD_MUTEX_INITIALIZER;
 
 static void remember(const uint32_t* buffer, uint64_t n, uint64_t total_words, uint64_t total_bits, uint8_t* side, uint64_t side_bytes) {
-    free(g_last.side);
-    g_last.buffer = buffer; g_last.n = n; g_last.total_words = total_words; g_last.total_bits = total_bits;
-    g_last.side = side; g_last.side_bytes = side_bytes;
+    pthread_mutex_lock(&g_streams_mu);
+    Stream* e = g_streams;
+    while (e && e->buffer != buffer) e = e->next;       /* the same words buffer written again replaces its entry */
+    if (!e) { e = (Stream*)calloc(1, sizeof(Stream)); e->next = g_streams; g_streams = e; }
+    free(e->side);
+    e->buffer = buffer; e->n = n; e->total_words = total_words; e->total_bits = total_bits; e->side = side; e->side_bytes = side_bytes;
+    pthread_mutex_unlock(&g_streams_mu);
+}
+
+/* copy of the entry for (buffer, bits), side index included, so that the caller works outside the lock */
+static bool lookup(const uint32_t* buffer, uint64_t total_bits, Stream* out) {
+    bool hit = false;
+    pthread_mutex_lock(&g_streams_mu);
+    for (Stream* e = g_streams; e; e = e->next) if (e->buffer == buffer && e->total_bits == total_bits) {
+        *out = *e;
+        out->side = (uint8_t*)malloc(e->side_bytes);
+        memcpy(out->side, e->side, e->side_bytes);
+        hit = true;
+        break;
+    }
+    pthread_mutex_unlock(&g_streams_mu);
+    return hit;
 }
 
 /* host Node tree from the GPU's node array: i16 child[511][2], leaf = {-1, symbol} */
@@ -249,18 +274,19 @@ void huffman_decompress(BitWriter* writer, Node* root, char* output, uint64_t* o
     b200_ctx* ctx = shim_ctx();
     const uint64_t capacity = *output_size;
     memset(output, 0, capacity);   /* huffman.c:341 */
-    if (g_last.buffer && writer->buffer == g_last.buffer &&
-        writer->word_idx * 32 + writer->bit_idx == g_last.total_bits) {
-        const uint64_t n = g_last.n;
+    Stream st;
+    if (lookup(writer->buffer, writer->word_idx * 32 + writer->bit_idx, &st)) {
+        const uint64_t n = st.n;
         if (capacity >= n) {
-            SHIM_CHECK(b200_huffman_decompress_host(ctx, writer->buffer, g_last.total_words, g_last.side, g_last.side_bytes, n, 0, (uint8_t*)output));
+            SHIM_CHECK(b200_huffman_decompress_host(ctx, writer->buffer, st.total_words, st.side, st.side_bytes, n, 0, (uint8_t*)output));
         } else {
             uint8_t* tmp = (uint8_t*)malloc(n);
-            SHIM_CHECK(b200_huffman_decompress_host(ctx, writer->buffer, g_last.total_words, g_last.side, g_last.side_bytes, n, 0, tmp));
+            SHIM_CHECK(b200_huffman_decompress_host(ctx, writer->buffer, st.total_words, st.side, st.side_bytes, n, 0, tmp));
             memcpy(output, tmp, capacity);
             free(tmp);
         }
-        const uint64_t extra = trailing_symbols(writer, root, g_last.total_bits, g_last.total_words);
+        free(st.side);
+        const uint64_t extra = trailing_symbols(writer, root, st.total_bits, st.total_words);
         if (extra && capacity > n) {   /* the symbols the reference decodes out of the pad bits */
             const Node* v = root;
             while (v->left && v->right) v = v->left;   /* pad bits are zero */
@@ -280,4 +306,45 @@ void huffman_decompress(BitWriter* writer, Node* root, char* output, uint64_t* o
 
 void huffman_decompress_lookup_table(BitWriter* writer, Node* root, char* output, uint64_t* output_size) {
     huffman_decompress(writer, root, output, output_size);
+}
+
+/* ---- file-level helpers on the self-describing container (include/b200comp.h): what a driver that wants to keep
+ * the compressed data writes and reads. Returns the container bytes / the decoded bytes. */
+static char* slurp_file(const char* path, uint64_t* size) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { printf("ERROR: cannot open %s\n", path); exit(1); }
+    fseek(f, 0, SEEK_END); *size = (uint64_t)ftell(f); fseek(f, 0, SEEK_SET);
+    char* p = (char*)malloc(*size + 64);
+    if (fread(p, 1, *size, f) != *size) { printf("ERROR: short read on %s\n", path); exit(1); }
+    fclose(f);
+    return p;
+}
+
+uint64_t huffman_compress_file(const char* input_filename, const char* output_filename, uint64_t block_size) {
+    b200_ctx* ctx = shim_ctx();
+    uint64_t size = 0, total = 0;
+    char* in = slurp_file(input_filename, &size);
+    if (size == 0) { printf("ERROR: Queue is empty\n"); exit(1); }
+    const uint64_t cap = b200_huffman_container_max_bytes(size, block_size);
+    void* out = malloc(cap);
+    SHIM_CHECK(b200_huffman_compress_container_host(ctx, (const uint8_t*)in, size, block_size, out, cap, &total));
+    FILE* f = fopen(output_filename, "wb");
+    if (!f || fwrite(out, 1, total, f) != total) { printf("ERROR: cannot write %s\n", output_filename); exit(1); }
+    fclose(f);
+    free(out); free(in);
+    return total;
+}
+
+uint64_t huffman_decompress_file(const char* input_filename, const char* output_filename) {
+    b200_ctx* ctx = shim_ctx();
+    uint64_t bytes = 0, n = 0, bs = 0; uint32_t codec = 0;
+    char* c = slurp_file(input_filename, &bytes);
+    SHIM_CHECK(b200_container_info(c, bytes, &codec, &n, &bs));
+    uint8_t* out = (uint8_t*)malloc(n + 64);
+    SHIM_CHECK(b200_huffman_decompress_container_host(ctx, c, bytes, out, n, &n));
+    FILE* f = fopen(output_filename, "wb");
+    if (!f || fwrite(out, 1, n, f) != n) { printf("ERROR: cannot write %s\n", output_filename); exit(1); }
+    fclose(f);
+    free(out); free(c);
+    return n;
 }

@@ -99,6 +99,11 @@ uint64_t deflate_compress_buffer(const char* in, uint64_t size, uint64_t block_s
 void     deflate_decompress_buffer(const char* tokens, uint64_t token_bytes, const uint64_t* block_off,
                                    uint64_t size, uint64_t block_size, char* out);
 
+/* Extension: the pipeline with the entropy stage the reference leaves as a TODO (deflate/lz77.c:279), file to
+ * file through ONE self-describing container (b200comp.h "containers"). Returns the bytes written. */
+uint64_t compress_entropy(const char* input_filename, const char* output_filename);
+uint64_t decompress_entropy(const char* input_filename, const char* output_filename);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,8 +18,9 @@
  *    (n + the symbols decoded out of the pad bits) but never writes past
  *    the capacity passed in *output_size.
  *  - a stream produced by this library in the same process is decoded by the parallel
- *    table-lookup decoder (the library keeps the bit-offset index of its last stream);
- *    any other stream is decoded by one GPU thread walking it like the reference.
+ *    table-lookup decoder (the library keeps the bit-offset index of every stream it produced,
+ *    keyed by words pointer + bit count, mutex protected); any other stream is decoded by one GPU
+ *    thread walking it like the reference. Streams that leave the process use the container calls.
  */
 #ifndef B200_HUFFMAN_H
 #define B200_HUFFMAN_H
@@ -77,6 +78,12 @@ void  huffman_decompress(BitWriter* writer, Node* root, char* output,
  * table-lookup decoder with the contract of huffman_decompress */
 void  huffman_decompress_lookup_table(BitWriter* writer, Node* root, char* output,
                                       uint64_t* output_size);
+
+/* Extension (not in the reference, which never writes its stream anywhere): file in, self-describing container out
+ * (b200comp.h "containers": tables + decode index + words in ONE stream), and back, in any process.
+ * block_size 0 = one table for the whole file (what huffman_compress does), else a multiple of 4096. */
+uint64_t huffman_compress_file(const char* input_filename, const char* output_filename, uint64_t block_size);
+uint64_t huffman_decompress_file(const char* input_filename, const char* output_filename);
 
 #ifdef __cplusplus
 }

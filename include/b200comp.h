@@ -295,6 +295,29 @@ int b200_fse_normalize_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint
 int b200_fse_tables_host(b200_ctx* ctx, const uint32_t* h_freq, const uint16_t* h_norm_in,
                          uint16_t* h_norm_out, uint32_t* h_tt_out);
 
+/* ---- self-describing containers (csrc/container.cu documents the layout) ----------
+ * ONE buffer = header {magic "B200CONT", version, codec, n, block_size, ...} + serialized code tables (the
+ * histogram of every table scope: the decoder replays the reference's heap on it) + per-chunk bit counts and
+ * the parallel-decode index + the payload words (bit-exact with the non-container calls). A decoder needs
+ * nothing else; model: the Zig Huffman's tree dump + size header, zig_huffman/src/main.zig:11-18,155-200,513-530.
+ * codec 1 = Huffman (algorithms/huffman), codec 2 = deflate with the entropy stage (algorithms/deflate). */
+#define B200_CODEC_HUFFMAN 1u
+#define B200_CODEC_DEFLATE 2u
+uint64_t b200_huffman_container_max_bytes(uint64_t n, uint64_t block_size);
+uint64_t b200_deflate_container_max_bytes(uint64_t n, uint64_t block_size);
+int b200_container_info(const void* h_container, uint64_t bytes, uint32_t* codec, uint64_t* n, uint64_t* block_size);
+int b200_huffman_compress_container_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
+                                         void* h_out, uint64_t out_capacity, uint64_t* h_total_bytes);
+int b200_huffman_decompress_container_host(b200_ctx* ctx, const void* h_container, uint64_t bytes,
+                                           uint8_t* h_out, uint64_t out_capacity, uint64_t* h_n);
+int b200_deflate_compress_container_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
+                                         void* h_out, uint64_t out_capacity, uint64_t* h_total_bytes);
+int b200_deflate_decompress_container_host(b200_ctx* ctx, const void* h_container, uint64_t bytes,
+                                           uint8_t* h_out, uint64_t out_capacity, uint64_t* h_n);
+/* decoder side: rebuild codes / lengths / trees from the histograms already in d_side */
+int b200_huffman_tables_from_freq_dev(b200_ctx* ctx, uint8_t* d_side, uint64_t side_bytes, uint64_t n, uint64_t block_size);
+int b200_dfl_tables_from_freq_dev(b200_ctx* ctx, uint8_t* d_side, uint64_t side_bytes, uint64_t n, uint64_t block_size);
+
 #ifdef __cplusplus
 }
 #endif
