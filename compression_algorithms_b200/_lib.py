@@ -94,6 +94,10 @@ def core():
             getattr(lib, name).argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, u64p]
         for name in ("b200_huffman_decompress_container_host", "b200_deflate_decompress_container_host"):
             getattr(lib, name).argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p]
+        lib.b200_zig_huffman_max_bytes.restype = C.c_uint64
+        lib.b200_zig_huffman_max_bytes.argtypes = [C.c_uint64]
+        lib.b200_zig_huffman_compress_host.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p]
+        lib.b200_zig_huffman_decompress_host.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p]
         if hasattr(lib, "b200_fse_layout_for"):
             lib.b200_fse_layout_for.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(FseLayout)]
             lib.b200_fse_max_words.restype = C.c_uint64

@@ -13,7 +13,11 @@
 // NSYM symbols per table (256: algorithms/huffman; 286: NUM_CODES of algorithms/deflate/huffman.h:6),
 // rows of STRIDE entries in freq/codes/lens, 2*NSYM-1 nodes per tree. SINGLE_OK: a table with one
 // distinct symbol gets the 1-bit code 0 (an inner root over that leaf) instead of status 1.
-template <int NSYM, int STRIDE, bool SINGLE_OK>
+// ZIGPQ: the sift-down of Zig's std.PriorityQueue instead of the reference C heap's (algorithms/huffman/zig_huffman/
+// src/main.zig:133-156 builds its tree with it): the lesser child is the right one only when strictly smaller than the
+// left, and the moved element stops only when STRICTLY smaller than that child (so it keeps sinking through equal
+// frequencies, where heapify_down of huffman.c:112-131 stops). Sift-up is the same strict '<' in both.
+template <int NSYM, int STRIDE, bool SINGLE_OK, bool ZIGPQ = false>
 static __global__ void __launch_bounds__(32) huff_build_kernel(const uint32_t* __restrict__ freq, uint32_t* __restrict__ codes,
                                                        uint8_t* __restrict__ lens, int16_t* __restrict__ tree,
                                                        uint32_t* __restrict__ meta) {
@@ -62,11 +66,17 @@ static __global__ void __launch_bounds__(32) huff_build_kernel(const uint32_t* _
                     const int l = 2 * idx + 1, r = l + 1;
                     if (l >= size) break;
                     const uint64_t yl = hq[l], yr = r < size ? hq[r] : 0xFFFFFFFFFFFFFFFFull;
-                    // smallest of (x, left, right) with the reference's order of comparisons (strict <, left first)
                     int sm = idx; uint64_t ys = x;
-                    if (HQ_F(yl) < HQ_F(ys)) { sm = l; ys = yl; }
-                    if (r < size && HQ_F(yr) < HQ_F(ys)) { sm = r; ys = yr; }
-                    if (sm == idx) break;
+                    if (ZIGPQ) {
+                        sm = l; ys = yl;
+                        if (r < size && HQ_F(yr) < HQ_F(yl)) { sm = r; ys = yr; }
+                        if (HQ_F(x) < HQ_F(ys)) break;
+                    } else {
+                        // smallest of (x, left, right) with the reference's order of comparisons (strict <, left first)
+                        if (HQ_F(yl) < HQ_F(ys)) { sm = l; ys = yl; }
+                        if (r < size && HQ_F(yr) < HQ_F(ys)) { sm = r; ys = yr; }
+                        if (sm == idx) break;
+                    }
                     hq[idx] = ys;
                     idx = sm;
                 }

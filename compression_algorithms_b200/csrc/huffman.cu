@@ -9,6 +9,7 @@
 // table scope ("block") starting on a word boundary; a side buffer (b200_huff_layout)
 // with per-block tables and the chunk/sub-chunk bit index used for parallel decode.
 #include <algorithm>
+#include <vector>
 #include "common.cuh"
 #include "hist.cuh"
 #include "huff_shared.cuh"
@@ -593,5 +594,247 @@ extern "C" int b200_huffman_decode_serial_dev(b200_ctx* ctx, const uint32_t* d_w
     CUDA_TRY(cudaMemcpyAsync(pin, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (h_count) *h_count = pin[0];
+    return B200_OK;
+}
+
+// ================================================================================================================
+// Zig-Huffman-compatible chunked mode: the file format of algorithms/huffman/zig_huffman/src/main.zig.
+//   per 4 MiB chunk (BUFFER_SIZE, main.zig:5):
+//     tree, pre-order: value u8 + freq u32 LE per node, then the left and the right subtree; a missing child is the
+//       i32 -1 (main.zig:155-176). The tree is built by std.PriorityQueue over the histogram of the WHOLE 4 MiB read
+//       buffer (main.zig:109-121 counts BUFFER_SIZE bytes whatever was read: a short last chunk also counts the stale
+//       bytes the previous chunk left behind it; a first short chunk counts the allocator's zero pages).
+//     CompressedSize u32 = last_block | bytes << 1 (main.zig:11-18,513-520), last_block = the read was short
+//     payload: codes MSB-first into BYTES (main.zig:316-338), whole bytes only -- the trailing partial byte is dropped
+//       (main.zig:523 writes compression_buffer[0..idx]), so the last symbol(s) of a chunk can be lost: the format is
+//       reproduced as it is, bug included.
+//   a file whose size is a multiple of 4 MiB ends with one more chunk of zero bytes (the read that finds the end).
+// PARITY UNPINNED: no Zig toolchain here; the heap order is std.PriorityQueue's as restated in huff_shared.cuh /
+// oracle/port/zig_huffman_port.c. The GPU must match that port byte for byte.
+namespace {
+constexpr uint64_t ZIG_CHUNK = 1ull << 22;
+
+__global__ void __launch_bounds__(256) zig_bswap_kernel(uint32_t* __restrict__ w, uint64_t nwords) {
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * 256) w[i] = __byte_perm(w[i], 0, 0x0123);
+}
+
+// one thread per chunk walks its bytes like main.zig:413-441: a symbol starts while byte_idx < size; bits past the
+// payload read as zero (the reference reads whatever its buffer holds there)
+__global__ void __launch_bounds__(32) zig_decode_kernel(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ pay_off,
+                                                        const uint32_t* __restrict__ pay_size, const int16_t* __restrict__ trees,
+                                                        uint8_t* __restrict__ out, uint32_t* __restrict__ counts) {
+    __shared__ int16_t kid[511][2];
+    const uint32_t k = blockIdx.x;
+    for (int i = threadIdx.x; i < 511 * 2; i += 32) (&kid[0][0])[i] = trees[(uint64_t)k * 511 * 2 + i];
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const uint8_t* p = payload + pay_off[k];
+    const uint32_t size = pay_size[k];
+    uint8_t* o = out + (uint64_t)k * ZIG_CHUNK;
+    uint32_t byte_idx = 0, bit_idx = 0, cnt = 0;
+    uint32_t cur = size ? p[0] : 0;
+    while (byte_idx < size) {
+        int v = 0;
+        while (kid[v][0] >= 0) {   // inner node: both children present
+            const uint32_t bit = (cur >> (7 - bit_idx)) & 1u;
+            v = kid[v][bit];
+            if (++bit_idx == 8) { bit_idx = 0; ++byte_idx; cur = byte_idx < size ? p[byte_idx] : 0u; }
+        }
+        if (cnt < ZIG_CHUNK) o[cnt] = (uint8_t)kid[v][1];
+        ++cnt;
+        if (kid[0][0] < 0) break;   // a root without children consumes no bits: the reference would spin
+    }
+    counts[k] = cnt;
+}
+}  // namespace
+
+extern "C" uint64_t b200_zig_huffman_max_bytes(uint64_t n) {
+    const uint64_t nchunks = n / ZIG_CHUNK + 1;
+    return n + n / 4 + nchunks * (511 * 5 + 512 * 4 + 4 + 64) + 64;
+}
+
+// serialise the tree of one chunk pre-order; kids = i16[511][2] (leaf = {-1, symbol}); returns bytes written
+static uint64_t zig_put_tree(const int16_t* kids, const uint32_t* freq, int v, uint8_t* o, uint32_t* f_out) {
+    uint64_t w = 0;
+    if (kids[2 * v] < 0) {
+        const uint32_t f = freq[kids[2 * v + 1]];
+        o[w++] = (uint8_t)kids[2 * v + 1]; memcpy(o + w, &f, 4); w += 4;
+        memset(o + w, 0xFF, 8); w += 8;   // two missing children
+        *f_out = f;
+        return w;
+    }
+    uint8_t* head = o; w = 5;
+    uint32_t fl = 0, fr = 0;
+    w += zig_put_tree(kids, freq, kids[2 * v], o + w, &fl);
+    w += zig_put_tree(kids, freq, kids[2 * v + 1], o + w, &fr);
+    const uint32_t f = fl + fr;
+    head[0] = 0; memcpy(head + 1, &f, 4);
+    *f_out = f;
+    return w;
+}
+
+extern "C" int b200_zig_huffman_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint8_t* h_out, uint64_t out_capacity,
+                                              uint64_t* h_total_bytes) {
+    const uint64_t nz = n / ZIG_CHUNK + 1;                     // chunks the reference writes (an exact multiple ends with an empty one)
+    const uint64_t n_aug = nz * ZIG_CHUNK;
+    const uint64_t nb = n ? (n + ZIG_CHUNK - 1) / ZIG_CHUNK : 0;   // chunks that carry data
+    b200_huff_layout LA, LB;
+    B200_TRY(b200_huffman_layout(n_aug, ZIG_CHUNK, &LA));
+    uint8_t *d_aug, *d_sideA, *d_sideB = nullptr; uint32_t* d_words = nullptr;
+    B200_TRY(b200_scratch(ctx, 8, n_aug + 64, reinterpret_cast<void**>(&d_aug)));
+    B200_TRY(b200_scratch(ctx, 12, LA.bytes, reinterpret_cast<void**>(&d_sideA)));
+    // the read buffer as the reference sees it chunk by chunk: the data, and behind a short read what the previous
+    // chunk left there (zero pages before the first chunk)
+    if (n) CUDA_TRY(cudaMemcpyAsync(d_aug, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        const uint64_t last = nz - 1, len_last = n - last * ZIG_CHUNK;
+        if (last == 0) CUDA_TRY(cudaMemsetAsync(d_aug + len_last, 0, ZIG_CHUNK - len_last, ctx->stream));
+        else CUDA_TRY(cudaMemcpyAsync(d_aug + last * ZIG_CHUNK + len_last, d_aug + (last - 1) * ZIG_CHUNK + len_last, ZIG_CHUNK - len_last,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CUDA_TRY(cudaMemsetAsync(d_sideA, 0, LA.off_tree, ctx->stream));
+    const uint32_t tpb = (uint32_t)((LA.chunks_per_block + TILE_CHUNKS - 1) / TILE_CHUNKS);
+    byte_hist_kernel<<<(unsigned)(LA.nblocks * tpb), 256, 0, ctx->stream>>>(d_aug, n_aug, ZIG_CHUNK, tpb, reinterpret_cast<uint32_t*>(d_sideA + LA.off_freq));
+    huff_build_kernel<256, 256, false, true><<<(unsigned)LA.nblocks, 32, 0, ctx->stream>>>(
+        reinterpret_cast<const uint32_t*>(d_sideA + LA.off_freq), reinterpret_cast<uint32_t*>(d_sideA + LA.off_codes),
+        d_sideA + LA.off_lens, reinterpret_cast<int16_t*>(d_sideA + LA.off_tree), reinterpret_cast<uint32_t*>(d_sideA + LA.off_meta));
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    // trees and histograms to the host; inputs the reference cannot handle are refused before anything is packed
+    std::vector<uint8_t> sideA(LA.off_block_bits);
+    CUDA_TRY(cudaMemcpyAsync(sideA.data(), d_sideA, LA.off_block_bits, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const uint32_t* meta = reinterpret_cast<const uint32_t*>(sideA.data() + LA.off_meta);
+    for (uint64_t k = 0; k < nz; ++k) {
+        if (meta[k * 4] == 1) { B200_SET_ERR("zig huffman: chunk %llu has a single symbol (the reference shifts a u32 by 32, main.zig:222)", (unsigned long long)k); return B200_ERR_DOMAIN; }
+        if (meta[k * 4 + 3] > 25) { B200_SET_ERR("zig huffman: chunk %llu needs a %u-bit code; the reference's byte-offset shift loses bits beyond 25 (main.zig:320)", (unsigned long long)k, meta[k * 4 + 3]); return B200_ERR_DOMAIN; }
+    }
+    uint64_t total_words = 0;
+    std::vector<uint64_t> bbits(nb + 1), bword(nb + 2);
+    if (nb) {
+        B200_TRY(b200_huffman_layout(n, ZIG_CHUNK, &LB));
+        // a table that also counts stale bytes is not the data's own, so the 8-bit bound of a self-built table does not hold
+        const uint64_t capw = n / 2 + nb + 8;   // 16 bits per symbol; beyond that the call reports B200_ERR_CAPACITY
+        B200_TRY(b200_scratch(ctx, 9, LB.bytes, reinterpret_cast<void**>(&d_sideB)));
+        B200_TRY(b200_scratch(ctx, 11, capw * 4, reinterpret_cast<void**>(&d_words)));
+        CUDA_TRY(cudaMemsetAsync(d_sideB, 0, LB.off_tree, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_sideB + LB.off_freq, d_sideA + LA.off_freq, nb * 1024, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_sideB + LB.off_codes, d_sideA + LA.off_codes, nb * 1024, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_sideB + LB.off_lens, d_sideA + LA.off_lens, nb * 256, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_sideB + LB.off_tree, d_sideA + LA.off_tree, nb * 511 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_sideB + LB.off_meta, d_sideA + LA.off_meta, nb * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+        uint32_t worst = 0;
+        B200_TRY(huff_pack(ctx, d_aug, n, LB, d_words, capw, d_sideB, &total_words, &worst));
+        if (total_words) {
+            zig_bswap_kernel<<<(unsigned)std::min<uint64_t>((total_words + 255) / 256, (uint64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(d_words, total_words);
+            ctx->launches += 1;
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaMemcpyAsync(bbits.data(), d_sideB + LB.off_block_bits, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(bword.data(), d_sideB + LB.off_block_word, (nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    uint64_t o = 0;
+    for (uint64_t k = 0; k < nz; ++k) {
+        if (o + 511 * 5 + 512 * 4 + 4 > out_capacity) { B200_SET_ERR("zig huffman: output buffer too small"); return B200_ERR_CAPACITY; }
+        uint32_t froot = 0;
+        o += zig_put_tree(reinterpret_cast<const int16_t*>(sideA.data() + LA.off_tree) + k * 511 * 2,
+                          reinterpret_cast<const uint32_t*>(sideA.data() + LA.off_freq) + k * 256, (int)meta[k * 4 + 2], h_out + o, &froot);
+        const uint64_t len_k = k < nb ? (k + 1 < nb || n % ZIG_CHUNK == 0 ? ZIG_CHUNK : n % ZIG_CHUNK) : 0;
+        const uint64_t pay = k < nb ? bbits[k] / 8 : 0;
+        const uint32_t hdr = (uint32_t)(len_k < ZIG_CHUNK ? 1u : 0u) | (uint32_t)(pay << 1);
+        memcpy(h_out + o, &hdr, 4); o += 4;
+        if (pay) {
+            if (o + pay > out_capacity) { B200_SET_ERR("zig huffman: output buffer too small"); return B200_ERR_CAPACITY; }
+            CUDA_TRY(cudaMemcpyAsync(h_out + o, reinterpret_cast<const uint8_t*>(d_words + bword[k]), pay, cudaMemcpyDeviceToHost, ctx->stream));
+            o += pay;
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_total_bytes) *h_total_bytes = o;
+    return B200_OK;
+}
+
+extern "C" int b200_zig_huffman_decompress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t bytes, uint8_t* h_out, uint64_t out_capacity,
+                                                uint64_t* h_n) {
+    // parse: trees + chunk table on the host
+    std::vector<int16_t> trees;       // [chunk][511][2]
+    std::vector<uint64_t> pay_off; std::vector<uint32_t> pay_size;
+    uint64_t i = 0;
+    bool done = false;
+    while (!done) {
+        const size_t base = trees.size();
+        trees.resize(base + 511 * 2, -1);
+        int16_t* kid = trees.data() + base;
+        // iterative pre-order read (main.zig:178-200): stack of (node, which child comes next)
+        int nn = 0, sp = 0; int stack[1024]; int side[1024];
+        auto read_node = [&](int* out_v) -> int {
+            if (i + 4 > bytes) return -1;
+            int32_t m; memcpy(&m, h_in + i, 4);
+            if (m == -1) { i += 4; *out_v = -1; return 0; }
+            if (i + 5 > bytes || nn >= 511) return -1;
+            const int v = nn++;
+            kid[2 * v] = -1; kid[2 * v + 1] = (int16_t)h_in[i];   // leaf until a child shows up: {-1, symbol}
+            i += 5;
+            *out_v = v;
+            return 0;
+        };
+        int root;
+        if (read_node(&root) || root < 0) { B200_SET_ERR("zig huffman: corrupt tree at byte %llu", (unsigned long long)i); return B200_ERR_FORMAT; }
+        stack[sp] = root; side[sp] = 0; ++sp;
+        while (sp) {
+            const int v = stack[sp - 1], s = side[sp - 1];
+            if (s == 2) { --sp; continue; }
+            side[sp - 1] = s + 1;
+            int c;
+            if (read_node(&c)) { B200_SET_ERR("zig huffman: corrupt tree at byte %llu", (unsigned long long)i); return B200_ERR_FORMAT; }
+            if (c >= 0) {
+                if (s == 0) { const int16_t sym = kid[2 * v + 1]; (void)sym; kid[2 * v] = (int16_t)c; kid[2 * v + 1] = -2; }   // becomes an inner node
+                else {
+                    if (kid[2 * v] < 0) { B200_SET_ERR("zig huffman: a node with one child at byte %llu", (unsigned long long)i); return B200_ERR_FORMAT; }
+                    kid[2 * v + 1] = (int16_t)c;
+                }
+                if (sp >= 1023) { B200_SET_ERR("zig huffman: tree too deep"); return B200_ERR_FORMAT; }
+                stack[sp] = c; side[sp] = 0; ++sp;
+            } else if (s == 1 && kid[2 * v] >= 0) { B200_SET_ERR("zig huffman: a node with one child at byte %llu", (unsigned long long)i); return B200_ERR_FORMAT; }
+        }
+        for (int v = 0; v < nn; ++v) if (kid[2 * v] >= 0 && kid[2 * v + 1] < 0) { B200_SET_ERR("zig huffman: a node with one child"); return B200_ERR_FORMAT; }
+        if (i + 4 > bytes) { B200_SET_ERR("zig huffman: truncated before a chunk header"); return B200_ERR_FORMAT; }
+        uint32_t hdr; memcpy(&hdr, h_in + i, 4); i += 4;
+        done = (hdr & 1u) != 0;
+        const uint32_t size = hdr >> 1;
+        if (i + size > bytes) { B200_SET_ERR("zig huffman: truncated payload"); return B200_ERR_FORMAT; }
+        pay_off.push_back(i); pay_size.push_back(size);
+        i += size;
+    }
+    const uint64_t nz = pay_off.size();
+    uint8_t *d_pay, *d_out, *d_tab;
+    B200_TRY(b200_scratch(ctx, 11, bytes + 64, reinterpret_cast<void**>(&d_pay)));
+    B200_TRY(b200_scratch(ctx, 8, nz * ZIG_CHUNK + 64, reinterpret_cast<void**>(&d_out)));
+    const uint64_t tab_bytes = nz * (511 * 4 + 8 + 4 + 4) + 64;
+    B200_TRY(b200_scratch(ctx, 12, tab_bytes, reinterpret_cast<void**>(&d_tab)));
+    int16_t* d_trees = reinterpret_cast<int16_t*>(d_tab);
+    uint64_t* d_off = reinterpret_cast<uint64_t*>(d_tab + ((nz * 511 * 4 + 7) & ~7ull));
+    uint32_t* d_size = reinterpret_cast<uint32_t*>(d_off + nz);
+    uint32_t* d_cnt = d_size + nz;
+    CUDA_TRY(cudaMemcpyAsync(d_pay, h_in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_trees, trees.data(), nz * 511 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_off, pay_off.data(), nz * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_size, pay_size.data(), nz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    zig_decode_kernel<<<(unsigned)nz, 32, 0, ctx->stream>>>(d_pay, d_off, d_size, d_trees, d_out, d_cnt);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    std::vector<uint32_t> cnt(nz);
+    CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, nz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint64_t o = 0;
+    for (uint64_t k = 0; k < nz; ++k) {
+        const uint64_t c = cnt[k] < ZIG_CHUNK ? cnt[k] : ZIG_CHUNK;
+        if (o + c > out_capacity) { B200_SET_ERR("zig huffman: output needs more than %llu bytes", (unsigned long long)out_capacity); return B200_ERR_CAPACITY; }
+        if (c) CUDA_TRY(cudaMemcpyAsync(h_out + o, d_out + k * ZIG_CHUNK, c, cudaMemcpyDeviceToHost, ctx->stream));
+        o += c;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_n) *h_n = o;
     return B200_OK;
 }

@@ -314,6 +314,19 @@ int b200_deflate_compress_container_host(b200_ctx* ctx, const uint8_t* h_in, uin
                                          void* h_out, uint64_t out_capacity, uint64_t* h_total_bytes);
 int b200_deflate_decompress_container_host(b200_ctx* ctx, const void* h_container, uint64_t bytes,
                                            uint8_t* h_out, uint64_t out_capacity, uint64_t* h_n);
+/* ---- Zig-Huffman-compatible chunked mode: the FILE FORMAT of
+ * algorithms/huffman/zig_huffman/src/main.zig -- 4 MiB chunks (:5), per chunk the tree dumped pre-order (value u8 +
+ * freq u32 per node, i32 -1 for a missing child, :155-176), CompressedSize{last_block:1, value:31} (:11-18,513-520)
+ * and the codes packed MSB-first into bytes (:316-338), whole bytes only (the format loses the tail bits of a chunk,
+ * :523; reproduced as it is). The tree comes from std.PriorityQueue over the histogram of the whole read buffer
+ * (:100-153). PARITY UNPINNED (no Zig toolchain here): oracle/port/zig_huffman_port.c is the written spec. */
+uint64_t b200_zig_huffman_max_bytes(uint64_t n);
+int b200_zig_huffman_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint8_t* h_out, uint64_t out_capacity,
+                                   uint64_t* h_total_bytes);
+/* h_out needs 4 MiB per chunk at most; *h_n = bytes the reference's decoder would write */
+int b200_zig_huffman_decompress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t bytes, uint8_t* h_out, uint64_t out_capacity,
+                                     uint64_t* h_n);
+
 /* decoder side: rebuild codes / lengths / trees from the histograms already in d_side */
 int b200_huffman_tables_from_freq_dev(b200_ctx* ctx, uint8_t* d_side, uint64_t side_bytes, uint64_t n, uint64_t block_size);
 int b200_dfl_tables_from_freq_dev(b200_ctx* ctx, uint8_t* d_side, uint64_t side_bytes, uint64_t n, uint64_t block_size);

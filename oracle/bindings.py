@@ -413,6 +413,27 @@ def port_lz77_decompress_blocks(stream, off, block, n, variant, threads=0):
     return out[:n], int(bad)
 
 
+def port_zig_huffman_compress(data):
+    """Zig Huffman file format (parity unpinned) -> bytes, or None where the reference's behaviour is undefined."""
+    d = _as_u8(data)
+    out = np.zeros(d.size + d.size // 4 + 8192 * (d.size // (1 << 22) + 2), dtype=np.uint8)
+    f = _lib("oracle_port").port_zig_huffman_compress
+    f.restype = C.c_uint64
+    n = f(_p(d, _u8p), C.c_uint64(d.size), _p(out, _u8p))
+    return out[:n].copy() if n else None
+
+
+def port_zig_huffman_decompress(stream, max_out):
+    s = _as_u8(stream)
+    out = np.zeros(max_out + 64, dtype=np.uint8)
+    f = _lib("oracle_port").port_zig_huffman_decompress
+    f.restype = C.c_uint64
+    n = f(_p(s, _u8p), C.c_uint64(s.size), _p(out, _u8p), C.c_uint64(out.size))
+    if n == 0xFFFFFFFFFFFFFFFF:
+        raise RuntimeError("zig huffman: corrupt stream")
+    return out[: min(n, out.size)].copy()
+
+
 def port_threads():
     import os
     return os.cpu_count() or 1

@@ -38,3 +38,7 @@ int port_dfl_build(const uint64_t* freq, uint32_t* codes, uint8_t* lens);
 uint64_t port_dfl_encode(const uint8_t* tok, uint64_t nbytes, const uint32_t* codes, const uint8_t* lens, uint32_t* words);
 int port_dfl_decode(const uint32_t* words, uint64_t nwords, const uint32_t* codes, const uint8_t* lens,
                     uint64_t nbytes, uint8_t* tok_out, uint64_t* bits_used);
+
+/* Zig Huffman file format (zig_huffman_port.c) -- parity unpinned */
+uint64_t port_zig_huffman_compress(const uint8_t* in, uint64_t n, uint8_t* out);
+uint64_t port_zig_huffman_decompress(const uint8_t* in, uint64_t bytes, uint8_t* out, uint64_t out_cap);

@@ -268,3 +268,18 @@ def test_deflate_entropy_stage_degenerate(ob):
         assert used == e["bits"] and np.array_equal(back, tok)
         if e["distinct"] == 1:
             assert e["lens"].max() == 1 and e["bits"] >= 1
+
+
+def test_zig_huffman_port_format(ob):
+    """structure of the restated Zig Huffman file (parity unpinned): pre-order tree dump, CompressedSize header with the
+    last-block bit, whole-byte payload; an input of exactly 4 MiB ends with an empty last chunk"""
+    from compression_algorithms_b200 import corpus
+    n = (1 << 22) + 1000
+    data = corpus.generate(n, corpus.ENWIK, 4)
+    c = ob.port_zig_huffman_compress(data)
+    # first node = the root: value 0, freq = the whole 4 MiB read buffer
+    assert c[0] == 0 and int(np.frombuffer(c[1:5].tobytes(), np.uint32)[0]) == 1 << 22
+    dec = ob.port_zig_huffman_decompress(c, 2 << 22)
+    assert abs(int(dec.size) - n) <= 4 and np.array_equal(dec[: (1 << 22) - 8], data[: (1 << 22) - 8])
+    full = ob.port_zig_huffman_compress(corpus.generate(1 << 22, corpus.ENWIK, 4))
+    assert int(np.frombuffer(full[-4:].tobytes(), np.uint32)[0]) == 1          # last header: last_block = 1, 0 bytes
