@@ -94,6 +94,15 @@ def core():
             getattr(lib, name).argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, u64p]
         for name in ("b200_huffman_decompress_container_host", "b200_deflate_decompress_container_host"):
             getattr(lib, name).argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p]
+        lib.b200_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+        lib.b200_multi_destroy.argtypes = [vp]
+        lib.b200_multi_device_count.argtypes = [vp]
+        lib.b200_multi_allgathers.restype = C.c_uint64
+        lib.b200_multi_allgathers.argtypes = [vp]
+        lib.b200_multi_launches.restype = C.c_uint64
+        lib.b200_multi_launches.argtypes = [vp]
+        lib.b200_lz77_compress_multi_host.argtypes = [vp, C.c_int, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp, u64p]
+        lib.b200_lz77_decompress_multi_host.argtypes = [vp, C.c_int, vp, C.c_uint64, vp, vp, C.c_uint64, C.c_uint64, vp]
         lib.b200_zig_huffman_max_bytes.restype = C.c_uint64
         lib.b200_zig_huffman_max_bytes.argtypes = [C.c_uint64]
         lib.b200_zig_huffman_compress_host.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p]

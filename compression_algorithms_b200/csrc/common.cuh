@@ -64,6 +64,9 @@ struct b200_ctx {
 int b200_pipe_init(b200_ctx* ctx);
 
 #define B200_SLOT(ctx, s) ((s) + 20 * (ctx)->bank)
+// every public entry point runs on its context's device, whatever device the calling thread had current
+// (one host thread per GPU in multi.cu; a caller that created contexts on several devices)
+#define B200_ENTER(ctx) do { if (ctx) { int cur_ = -1; if (cudaGetDevice(&cur_) != cudaSuccess || cur_ != (ctx)->device) CUDA_TRY(cudaSetDevice((ctx)->device)); } } while (0)
 int b200_scratch(b200_ctx* ctx, int slot, size_t bytes, void** out);
 int b200_pinned(b200_ctx* ctx, size_t bytes, void** out);
 

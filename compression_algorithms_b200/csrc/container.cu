@@ -78,6 +78,7 @@ extern "C" int b200_container_info(const void* h_container, uint64_t bytes, uint
 // ------------------------------------------------------------------------------------------ Huffman
 extern "C" int b200_huffman_compress_container_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
                                                     void* h_out, uint64_t out_capacity, uint64_t* h_total_bytes) {
+    B200_ENTER(ctx);
     b200_huff_layout L;
     B200_TRY(b200_huffman_layout(n, block_size, &L));
     const uint64_t cap = b200_huffman_max_words(n, block_size);
@@ -107,6 +108,7 @@ extern "C" int b200_huffman_compress_container_host(b200_ctx* ctx, const uint8_t
 
 extern "C" int b200_huffman_decompress_container_host(b200_ctx* ctx, const void* h_container, uint64_t bytes,
                                                       uint8_t* h_out, uint64_t out_capacity, uint64_t* h_n) {
+    B200_ENTER(ctx);
     uint32_t codec; uint64_t n, bs;
     B200_TRY(b200_container_info(h_container, bytes, &codec, &n, &bs));
     if (codec != CODEC_HUFFMAN) { B200_SET_ERR("container: codec %u is not Huffman", codec); return B200_ERR_FORMAT; }
@@ -168,6 +170,7 @@ extern "C" int b200_huffman_decompress_container_host(b200_ctx* ctx, const void*
 // ------------------------------------------------------------------------------------------ deflate
 extern "C" int b200_deflate_compress_container_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
                                                     void* h_out, uint64_t out_capacity, uint64_t* h_total_bytes) {
+    B200_ENTER(ctx);
     if (n == 0) { B200_SET_ERR("deflate container: empty input"); return B200_ERR_DOMAIN; }
     b200_dfl_layout L;
     B200_TRY(b200_dfl_layout_for(n, block_size, &L));
@@ -217,6 +220,7 @@ extern "C" int b200_deflate_compress_container_host(b200_ctx* ctx, const uint8_t
 
 extern "C" int b200_deflate_decompress_container_host(b200_ctx* ctx, const void* h_container, uint64_t bytes,
                                                       uint8_t* h_out, uint64_t out_capacity, uint64_t* h_n) {
+    B200_ENTER(ctx);
     uint32_t codec; uint64_t n, bs;
     B200_TRY(b200_container_info(h_container, bytes, &codec, &n, &bs));
     if (codec != CODEC_DEFLATE) { B200_SET_ERR("container: codec %u is not deflate", codec); return B200_ERR_FORMAT; }

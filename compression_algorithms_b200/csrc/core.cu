@@ -62,6 +62,7 @@ int b200_pipe_init(b200_ctx* ctx) {
 }
 
 extern "C" int b200_ctx_sync(b200_ctx* ctx) {
+    B200_ENTER(ctx);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
@@ -83,6 +84,7 @@ void b200_timed_end(b200_ctx* ctx) {
 }
 
 extern "C" int b200_ctx_set_timing(b200_ctx* ctx, int enable) {
+    B200_ENTER(ctx);
     ctx->timing = enable != 0;
     ctx->ev_used = 0;   // (re)start collecting
     return B200_OK;
@@ -91,6 +93,7 @@ extern "C" int b200_ctx_set_timing(b200_ctx* ctx, int enable) {
 extern "C" int b200_ctx_timing_count(b200_ctx* ctx) { return ctx->ev_used; }
 
 extern "C" int b200_ctx_timing_get(b200_ctx* ctx, int i, int* kind, float* ms) {
+    B200_ENTER(ctx);
     if (i < 0 || i >= ctx->ev_used) { B200_SET_ERR("timing entry %d out of range", i); return B200_ERR_ARG; }
     CUDA_TRY(cudaEventSynchronize(ctx->ev_b[i]));
     CUDA_TRY(cudaEventElapsedTime(ms, ctx->ev_a[i], ctx->ev_b[i]));
@@ -131,11 +134,14 @@ extern "C" int b200_dev_free(void* d_ptr) { CUDA_TRY(cudaFree(d_ptr)); return B2
 extern "C" int b200_host_alloc(void** h_ptr, uint64_t bytes) { CUDA_TRY(cudaMallocHost(h_ptr, bytes ? bytes : 1)); return B200_OK; }
 extern "C" int b200_host_free(void* h_ptr) { CUDA_TRY(cudaFreeHost(h_ptr)); return B200_OK; }
 extern "C" int b200_copy_h2d(b200_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes) {
+    B200_ENTER(ctx);
     CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream)); return B200_OK;
 }
 extern "C" int b200_copy_d2h(b200_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes) {
+    B200_ENTER(ctx);
     CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); return B200_OK;
 }
 extern "C" int b200_memset(b200_ctx* ctx, void* d_dst, int value, uint64_t bytes) {
+    B200_ENTER(ctx);
     CUDA_TRY(cudaMemsetAsync(d_dst, value, bytes, ctx->stream)); return B200_OK;
 }

@@ -407,6 +407,7 @@ extern "C" int b200_dfl_encode_dev(b200_ctx* ctx, const uint8_t* d_tokens, uint6
                                    const uint64_t* d_tok_off, const uint64_t* d_tok_sizes, uint64_t n, uint64_t block_size,
                                    uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
                                    uint64_t* h_total_words, uint32_t* h_worst_status) {
+    B200_ENTER(ctx);
     if (n == 0) { if (h_total_words) *h_total_words = 0; if (h_worst_status) *h_worst_status = 0; return B200_OK; }
     if ((reinterpret_cast<uintptr_t>(d_tokens) & 15) || (reinterpret_cast<uintptr_t>(d_side) & 7)) {
         B200_SET_ERR("deflate entropy stage: d_tokens must be 16-byte and d_side 8-byte aligned"); return B200_ERR_ARG;
@@ -460,6 +461,7 @@ extern "C" int b200_dfl_encode_dev(b200_ctx* ctx, const uint8_t* d_tokens, uint6
 
 // decoder side of a stored stream (container.cu): frequencies[286] of every block -> codes, lengths, trees, meta
 extern "C" int b200_dfl_tables_from_freq_dev(b200_ctx* ctx, uint8_t* d_side, uint64_t side_bytes, uint64_t n, uint64_t block_size) {
+    B200_ENTER(ctx);
     b200_dfl_layout L;
     B200_TRY(b200_dfl_layout_for(n, block_size, &L));
     if (side_bytes < L.bytes) { B200_SET_ERR("deflate entropy stage: side buffer too small"); return B200_ERR_CAPACITY; }
@@ -473,6 +475,7 @@ extern "C" int b200_dfl_tables_from_freq_dev(b200_ctx* ctx, uint8_t* d_side, uin
 
 extern "C" int b200_dfl_decode_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words, const uint8_t* d_side,
                                    uint64_t side_bytes, uint64_t n, uint64_t block_size, uint8_t* d_tokens_out) {
+    B200_ENTER(ctx);
     if (n == 0) return B200_OK;
     b200_dfl_layout L;
     B200_TRY(b200_dfl_layout_for(n, block_size, &L));
@@ -497,6 +500,7 @@ extern "C" int b200_deflate_compress_dev(b200_ctx* ctx, const uint8_t* d_in, uin
                                          uint8_t* d_tokens, uint64_t tokens_capacity, uint64_t* d_tok_sizes, uint64_t* d_tok_off,
                                          uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
                                          uint64_t* h_total_words, uint32_t* h_worst_status) {
+    B200_ENTER(ctx);
     B200_TRY(b200_lz77_encode_dev(ctx, B200_LZ_DEFLATE, d_in, n, block_size, d_tokens, tokens_capacity, d_tok_sizes, d_tok_off, nullptr));
     return b200_dfl_encode_dev(ctx, d_tokens, tokens_capacity, d_tok_off, d_tok_sizes, n, block_size, d_words, words_capacity,
                                d_side, side_bytes, h_total_words, h_worst_status);
@@ -506,6 +510,7 @@ extern "C" int b200_deflate_compress_dev(b200_ctx* ctx, const uint8_t* d_in, uin
 // (d_tokens, scratch of at least the encoder's token bytes) -> the original bytes
 extern "C" int b200_deflate_decompress_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words, const uint8_t* d_side,
                                            uint64_t side_bytes, uint64_t n, uint64_t block_size, uint8_t* d_tokens, uint8_t* d_out) {
+    B200_ENTER(ctx);
     if (n == 0) return B200_OK;
     b200_dfl_layout L;
     B200_TRY(b200_dfl_layout_for(n, block_size, &L));

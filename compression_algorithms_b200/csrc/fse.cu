@@ -337,6 +337,7 @@ static int fse_front(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t bl
 }
 
 extern "C" int b200_fse_normalize_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size, uint8_t* d_side, uint64_t side_bytes) {
+    B200_ENTER(ctx);
     b200_fse_layout L; uint64_t bs;
     return fse_front(ctx, d_in, n, block_size, 1024, d_side, side_bytes, &L, &bs);
 }
@@ -344,6 +345,7 @@ extern "C" int b200_fse_normalize_dev(b200_ctx* ctx, const uint8_t* d_in, uint64
 extern "C" int b200_fse_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size, uint64_t seg_size,
                                    uint64_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
                                    uint64_t* h_total_words) {
+    B200_ENTER(ctx);
     b200_fse_layout L; uint64_t bs;
     B200_TRY(fse_front(ctx, d_in, n, block_size, seg_size, d_side, side_bytes, &L, &bs));
     const uint32_t spb = (uint32_t)L.segs_per_block;
@@ -377,6 +379,7 @@ extern "C" int b200_fse_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t 
 
 extern "C" int b200_fse_decode_dev(b200_ctx* ctx, const uint64_t* d_words, const uint8_t* d_side, uint64_t side_bytes,
                                    uint64_t n, uint64_t block_size, uint64_t seg_size, uint8_t* d_out, uint32_t* h_bad_segments) {
+    B200_ENTER(ctx);
     if (n == 0) { if (h_bad_segments) *h_bad_segments = 0; return B200_OK; }
     b200_fse_layout L; uint64_t bs;
     B200_TRY(b200_fse_layout_for(n, block_size, seg_size, &L));
@@ -408,6 +411,7 @@ extern "C" int b200_fse_decode_dev(b200_ctx* ctx, const uint64_t* d_words, const
 // counts, seg_word from seg_bits. d_side holds norm and seg_bits already (layout L).
 extern "C" int b200_fse_rebuild_index_dev(b200_ctx* ctx, uint64_t n, uint64_t block_size, uint64_t seg_size,
                                           uint8_t* d_side, uint64_t side_bytes) {
+    B200_ENTER(ctx);
     b200_fse_layout L;
     B200_TRY(b200_fse_layout_for(n, block_size, seg_size, &L));
     if (side_bytes < L.bytes) { B200_SET_ERR("fse: side buffer too small"); return B200_ERR_CAPACITY; }
@@ -426,6 +430,7 @@ extern "C" int b200_fse_rebuild_index_dev(b200_ctx* ctx, uint64_t n, uint64_t bl
 // h_freq (raw counts -> normalise, then build) and h_norm_in (already normalised) is given.
 extern "C" int b200_fse_tables_host(b200_ctx* ctx, const uint32_t* h_freq, const uint16_t* h_norm_in,
                                     uint16_t* h_norm_out, uint32_t* h_tt_out) {
+    B200_ENTER(ctx);
     if ((h_freq != nullptr) == (h_norm_in != nullptr)) { B200_SET_ERR("fse: give either counts or normalised counts"); return B200_ERR_ARG; }
     uint8_t* d; uint8_t* pin;
     B200_TRY(b200_scratch(ctx, 6, 4096, reinterpret_cast<void**>(&d)));

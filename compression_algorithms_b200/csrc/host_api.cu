@@ -58,6 +58,7 @@ static uint64_t lz_chunk_blocks(const b200_ctx* ctx, uint64_t nblocks) {
 extern "C" int b200_lz77_compress_host(b200_ctx* ctx, int variant, const uint8_t* h_in, uint64_t n, uint64_t block_size,
                                        uint8_t* h_out, uint64_t out_capacity, uint64_t* h_block_sizes,
                                        uint64_t* h_block_off, uint64_t* h_total_bytes) {
+    B200_ENTER(ctx);
     if (n == 0) { if (h_block_off) h_block_off[0] = 0; if (h_total_bytes) *h_total_bytes = 0; return B200_OK; }
     if (variant != 0 && variant != 1) { B200_SET_ERR("lz77: variant must be 0 or 1"); return B200_ERR_ARG; }
     const uint64_t bs = lz_bs(n, block_size);
@@ -134,6 +135,7 @@ extern "C" int b200_lz77_compress_host(b200_ctx* ctx, int variant, const uint8_t
 extern "C" int b200_lz77_decompress_host(b200_ctx* ctx, int variant, const uint8_t* h_stream, uint64_t stream_bytes,
                                          const uint64_t* h_block_off, const uint64_t* h_block_sizes,
                                          uint64_t n, uint64_t block_size, uint8_t* h_out) {
+    B200_ENTER(ctx);
     if (n == 0) return B200_OK;
     const uint64_t bs = lz_bs(n, block_size);
     const uint64_t nblocks = (n + bs - 1) / bs;
@@ -191,6 +193,7 @@ extern "C" int b200_lz77_decompress_host(b200_ctx* ctx, int variant, const uint8
 extern "C" int b200_huffman_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
                                           uint32_t* h_words, uint64_t words_capacity, uint8_t* h_side, uint64_t side_bytes,
                                           uint64_t* h_total_words, uint32_t* h_worst_status) {
+    B200_ENTER(ctx);
     b200_huff_layout L;
     B200_TRY(b200_huffman_layout(n, block_size, &L));
     if (h_side && side_bytes < L.bytes) { B200_SET_ERR("huffman: host side buffer too small"); return B200_ERR_CAPACITY; }
@@ -217,6 +220,7 @@ extern "C" int b200_huffman_compress_host(b200_ctx* ctx, const uint8_t* h_in, ui
 extern "C" int b200_huffman_decompress_host(b200_ctx* ctx, const uint32_t* h_words, uint64_t total_words,
                                             const uint8_t* h_side, uint64_t side_bytes, uint64_t n, uint64_t block_size,
                                             uint8_t* h_out) {
+    B200_ENTER(ctx);
     if (n == 0) return B200_OK;
     b200_huff_layout L;
     B200_TRY(b200_huffman_layout(n, block_size, &L));
@@ -237,6 +241,7 @@ extern "C" int b200_huffman_decompress_host(b200_ctx* ctx, const uint32_t* h_wor
 extern "C" int b200_huffman_decompress_serial_host(b200_ctx* ctx, const uint32_t* h_words, uint64_t nwords,
                                                    uint64_t buffer_size, const uint32_t* h_codes, const uint8_t* h_lens,
                                                    uint8_t* h_out, uint64_t out_capacity, uint64_t* h_count) {
+    B200_ENTER(ctx);
     uint8_t *d_out, *d_tab; uint32_t* d_words;
     B200_TRY(b200_scratch(ctx, 8, out_capacity + 64, reinterpret_cast<void**>(&d_out)));
     B200_TRY(b200_scratch(ctx, 11, (nwords + 4) * 4, reinterpret_cast<void**>(&d_words)));
@@ -257,6 +262,7 @@ extern "C" int b200_huffman_decompress_serial_host(b200_ctx* ctx, const uint32_t
 // build_huffman_tree + gather_codes from a host buffer: only the side buffer comes back
 extern "C" int b200_huffman_tables_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
                                         uint8_t* h_side, uint64_t side_bytes) {
+    B200_ENTER(ctx);
     b200_huff_layout L;
     B200_TRY(b200_huffman_layout(n, block_size, &L));
     if (side_bytes < L.bytes) { B200_SET_ERR("huffman: host side buffer too small"); return B200_ERR_CAPACITY; }
@@ -275,6 +281,7 @@ extern "C" int b200_huffman_compress_codes_host(b200_ctx* ctx, const uint8_t* h_
                                                 const uint32_t* h_codes, const uint8_t* h_lens,
                                                 uint32_t* h_words, uint64_t words_capacity, uint8_t* h_side, uint64_t side_bytes,
                                                 uint64_t* h_total_words, uint32_t* h_worst_status) {
+    B200_ENTER(ctx);
     if (n == 0) { if (h_total_words) *h_total_words = 0; if (h_worst_status) *h_worst_status = 0; return B200_OK; }
     b200_huff_layout L;
     B200_TRY(b200_huffman_layout(n, 0, &L));
@@ -317,6 +324,7 @@ extern "C" uint64_t b200_fse_container_max_words(uint64_t n, uint64_t block_size
 
 extern "C" int b200_fse_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size, uint64_t seg_size,
                                       uint64_t* h_out, uint64_t out_capacity_words, uint64_t* h_total_words) {
+    B200_ENTER(ctx);
     if (n == 0) { B200_SET_ERR("fse: empty input"); return B200_ERR_DOMAIN; }
     b200_fse_layout L;
     B200_TRY(b200_fse_layout_for(n, block_size, seg_size, &L));
@@ -350,6 +358,7 @@ extern "C" int b200_fse_container_size(const uint64_t* h_container, uint64_t wor
 
 extern "C" int b200_fse_decompress_host(b200_ctx* ctx, const uint64_t* h_container, uint64_t words,
                                         uint8_t* h_out, uint64_t out_capacity, uint64_t* h_n) {
+    B200_ENTER(ctx);
     uint64_t n = 0;
     B200_TRY(b200_fse_container_size(h_container, words, &n));
     const uint64_t bs = h_container[2], seg = h_container[3], nblocks = h_container[4], nsegs = h_container[5], total = h_container[6];
@@ -397,6 +406,7 @@ extern "C" int b200_fse_decompress_host(b200_ctx* ctx, const uint64_t* h_contain
 // histogram + normalisation of one table scope from a host buffer (buildFrequencyTable +
 // normalizeFrequencyTable, main.zig:88-149): freq[256] and norm[256] of block 0 come back
 extern "C" int b200_fse_normalize_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint32_t* h_freq, uint16_t* h_norm) {
+    B200_ENTER(ctx);
     if (n == 0) { B200_SET_ERR("fse: empty input"); return B200_ERR_DOMAIN; }
     b200_fse_layout L;
     B200_TRY(b200_fse_layout_for(n, 0, 1024, &L));
@@ -417,6 +427,7 @@ extern "C" int b200_fse_normalize_host(b200_ctx* ctx, const uint8_t* h_in, uint6
 extern "C" int b200_deflate_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint64_t block_size,
                                           uint32_t* h_words, uint64_t words_capacity, uint8_t* h_side, uint64_t side_bytes,
                                           uint64_t* h_total_words, uint32_t* h_worst_status) {
+    B200_ENTER(ctx);
     if (n == 0) { if (h_total_words) *h_total_words = 0; if (h_worst_status) *h_worst_status = 0; return B200_OK; }
     b200_dfl_layout L;
     B200_TRY(b200_dfl_layout_for(n, block_size, &L));
@@ -446,6 +457,7 @@ extern "C" int b200_deflate_compress_host(b200_ctx* ctx, const uint8_t* h_in, ui
 extern "C" int b200_deflate_decompress_host(b200_ctx* ctx, const uint32_t* h_words, uint64_t total_words,
                                             const uint8_t* h_side, uint64_t side_bytes, uint64_t n, uint64_t block_size,
                                             uint8_t* h_out) {
+    B200_ENTER(ctx);
     if (n == 0) return B200_OK;
     b200_dfl_layout L;
     B200_TRY(b200_dfl_layout_for(n, block_size, &L));

@@ -254,6 +254,7 @@ __global__ void huff_decode_serial_kernel(const uint32_t* __restrict__ words, ui
         symv[cur] = (uint8_t)s;
     }
     uint64_t consumed = 0, o = 0;
+    if (left[0] < 0 || right[0] < 0) { *count = 0; return; }   // an empty or one-code table never consumes a bit: the walk below would spin
     do {
         int v = 0;
         while (left[v] >= 0 && right[v] >= 0) {
@@ -332,6 +333,7 @@ static int huff_tables(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t 
 
 extern "C" int b200_huffman_tables_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
                                        uint8_t* d_side, uint64_t side_bytes) {
+    B200_ENTER(ctx);
     b200_huff_layout L; uint64_t bs;
     return huff_tables(ctx, d_in, n, block_size, d_side, side_bytes, &L, &bs);
 }
@@ -339,6 +341,7 @@ extern "C" int b200_huffman_tables_dev(b200_ctx* ctx, const uint8_t* d_in, uint6
 // decoder side of a stored stream (container.cu): with freq[] of every block already in d_side, rebuild codes, lengths,
 // trees and meta with the same heap replay the encoder ran
 extern "C" int b200_huffman_tables_from_freq_dev(b200_ctx* ctx, uint8_t* d_side, uint64_t side_bytes, uint64_t n, uint64_t block_size) {
+    B200_ENTER(ctx);
     b200_huff_layout L;
     B200_TRY(b200_huffman_layout(n, block_size, &L));
     if (side_bytes < L.bytes) { B200_SET_ERR("huffman: side buffer too small"); return B200_ERR_CAPACITY; }
@@ -390,6 +393,7 @@ static int huff_pack(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, const b200_
 extern "C" int b200_huffman_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t block_size,
                                        uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
                                        uint64_t* h_total_words, uint32_t* h_worst_status) {
+    B200_ENTER(ctx);
     b200_huff_layout L; uint64_t bs;
     B200_TRY(huff_tables(ctx, d_in, n, block_size, d_side, side_bytes, &L, &bs));
     return huff_pack(ctx, d_in, n, L, d_words, words_capacity, d_side, h_total_words, h_worst_status);
@@ -408,6 +412,7 @@ extern "C" int b200_huffman_encode_with_codes_dev(b200_ctx* ctx, const uint8_t* 
                                                   const uint32_t* h_codes, const uint8_t* h_lens,
                                                   uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
                                                   uint64_t* h_total_words, uint32_t* h_worst_status) {
+    B200_ENTER(ctx);
     if (n == 0) { if (h_total_words) *h_total_words = 0; if (h_worst_status) *h_worst_status = 0; return B200_OK; }
     if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_side) & 7)) {
         B200_SET_ERR("huffman: d_in must be 16-byte and d_side 8-byte aligned"); return B200_ERR_ARG;
@@ -472,6 +477,7 @@ __global__ void __launch_bounds__(256) huff_narrow_freq_kernel(const uint64_t* _
 }
 
 extern "C" int b200_huffman_histogram_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t* d_freq64) {
+    B200_ENTER(ctx);
     if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_freq64) & 7)) {
         B200_SET_ERR("huffman: d_in must be 16-byte and d_freq64 8-byte aligned"); return B200_ERR_ARG;
     }
@@ -493,6 +499,7 @@ extern "C" int b200_huffman_histogram_dev(b200_ctx* ctx, const uint8_t* d_in, ui
 extern "C" int b200_huffman_encode_with_freq_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, const uint64_t* d_freq64,
                                                  uint32_t* d_words, uint64_t words_capacity, uint8_t* d_side, uint64_t side_bytes,
                                                  uint64_t* h_total_words, uint64_t* h_total_bits, uint32_t* h_worst_status) {
+    B200_ENTER(ctx);
     if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_side) & 7)) {
         B200_SET_ERR("huffman: d_in must be 16-byte and d_side 8-byte aligned"); return B200_ERR_ARG;
     }
@@ -552,6 +559,7 @@ __global__ void __launch_bounds__(256) huff_splice_kernel(uint32_t* __restrict__
 
 extern "C" int b200_huffman_splice_dev(b200_ctx* ctx, uint32_t* d_dst, uint64_t dst_words_capacity, uint64_t dst_bit,
                                        const uint32_t* d_src, uint64_t src_bits) {
+    B200_ENTER(ctx);
     if (src_bits == 0) return B200_OK;
     const uint64_t nwords = ((dst_bit & 31) + src_bits + 31) >> 5;
     if ((dst_bit >> 5) + nwords > dst_words_capacity) { B200_SET_ERR("huffman splice: destination too small"); return B200_ERR_CAPACITY; }
@@ -564,6 +572,7 @@ extern "C" int b200_huffman_splice_dev(b200_ctx* ctx, uint32_t* d_dst, uint64_t 
 
 extern "C" int b200_huffman_decode_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t total_words, const uint8_t* d_side,
                                        uint64_t side_bytes, uint64_t n, uint64_t block_size, uint8_t* d_out) {
+    B200_ENTER(ctx);
     if (n == 0) return B200_OK;
     b200_huff_layout L;
     B200_TRY(b200_huffman_layout(n, block_size, &L));
@@ -585,6 +594,7 @@ extern "C" int b200_huffman_decode_dev(b200_ctx* ctx, const uint32_t* d_words, u
 extern "C" int b200_huffman_decode_serial_dev(b200_ctx* ctx, const uint32_t* d_words, uint64_t nwords, uint64_t buffer_size,
                                               const uint32_t* d_codes, const uint8_t* d_lens, uint8_t* d_out,
                                               uint64_t out_capacity, uint64_t* h_count) {
+    B200_ENTER(ctx);
     uint64_t* d_cnt;
     B200_TRY(b200_scratch(ctx, 0, 64, reinterpret_cast<void**>(&d_cnt)));
     huff_decode_serial_kernel<<<1, 32, 0, ctx->stream>>>(d_words, nwords, buffer_size, d_codes, d_lens, d_out, out_capacity, d_cnt);
@@ -675,6 +685,7 @@ static uint64_t zig_put_tree(const int16_t* kids, const uint32_t* freq, int v, u
 
 extern "C" int b200_zig_huffman_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t n, uint8_t* h_out, uint64_t out_capacity,
                                               uint64_t* h_total_bytes) {
+    B200_ENTER(ctx);
     const uint64_t nz = n / ZIG_CHUNK + 1;                     // chunks the reference writes (an exact multiple ends with an empty one)
     const uint64_t n_aug = nz * ZIG_CHUNK;
     const uint64_t nb = n ? (n + ZIG_CHUNK - 1) / ZIG_CHUNK : 0;   // chunks that carry data
@@ -757,6 +768,7 @@ extern "C" int b200_zig_huffman_compress_host(b200_ctx* ctx, const uint8_t* h_in
 
 extern "C" int b200_zig_huffman_decompress_host(b200_ctx* ctx, const uint8_t* h_in, uint64_t bytes, uint8_t* h_out, uint64_t out_capacity,
                                                 uint64_t* h_n) {
+    B200_ENTER(ctx);
     // parse: trees + chunk table on the host
     std::vector<int16_t> trees;       // [chunk][511][2]
     std::vector<uint64_t> pay_off; std::vector<uint32_t> pay_size;

@@ -529,6 +529,7 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
 extern "C" int b200_lz77_encode_dev(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t block_size,
                                     uint8_t* d_out, uint64_t out_capacity, uint64_t* d_block_sizes, uint64_t* d_block_off,
                                     uint64_t* h_total_bytes) {
+    B200_ENTER(ctx);
     return lz77_encode_impl(ctx, variant, d_in, n, block_size, d_out, out_capacity, d_block_sizes, d_block_off, h_total_bytes, nullptr);
 }
 
@@ -538,11 +539,13 @@ extern "C" int b200_lz77_encode_dev(b200_ctx* ctx, int variant, const uint8_t* d
 extern "C" int b200_lz77_encode_debug_dev(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t block_size,
                                           uint8_t* d_out, uint64_t out_capacity, uint64_t* d_block_sizes, uint64_t* d_block_off,
                                           uint64_t* h_total_bytes, uint32_t* d_tok) {
+    B200_ENTER(ctx);
     return lz77_encode_impl(ctx, variant, d_in, n, block_size, d_out, out_capacity, d_block_sizes, d_block_off, h_total_bytes, d_tok);
 }
 
 extern "C" int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d_stream, const uint64_t* d_block_off,
                                     const uint64_t* d_block_sizes, uint64_t n, uint64_t block_size, uint8_t* d_out) {
+    B200_ENTER(ctx);
     if (variant != 0 && variant != 1) { B200_SET_ERR("lz77: variant must be 0 or 1"); return B200_ERR_ARG; }
     if (n == 0) return B200_OK;
     const uint64_t bs = (block_size == 0 || block_size > n) ? n : block_size;

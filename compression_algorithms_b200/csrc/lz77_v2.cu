@@ -976,7 +976,8 @@ bool lz77_v2_supported(uint64_t bs) { return bs <= (1ull << 31); }
 // scratch slots: 13 = lists, 14 = tok
 int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
                    uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok) {
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};   // the attribute is per device
+    bool& attr_done = attr_done_dev[ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0];
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(lz77_v2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(lz77_v2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

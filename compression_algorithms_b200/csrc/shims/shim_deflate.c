@@ -95,29 +95,50 @@ void destroy_huffman_node(HuffmanNode* n) {
 bool compare_huffman_node(const HuffmanNode* a, const HuffmanNode* b) { return a->frequency < b->frequency; }
 
 /* ---- GPU-backed entry points ------------------------------------------------------------ */
+/* Every GPU of the box works on a buffer of many blocks (blocks are independent: fresh table per block), one host
+ * thread per GPU inside libb200comp.so (b200_lz77_compress_multi_host). B200_DEVICES = "n" limits the count
+ * (default: all visible devices); buffers below 64 blocks per device stay on one GPU. */
+static b200_multi* shim_multi(uint64_t nblocks) {
+    static b200_multi* m = NULL;
+    static int tried = 0;
+    if (!tried) {
+        tried = 1;
+        int want = b200_device_count();
+        const char* e = getenv("B200_DEVICES");
+        if (e && atoi(e) > 0 && atoi(e) < want) want = atoi(e);
+        if (want > 1 && b200_multi_create(&m, NULL, want) != B200_OK) { fprintf(stderr, "warning: multi-GPU setup failed (%s); using one GPU\n", b200_last_error()); m = NULL; }
+    }
+    if (m && nblocks < 64ull * (uint64_t)b200_multi_device_count(m)) return NULL;
+    return m;
+}
+
 uint64_t deflate_compress_buffer(const char* in, uint64_t size, uint64_t block_size, char* out, uint64_t* block_off) {
-    b200_ctx* ctx = shim_ctx();
     if (size == 0) { block_off[0] = 0; return 0; }
     const uint64_t bs = (block_size == 0 || block_size > size) ? size : block_size;
     const uint64_t nblocks = (size + bs - 1) / bs;
     uint64_t* sizes = (uint64_t*)malloc(nblocks * sizeof(uint64_t));
     uint64_t total = 0;
-    GPU_CHECK(b200_lz77_compress_host(ctx, B200_LZ_DEFLATE, (const uint8_t*)in, size, block_size, (uint8_t*)out,
-                                      b200_lz77_max_bytes(B200_LZ_DEFLATE, size, block_size), sizes, block_off, &total));
+    b200_multi* m = shim_multi(nblocks);
+    if (m) GPU_CHECK(b200_lz77_compress_multi_host(m, B200_LZ_DEFLATE, (const uint8_t*)in, size, block_size, (uint8_t*)out,
+                                                   b200_lz77_max_bytes(B200_LZ_DEFLATE, size, block_size), sizes, block_off, &total));
+    else GPU_CHECK(b200_lz77_compress_host(shim_ctx(), B200_LZ_DEFLATE, (const uint8_t*)in, size, block_size, (uint8_t*)out,
+                                           b200_lz77_max_bytes(B200_LZ_DEFLATE, size, block_size), sizes, block_off, &total));
     free(sizes);
     return total;
 }
 
 void deflate_decompress_buffer(const char* tokens, uint64_t token_bytes, const uint64_t* block_off, uint64_t size,
                                uint64_t block_size, char* out) {
-    b200_ctx* ctx = shim_ctx();
     if (size == 0) return;
     const uint64_t bs = (block_size == 0 || block_size > size) ? size : block_size;
     const uint64_t nblocks = (size + bs - 1) / bs;
     uint64_t* sizes = (uint64_t*)malloc(nblocks * sizeof(uint64_t));
     for (uint64_t b = 0; b < nblocks; ++b) sizes[b] = block_off[b + 1] - block_off[b];
-    GPU_CHECK(b200_lz77_decompress_host(ctx, B200_LZ_DEFLATE, (const uint8_t*)tokens, token_bytes, block_off, sizes, size,
-                                        block_size, (uint8_t*)out));
+    b200_multi* m = shim_multi(nblocks);
+    if (m) GPU_CHECK(b200_lz77_decompress_multi_host(m, B200_LZ_DEFLATE, (const uint8_t*)tokens, token_bytes, block_off, sizes, size,
+                                                     block_size, (uint8_t*)out));
+    else GPU_CHECK(b200_lz77_decompress_host(shim_ctx(), B200_LZ_DEFLATE, (const uint8_t*)tokens, token_bytes, block_off, sizes, size,
+                                             block_size, (uint8_t*)out));
     free(sizes);
 }
 

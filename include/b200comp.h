@@ -314,6 +314,24 @@ int b200_deflate_compress_container_host(b200_ctx* ctx, const uint8_t* h_in, uin
                                          void* h_out, uint64_t out_capacity, uint64_t* h_total_bytes);
 int b200_deflate_decompress_container_host(b200_ctx* ctx, const void* h_container, uint64_t bytes,
                                            uint8_t* h_out, uint64_t out_capacity, uint64_t* h_n);
+/* ---- multi-GPU host entry points in C (csrc/multi.cu) -------------------------------------
+ * ONE buffer sharded by block over the GPUs of the box: contiguous block ranges, ceil(nblocks / G) per device, one
+ * host thread per GPU, no data-path collective. The one exchange is an ncclAllGather of the G shard sizes (NCCL is
+ * bound at run time from libnccl.so.2; a handle with one device needs no NCCL), after which every device copies its
+ * shard to its global offset of h_out: the result is byte for byte what the single-device call returns. */
+typedef struct b200_multi b200_multi;
+int      b200_multi_create(b200_multi** out, const int* devices /* NULL = 0..ndev-1 */, int ndev);
+void     b200_multi_destroy(b200_multi* m);
+int      b200_multi_device_count(b200_multi* m);
+uint64_t b200_multi_allgathers(b200_multi* m);   /* size exchanges issued so far */
+uint64_t b200_multi_launches(b200_multi* m);     /* kernels launched on all devices */
+int b200_lz77_compress_multi_host(b200_multi* m, int variant, const uint8_t* h_in, uint64_t n, uint64_t block_size,
+                                  uint8_t* h_out, uint64_t out_capacity, uint64_t* h_block_sizes, uint64_t* h_block_off,
+                                  uint64_t* h_total_bytes);
+int b200_lz77_decompress_multi_host(b200_multi* m, int variant, const uint8_t* h_stream, uint64_t stream_bytes,
+                                    const uint64_t* h_block_off, const uint64_t* h_block_sizes, uint64_t n,
+                                    uint64_t block_size, uint8_t* h_out);
+
 /* ---- Zig-Huffman-compatible chunked mode: the FILE FORMAT of
  * algorithms/huffman/zig_huffman/src/main.zig -- 4 MiB chunks (:5), per chunk the tree dumped pre-order (value u8 +
  * freq u32 per node, i32 -1 for a missing child, :155-176), CompressedSize{last_block:1, value:31} (:11-18,513-520)
