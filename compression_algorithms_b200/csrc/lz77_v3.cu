@@ -44,6 +44,7 @@ constexpr uint32_t MAXB = 65536;
 constexpr uint32_t NTHREADS = 1024;
 constexpr uint32_t NBIN = 1024;                              // lane lists: bin = compact cluster start >> 6
 constexpr uint32_t BIN_SPECIAL = NBIN;                       // slot-0 / table-end cluster
+constexpr uint32_t LONG_LIST_MIN = 48;                           // list length from which a warp takes the list
 constexpr uint32_t CNT_STRIDE = 1026;                        // u16 counters per warp row (even: pairs share a u32)
 
 // shared memory layout (bytes)
@@ -70,11 +71,12 @@ constexpr uint32_t OFF_STAGE = PADDED;
 struct Misc3 {
     uint32_t scan[34];
     uint32_t cut0, top_start, sp_lo_end, sp_hi_start;
-    uint32_t p1_next, pad0, pad1, pad2;
+    uint32_t p1_next, nlong, next_long, pad2;
     uint32_t clr[64];            // slot-0 clear times
     uint8_t  sexit[32][32];
     uint8_t  sentry[36];
     uint32_t binstart[NBIN + 4]; // first list entry of every lane list; [1024] = special list, [1025] = end
+    uint16_t longbin[NBIN];      // lists of more than LONG_LIST_MIN entries: simulated by a whole warp each (stage B of P7)
 };
 static_assert(sizeof(Misc3) <= SZ_MISC, "misc region too small");
 
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v3_kernel(const uint8_t* __r
             }
             for (uint32_t i = tid; i < BM_WORDS; i += NTHREADS) bm[i] = 0;
             for (uint32_t i = tid; i < BM_WORDS / 32; i += NTHREADS) pre[i] = 0;   // P1's "word is full" summary
-            if (tid == 0) ms->p1_next = 0;
+            if (tid == 0) { ms->p1_next = 0; ms->nlong = 0; ms->next_long = 0; }
         }
         __syncthreads();
 
@@ -466,28 +468,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v3_kernel(const uint8_t* __r
         {
             const long long t_p7 = CLK3();
             const uint32_t lo = ms->binstart[tid], hi = ms->binstart[tid + 1];
-            uint32_t i = lo, ei = lo;
+            // ---- stage A: one lane per list, the short lists only (a long list would keep its whole warp waiting)
+            const bool is_long = hi - lo > LONG_LIST_MIN;
+            if (is_long) ms->longbin[atomicAdd(&ms->nlong, 1u)] = (uint16_t)tid;
+            uint32_t i = is_long ? hi : lo, ei = lo;
             uint32_t hint_c = NONE, hint_w = 0;
-            uint32_t a_n = lo < hi ? la[lo] : 0u, f_n = lo < hi ? lb[lo] : 0u;
-            uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0, xm = 0;   // records of the entries ei .. ei+3 (position | slot << 16), xm = which are loaded
+            uint32_t a_n = i < hi ? la[i] : 0u, f_n = i < hi ? lb[i] : 0u;
             uint32_t st_walk = 0, st_exp = 0;
             while (i < hi) {
                 const uint32_t a = a_n, f = f_n;
                 if (i + 1 < hi) { a_n = la[i + 1]; f_n = lb[i + 1]; }
                 const uint32_t p = a & 0xFFFFu, c = a >> 16;
-                // prefetch the records of the next entries to expire (only placed ones: index < i)
-                if (!(xm & 1u) && ei < i) { x0 = lb[ei]; xm |= 1u; }
-                if (!(xm & 2u) && ei + 1 < i) { x1 = lb[ei + 1]; xm |= 2u; }
-                if (!(xm & 4u) && ei + 2 < i) { x2 = lb[ei + 2]; xm |= 4u; }
-                if (!(xm & 8u) && ei + 3 < i) { x3 = lb[ei + 3]; xm |= 8u; }
                 // FIFO expiry: the entry of position j is live at time p iff j + W >= p
                 while (ei < i) {
-                    if (!(xm & 1u)) { x0 = lb[ei]; xm |= 1u; }
+                    const uint32_t x0 = lb[ei];
                     if ((x0 & 0xFFFFu) + W >= p) break;
                     const uint32_t s = x0 >> 16;
                     atomicAnd(&M[s >> 5], ~(1u << (s & 31)));
                     if (s >= hint_c && (s >> 5) < hint_w) hint_w = s >> 5;
-                    ++ei; x0 = x1; x1 = x2; x2 = x3; xm >>= 1;
+                    ++ei;
                     if (DBG) ++st_exp;
                 }
                 if (f & 1u) {   // find: walk the live slots from the home until the pattern or a dead slot
@@ -514,6 +513,80 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v3_kernel(const uint8_t* __r
                 lb[i] = p | (e << 16);
                 ++i;
             }
+            const long long t_a = CLK3();
+            __syncthreads();     // longbin complete (the clusters of long lists are touched by nobody in stage A)
+            // ---- stage B: the long lists (the chains of hot 4-grams), one WARP per list, pulled from a shared counter.
+            // All 32 lanes run the same serial simulation on the same values; the lanes serve as the prefetch buffer:
+            // 32 list entries (and 32 expiry records) are loaded with one coalesced access and handed out by shuffle,
+            // so that no global-memory latency sits on the chain. Side effects by lane 0 only.
+            {
+                const uint32_t nlong = ms->nlong;
+                for (;;) {
+                    uint32_t li = 0;
+                    if (lane == 0) li = atomicAdd(&ms->next_long, 1u);
+                    li = __shfl_sync(0xffffffffu, li, 0);
+                    if (li >= nlong) break;
+                    const uint32_t bin = ms->longbin[li];
+                    const uint32_t llo = ms->binstart[bin], lhi = ms->binstart[bin + 1];
+                    uint32_t j = llo, ej = llo;
+                    uint32_t ebase = llo;
+                    uint32_t ea = ebase + lane < lhi ? la[ebase + lane] : 0u, ef = ebase + lane < lhi ? lb[ebase + lane] : 0u;
+                    uint32_t xbase = llo, xcount = 0, xr = 0;        // records of the entries xbase .. xbase + xcount - 1
+                    // (hc, hwd, hw): every word of M in [hc >> 5, hwd) has no dead slot at/after hc; hw = this list's view of M[hwd]
+                    uint32_t hc = NONE, hwd = 0, hw = 0;
+                    while (j < lhi) {
+                        if (j - ebase == 32) { ebase += 32; ea = ebase + lane < lhi ? la[ebase + lane] : 0u; ef = ebase + lane < lhi ? lb[ebase + lane] : 0u; }
+                        const uint32_t a = __shfl_sync(0xffffffffu, ea, j - ebase), f = __shfl_sync(0xffffffffu, ef, j - ebase);
+                        const uint32_t p = a & 0xFFFFu, c = a >> 16;
+                        while (ej < j) {
+                            if (ej - xbase >= xcount) {      // next batch of records: only entries that are placed (index < j)
+                                __syncwarp();
+                                xbase = ej; xcount = j - ej < 32 ? j - ej : 32;
+                                xr = lane < xcount ? *reinterpret_cast<volatile uint32_t*>(&lb[xbase + lane]) : 0u;
+                            }
+                            const uint32_t x0 = __shfl_sync(0xffffffffu, xr, ej - xbase);
+                            if ((x0 & 0xFFFFu) + W >= p) break;
+                            const uint32_t s = x0 >> 16, sw = s >> 5, sbit = 1u << (s & 31);
+                            if (lane == 0) atomicAnd(&M[sw], ~sbit);
+                            if (s >= hc) {
+                                if (sw < hwd) { hwd = sw; hw = ~sbit; }   // that word had no dead slot at/after hc: now exactly this one
+                                else if (sw == hwd) hw &= ~sbit;
+                            }
+                            ++ej;
+                        }
+                        __syncwarp();
+                        if (f & 1u) {   // find (uniform: every lane reads the same words)
+                            const uint32_t w = sm_word(data, p);
+                            uint32_t s = c, m = NONE;
+                            for (;;) {
+                                if (!((*reinterpret_cast<volatile uint32_t*>(&M[s >> 5]) >> (s & 31)) & 1u)) break;
+                                const uint32_t q = *reinterpret_cast<volatile uint16_t*>(&T[s]);
+                                if (sm_word(data, q) == w) { m = q; break; }
+                                ++s;
+                            }
+                            if (lane == 0) cand[p] = candidate<V>(data, m, p);
+                        }
+                        uint32_t wi, z;
+                        if (c == hc) { wi = hwd; z = ~hw; if (wi == (c >> 5)) z &= 0xFFFFFFFFu << (c & 31); }
+                        else { wi = c >> 5; z = ~*reinterpret_cast<volatile uint32_t*>(&M[wi]) & (0xFFFFFFFFu << (c & 31)); }
+                        while (!z) { ++wi; z = ~*reinterpret_cast<volatile uint32_t*>(&M[wi]); }
+                        const uint32_t e = (wi << 5) + (uint32_t)(__ffs(z) - 1);
+                        const uint32_t ebit = 1u << (e & 31);
+                        if (f & 2u) {                       // a head: its home keys the hint from now on
+                            if (c != hc || wi != hwd) { hw = ~z; if (wi == (c >> 5)) hw |= ~(0xFFFFFFFFu << (c & 31)); }
+                            hc = c; hwd = wi; hw |= ebit;
+                        } else if (e >= hc && (e >> 5) == hwd) hw |= ebit;
+                        if (lane == 0) {
+                            atomicOr(&M[e >> 5], ebit);
+                            T[e] = (uint16_t)p;
+                            lb[j] = p | (e << 16);
+                        }
+                        ++j;
+                    }
+                    __syncwarp();
+                }
+            }
+            (void)t_a;
             // the slot-0 / table-end cluster: serial, exact reference order, T = position + 1 with lazy expiry (0 = never
             // used; its compact slots [0, sp_lo_end) and [sp_hi_start, nslots) are touched by nobody else)
             if (tid == 0) {
@@ -545,7 +618,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v3_kernel(const uint8_t* __r
             }
             if (DBG && dbg_stats && lane == 0) {
                 uint32_t* o = dbg_stats + (uint64_t)b * 136 + 8 + warp * 4;
-                o[0] = (uint32_t)(clock64() - t_p7); o[1] = hi - lo; o[2] = st_walk; o[3] = st_exp;
+                o[0] = (uint32_t)(clock64() - t_p7); o[1] = hi - lo; o[2] = (uint32_t)(t_a - t_p7); o[3] = ms->nlong;
             }
         }
         __threadfence_block();

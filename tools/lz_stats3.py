@@ -1,4 +1,4 @@
-"""Phase cycles of lz77_v3_kernel (debug instantiation): python tools/lz_stats3.py [kind] [blocks per CTA] [variant]"""
+"""Phase cycles of lz77_v3_kernel (debug instantiation): B200_LZ_V3=1 python tools/lz_stats3.py [kind] [blocks per CTA] [variant]"""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 from compression_algorithms_b200 import corpus, device as dv
@@ -19,5 +19,5 @@ for k, nm in enumerate(names):
     dtk = ph[:, k] - prev; prev = ph[:, k]
     print("  %-17s median %8d  p90 %8d  max %8d cycles" % (nm, np.median(dtk), np.percentile(dtk, 90), dtk.max()))
 w = s[:, 8:].reshape(len(s), 32, 4)
-cyc = w[:, :, 0]
-print("  P7 per-warp cycles (lane 0's view): median of max %d, median of median %d" % (np.median(cyc.max(1)), np.median(np.median(cyc, 1))))
+print("  P7 per warp: total median of max %d, median %d | stage A median of max %d, median %d | long lists per block median %d" % (
+    np.median(w[:, :, 0].max(1)), np.median(np.median(w[:, :, 0], 1)), np.median(w[:, :, 2].max(1)), np.median(np.median(w[:, :, 2], 1)), np.median(w[:, 0, 3])))
