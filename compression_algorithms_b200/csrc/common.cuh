@@ -60,7 +60,22 @@ struct b200_ctx {
     cudaStream_t s_in, s_out, s_aux;   // s_aux: second kernel stream, so that latency-bound chunk kernels overlap
     cudaEvent_t  ev_in[kPipe], ev_done[kPipe];
     bool         pipe_ready;
+    // pinned bounce rings for PAGEABLE caller buffers (malloc'd memory, what an unmodified reference driver passes):
+    // ring 0 feeds host -> device copies, ring 1 drains device -> host copies; see b200_copy_in / b200_copy_out
+    static const int kStage = 3;
+    static const size_t kStageBytes = 16u << 20;
+    void*        stage[2][kStage];
+    cudaEvent_t  stage_ev[2][kStage];
+    bool         stage_ready[2];
 };
+// Host <-> device copies that are fast for pageable host memory too: a large pageable buffer goes through a ring of
+// pinned 16 MiB bounce buffers, filled / drained by several host threads while the previous piece is on the bus
+// (the driver's own pageable path is a few GB/s). Pinned or small buffers are copied directly.
+//   b200_copy_in : returns when the source has been consumed and every piece is enqueued on `st`
+//   b200_copy_out: returns when the data is in h_dst (synchronous)
+int b200_copy_in(b200_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes, cudaStream_t st);
+int b200_copy_out(b200_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes, cudaStream_t st);
+bool b200_is_pageable(const void* h_ptr);
 int b200_pipe_init(b200_ctx* ctx);
 
 #define B200_SLOT(ctx, s) ((s) + 20 * (ctx)->bank)

@@ -86,7 +86,7 @@ extern "C" int b200_huffman_compress_container_host(b200_ctx* ctx, const uint8_t
     B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
     B200_TRY(b200_scratch(ctx, 11, cap * 4, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
-    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_in, h_in, n, ctx->stream));
     uint64_t total = 0; uint32_t worst = 0;
     B200_TRY(b200_huffman_encode_dev(ctx, d_in, n, block_size, d_words, cap, d_side, L.bytes, &total, &worst));
     if (worst) { B200_SET_ERR("huffman: input has a block the reference cannot encode (status %u)", worst); return B200_ERR_DOMAIN; }
@@ -98,10 +98,10 @@ extern "C" int b200_huffman_compress_container_host(b200_ctx* ctx, const uint8_t
     const uint64_t hdr[8] = {CONT_MAGIC, CONT_VERSION | (CODEC_HUFFMAN << 32), n, bs_eff, L.nblocks, L.nchunks, total, 0};
     memcpy(o, hdr, 64);
     memset(o + s.o_sub - 8, 0, 8); memset(o + s.o_words - 8, 0, 8); memset(o + s.total - 8, 0, 8);   // section padding
-    CUDA_TRY(cudaMemcpyAsync(o + s.o_freq, d_side + L.off_freq, L.nblocks * 1024, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(o + s.o_cbits, d_side + L.off_chunk_bits, L.nchunks * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(o + s.o_sub, d_side + L.off_sub_off, L.nchunks * 64, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(o + s.o_words, d_words, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, o + s.o_freq, d_side + L.off_freq, L.nblocks * 1024, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, o + s.o_cbits, d_side + L.off_chunk_bits, L.nchunks * 4, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, o + s.o_sub, d_side + L.off_sub_off, L.nchunks * 64, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, o + s.o_words, d_words, total * 4, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
@@ -152,7 +152,7 @@ extern "C" int b200_huffman_decompress_container_host(b200_ctx* ctx, const void*
     B200_TRY(b200_scratch(ctx, 11, (total + 4) * 4, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
     CUDA_TRY(cudaMemcpyAsync(d_side, side.data(), L.bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_words, c + s.o_words, total * 4, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_words, c + s.o_words, total * 4, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(d_words + total, 0, 16, ctx->stream));
     B200_TRY(b200_huffman_tables_from_freq_dev(ctx, d_side, L.bytes, n, bs));
     {   // a histogram that cannot have produced this stream (fewer than two symbols, a code beyond 32 bits) is corrupt
@@ -162,7 +162,7 @@ extern "C" int b200_huffman_decompress_container_host(b200_ctx* ctx, const void*
         for (uint64_t b = 0; b < L.nblocks; ++b) if (pin[b * 4]) { B200_SET_ERR("huffman container: the table of block %llu is not decodable (status %u)", (unsigned long long)b, pin[b * 4]); return B200_ERR_FORMAT; }
     }
     B200_TRY(b200_huffman_decode_dev(ctx, d_words, total, d_side, L.bytes, n, bs, d_out));
-    CUDA_TRY(cudaMemcpyAsync(h_out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_out, d_out, n, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
@@ -182,7 +182,7 @@ extern "C" int b200_deflate_compress_container_host(b200_ctx* ctx, const uint8_t
     B200_TRY(b200_scratch(ctx, 10, (2 * L.nblocks + 2) * 8, reinterpret_cast<void**>(&d_idx)));
     B200_TRY(b200_scratch(ctx, 11, cap * 4, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
-    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_in, h_in, n, ctx->stream));
     uint64_t total = 0; uint32_t worst = 0;
     B200_TRY(b200_deflate_compress_dev(ctx, d_in, n, block_size, d_tok, tok_cap, d_idx, d_idx + L.nblocks, d_words, cap, d_side, L.bytes, &total, &worst));
     if (worst) { B200_SET_ERR("deflate: a block needs a code longer than 32 bits (status %u)", worst); return B200_ERR_DOMAIN; }
@@ -212,8 +212,8 @@ extern "C" int b200_deflate_compress_container_host(b200_ctx* ctx, const uint8_t
         memcpy(osub + k * 16, sub.data() + c0 * 16, used * 64);
         k += used;
     }
-    CUDA_TRY(cudaMemcpyAsync(o + s.o_freq, d_side + L.off_freq, L.nblocks * 288 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(o + s.o_words, d_words, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, o + s.o_freq, d_side + L.off_freq, L.nblocks * 288 * 4, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, o + s.o_words, d_words, total * 4, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
@@ -278,7 +278,7 @@ extern "C" int b200_deflate_decompress_container_host(b200_ctx* ctx, const void*
     B200_TRY(b200_scratch(ctx, 11, (total + 4) * 4, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
     CUDA_TRY(cudaMemcpyAsync(d_side, side.data(), L.bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_words, c + s.o_words, total * 4, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_words, c + s.o_words, total * 4, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(d_words + total, 0, 16, ctx->stream));
     B200_TRY(b200_dfl_tables_from_freq_dev(ctx, d_side, L.bytes, n, bs));
     {
@@ -288,7 +288,7 @@ extern "C" int b200_deflate_decompress_container_host(b200_ctx* ctx, const void*
         for (uint64_t b = 0; b < L.nblocks; ++b) if (pin[b * 4] && tok_sizes[b]) { B200_SET_ERR("deflate container: the table of block %llu is not decodable (status %u)", (unsigned long long)b, pin[b * 4]); return B200_ERR_FORMAT; }
     }
     B200_TRY(b200_deflate_decompress_dev(ctx, d_words, total, d_side, L.bytes, n, bs, d_tok, d_out));
-    CUDA_TRY(cudaMemcpyAsync(h_out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_out, d_out, n, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }

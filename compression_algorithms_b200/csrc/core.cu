@@ -1,4 +1,7 @@
 // Context, scratch memory and copy helpers of libb200comp.so.
+#include <cstdlib>
+#include <thread>
+#include <vector>
 #include "common.cuh"
 #include "../../include/b200comp.h"
 
@@ -44,6 +47,7 @@ extern "C" void b200_ctx_destroy(b200_ctx* ctx) {
         for (int i = 0; i < b200_ctx::kPipe; ++i) { cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_done[i]); }
         cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); cudaStreamDestroy(ctx->s_aux);
     }
+    for (int r = 0; r < 2; ++r) if (ctx->stage_ready[r]) for (int k = 0; k < b200_ctx::kStage; ++k) { cudaFreeHost(ctx->stage[r][k]); cudaEventDestroy(ctx->stage_ev[r][k]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -144,4 +148,93 @@ extern "C" int b200_copy_d2h(b200_ctx* ctx, void* h_dst, const void* d_src, uint
 extern "C" int b200_memset(b200_ctx* ctx, void* d_dst, int value, uint64_t bytes) {
     B200_ENTER(ctx);
     CUDA_TRY(cudaMemsetAsync(d_dst, value, bytes, ctx->stream)); return B200_OK;
+}
+
+
+// ---------------------------------------------------------------- pageable host buffers
+bool b200_is_pageable(const void* h_ptr) {
+    if (!h_ptr) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, h_ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+namespace {
+const uint64_t kStageMin = [] { const char* e = getenv("B200_STAGE_MIN_BYTES"); return e ? (uint64_t)atoll(e) : (4ull << 20); }();
+const int kCopyThreads = [] { const char* e = getenv("B200_COPY_THREADS"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 32 ? v : 4; }();
+
+void par_memcpy(void* dst, const void* src, size_t bytes) {
+    const int nt = bytes >= (2u << 20) ? kCopyThreads : 1;
+    if (nt == 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+    for (int t = 1; t < nt; ++t) {
+        const size_t o = (size_t)t * per;
+        if (o >= bytes) break;
+        const size_t len = o + per < bytes ? per : bytes - o;
+        th.emplace_back([=] { memcpy(static_cast<uint8_t*>(dst) + o, static_cast<const uint8_t*>(src) + o, len); });
+    }
+    memcpy(dst, src, per < bytes ? per : bytes);
+    for (auto& t : th) t.join();
+}
+
+int stage_init(b200_ctx* ctx, int ring) {
+    if (ctx->stage_ready[ring]) return B200_OK;
+    for (int k = 0; k < b200_ctx::kStage; ++k) {
+        CUDA_TRY(cudaMallocHost(&ctx->stage[ring][k], b200_ctx::kStageBytes));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->stage_ev[ring][k], cudaEventDisableTiming));
+    }
+    ctx->stage_ready[ring] = true;
+    return B200_OK;
+}
+}  // namespace
+
+int b200_copy_in(b200_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes, cudaStream_t st) {
+    if (bytes == 0) return B200_OK;
+    if (bytes < kStageMin || !b200_is_pageable(h_src)) { CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st)); return B200_OK; }
+    B200_TRY(stage_init(ctx, 0));
+    const size_t S = b200_ctx::kStageBytes;
+    uint64_t k = 0;
+    for (uint64_t off = 0; off < bytes; off += S, ++k) {
+        const int slot = (int)(k % b200_ctx::kStage);
+        const size_t len = off + S < bytes ? S : (size_t)(bytes - off);
+        if (k >= (uint64_t)b200_ctx::kStage) CUDA_TRY(cudaEventSynchronize(ctx->stage_ev[0][slot]));   // its previous piece has left the bounce buffer
+        par_memcpy(ctx->stage[0][slot], static_cast<const uint8_t*>(h_src) + off, len);
+        CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(d_dst) + off, ctx->stage[0][slot], len, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(ctx->stage_ev[0][slot], st));
+    }
+    // the bounce buffers still hold the last pieces: the next call's first cudaEventSynchronize would not know, so wait here
+    for (int slot = 0; slot < b200_ctx::kStage; ++slot) if ((uint64_t)slot < k) CUDA_TRY(cudaEventSynchronize(ctx->stage_ev[0][slot]));
+    return B200_OK;
+}
+
+int b200_copy_out(b200_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes, cudaStream_t st) {
+    if (bytes == 0) return B200_OK;
+    if (bytes < kStageMin || !b200_is_pageable(h_dst)) {
+        CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return B200_OK;
+    }
+    B200_TRY(stage_init(ctx, 1));
+    const size_t S = b200_ctx::kStageBytes;
+    const uint64_t npieces = (bytes + S - 1) / S;
+    // piece k is on the bus while piece k - 1 is copied out of its bounce buffer by the host threads
+    for (uint64_t k = 0; k <= npieces; ++k) {
+        if (k < npieces) {
+            const int slot = (int)(k % b200_ctx::kStage);
+            const uint64_t off = k * S;
+            const size_t len = off + S < bytes ? S : (size_t)(bytes - off);
+            CUDA_TRY(cudaMemcpyAsync(ctx->stage[1][slot], static_cast<const uint8_t*>(d_src) + off, len, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaEventRecord(ctx->stage_ev[1][slot], st));
+        }
+        if (k >= 1) {
+            const uint64_t j = k - 1;
+            const int slot = (int)(j % b200_ctx::kStage);
+            const uint64_t off = j * S;
+            const size_t len = off + S < bytes ? S : (size_t)(bytes - off);
+            CUDA_TRY(cudaEventSynchronize(ctx->stage_ev[1][slot]));
+            par_memcpy(static_cast<uint8_t*>(h_dst) + off, ctx->stage[1][slot], len);
+        }
+    }
+    return B200_OK;
 }

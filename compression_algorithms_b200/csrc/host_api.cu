@@ -1,7 +1,10 @@
 // Host-buffer entry points: H2D -> *_dev -> D2H on the context's stream. These are
 // what the reference-named shims (csrc/shims/*.c) and bench.py's end-to-end leg call.
 // Device staging buffers live in the context's scratch slots 8..13 and are reused.
+#include <atomic>
 #include <cstdlib>
+#include <string>
+#include <thread>
 #include "common.cuh"
 #include "../../include/b200comp.h"
 
@@ -11,27 +14,6 @@ inline uint64_t lz_cap(int variant, uint64_t n, uint64_t nblocks) {
     return (variant == B200_LZ_DEFLATE ? 2 * n + 2 * nblocks : n + n / 8 + 8 * nblocks) + 64;
 }
 
-// A caller's malloc'd (pageable) buffer is copied by the driver through small bounce buffers at a few GB/s. Large
-// pageable buffers are page-locked for the duration of the call instead (cudaHostRegister), so that the chunked
-// copies run at PCIe speed and really overlap the kernels; pinned buffers (b200_host_alloc) are left alone.
-struct HostPin {
-    void* p = nullptr;
-    explicit HostPin(const void* ptr, uint64_t bytes, bool read_only) {
-        static const uint64_t min_bytes = [] { const char* e = getenv("B200_PIN_MIN_BYTES"); return e ? (uint64_t)atoll(e) : (16ull << 20); }();
-        if (!ptr || bytes < min_bytes) return;
-        cudaPointerAttributes a;
-        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return; }
-        if (a.type != cudaMemoryTypeUnregistered) return;
-        unsigned flags = cudaHostRegisterDefault;
-        if (read_only) flags |= cudaHostRegisterReadOnly;
-        cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, flags);
-        if (e != cudaSuccess && read_only) { cudaGetLastError(); e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault); }
-        if (e == cudaSuccess) p = const_cast<void*>(ptr); else cudaGetLastError();   // not fatal: the copy just stays pageable
-    }
-    ~HostPin() { if (p) cudaHostUnregister(p); }
-    HostPin(const HostPin&) = delete;
-    HostPin& operator=(const HostPin&) = delete;
-};
 }  // namespace
 
 extern "C" uint64_t b200_lz77_max_bytes(int variant, uint64_t n, uint64_t block_size) {
@@ -65,7 +47,6 @@ extern "C" int b200_lz77_compress_host(b200_ctx* ctx, int variant, const uint8_t
     const uint64_t nblocks = (n + bs - 1) / bs;
     const uint64_t cap = lz_cap(variant, n, nblocks);
     B200_TRY(b200_pipe_init(ctx));
-    HostPin pin_in(h_in, n, true), pin_out(h_out, out_capacity < cap ? out_capacity : cap, false);
     const uint64_t per = lz_chunk_blocks(ctx, nblocks);
     const uint64_t nchunks = (nblocks + per - 1) / per;
     uint8_t *d_in, *d_out; uint64_t* d_idx; uint64_t* pin;
@@ -76,14 +57,9 @@ extern "C" int b200_lz77_compress_host(b200_ctx* ctx, int variant, const uint8_t
     uint64_t* d_sizes = d_idx;                       // [nblocks]
     uint64_t* d_boff = d_idx + nblocks;              // per chunk: blocks_c + 1 chunk-local offsets
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));    // scratch and pinned staging are free again
-    // 1. all input copies are queued at once; a chunk's kernels wait only for their own chunk
-    for (uint64_t c = 0; c < nchunks; ++c) {
-        const uint64_t o = c * per * bs, len = o + per * bs < n ? per * bs : n - o;
-        CUDA_TRY(cudaMemcpyAsync(d_in + o, h_in + o, len, cudaMemcpyHostToDevice, ctx->s_in));
-        CUDA_TRY(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
-    }
-    // 2. kernels, chunk by chunk, each into its own worst-case slot of d_out
-    for (uint64_t c = 0; c < nchunks; ++c) {
+    // Steps 1 + 2 for one chunk: its input copy (through the pinned bounce ring when the caller's buffer is pageable)
+    // and its kernels, into the chunk's own worst-case slot of d_out
+    auto feed_chunk = [&](uint64_t c) -> int {
         const uint64_t b0 = c * per, nb = b0 + per < nblocks ? per : nblocks - b0;
         const uint64_t o = b0 * bs, len = o + nb * bs < n ? nb * bs : n - o;
         const uint64_t slot = lz_cap(variant, b0 * bs, b0) + 128 * c;  // worst cases are additive over chunks; 128 covers the rounding
@@ -98,19 +74,54 @@ extern "C" int b200_lz77_compress_host(b200_ctx* ctx, int variant, const uint8_t
         if (rc2 == B200_OK && cudaMemcpyAsync(pin + 8 + c, d_boff + b0 + c + nb, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc2 = B200_ERR_CUDA;   // chunk total
         if (rc2 == B200_OK && cudaEventRecord(ctx->ev_done[c], ctx->stream) != cudaSuccess) rc2 = B200_ERR_CUDA;
         ctx->stream = keep; ctx->bank = 0;
-        if (rc2 != B200_OK) { if (rc2 == B200_ERR_CUDA) B200_SET_ERR("lz77 compress: stream/event call failed: %s", cudaGetErrorString(cudaGetLastError())); return rc2; }
+        if (rc2 == B200_ERR_CUDA) B200_SET_ERR("lz77 compress: stream/event call failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return rc2;
+    };
+    const bool pageable = (b200_is_pageable(h_in) || b200_is_pageable(h_out)) && n >= (8u << 20);
+    std::atomic<uint64_t> fed(0);          // chunks whose kernels are enqueued
+    std::atomic<int> feed_rc(B200_OK);
+    std::string feed_err;
+    std::thread feeder;
+    if (!pageable) {
+        // 1. all input copies are queued at once; a chunk's kernels wait only for their own chunk
+        for (uint64_t c = 0; c < nchunks; ++c) {
+            const uint64_t o = c * per * bs, len = o + per * bs < n ? per * bs : n - o;
+            CUDA_TRY(cudaMemcpyAsync(d_in + o, h_in + o, len, cudaMemcpyHostToDevice, ctx->s_in));
+            CUDA_TRY(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+        }
+        // 2. kernels, chunk by chunk
+        for (uint64_t c = 0; c < nchunks; ++c) B200_TRY(feed_chunk(c));
+        fed.store(nchunks);
+    } else {
+        // malloc'd caller buffers (an unmodified reference driver): a helper thread feeds chunk after chunk through the
+        // bounce ring and enqueues its kernels, this thread drains the finished chunks through the other ring
+        feeder = std::thread([&] {
+            cudaSetDevice(ctx->device);
+            for (uint64_t c = 0; c < nchunks; ++c) {
+                const uint64_t o = c * per * bs, len = o + per * bs < n ? per * bs : n - o;
+                int rc2 = b200_copy_in(ctx, d_in + o, h_in + o, len, ctx->s_in);
+                if (rc2 == B200_OK && cudaEventRecord(ctx->ev_in[c], ctx->s_in) != cudaSuccess) rc2 = B200_ERR_CUDA;
+                if (rc2 == B200_OK) rc2 = feed_chunk(c);
+                if (rc2 != B200_OK) { feed_err = b200_last_error(); feed_rc.store(rc2); fed.store(nchunks); return; }
+                fed.store(c + 1);
+            }
+        });
     }
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{feeder};
     // 3. as each chunk finishes, its tokens go home while later chunks are still being compressed
     uint64_t total = 0;
     int rc = B200_OK;
     for (uint64_t c = 0; c < nchunks; ++c) {
         const uint64_t b0 = c * per, nb = b0 + per < nblocks ? per : nblocks - b0;
         const uint64_t slot = lz_cap(variant, b0 * bs, b0) + 128 * c;
+        while (fed.load() <= c) std::this_thread::yield();
+        if (feed_rc.load() != B200_OK) { B200_SET_ERR("%s", feed_err.c_str()); return feed_rc.load(); }
         CUDA_TRY(cudaEventSynchronize(ctx->ev_done[c]));
         const uint64_t tc = pin[8 + c];
         if (total + tc > out_capacity) { rc = B200_ERR_CAPACITY; total += tc; continue; }
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[c], 0));
-        CUDA_TRY(cudaMemcpyAsync(h_out + total, d_out + slot, tc, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (pageable) B200_TRY(b200_copy_out(ctx, h_out + total, d_out + slot, tc, ctx->s_out));
+        else CUDA_TRY(cudaMemcpyAsync(h_out + total, d_out + slot, tc, cudaMemcpyDeviceToHost, ctx->s_out));
         if (h_block_sizes) CUDA_TRY(cudaMemcpyAsync(h_block_sizes + b0, d_sizes + b0, nb * 8, cudaMemcpyDeviceToHost, ctx->s_out));
         if (h_block_off) CUDA_TRY(cudaMemcpyAsync(h_block_off + b0, d_boff + b0 + c, nb * 8, cudaMemcpyDeviceToHost, ctx->s_out));
         pin[8 + nchunks + c] = total;                // base of this chunk in the final stream
@@ -151,7 +162,6 @@ extern "C" int b200_lz77_decompress_host(b200_ctx* ctx, int variant, const uint8
         }
     }
     B200_TRY(b200_pipe_init(ctx));
-    HostPin pin_in(h_stream, stream_bytes, true), pin_out(h_out, n, false);
     const uint64_t per = lz_chunk_blocks(ctx, nblocks);
     const uint64_t nchunks = (nblocks + per - 1) / per;
     uint8_t *d_stream, *d_out; uint64_t* d_idx;
@@ -161,14 +171,16 @@ extern "C" int b200_lz77_decompress_host(b200_ctx* ctx, int variant, const uint8
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(d_idx, h_block_sizes, nblocks * 8, cudaMemcpyHostToDevice, ctx->s_in));
     CUDA_TRY(cudaMemcpyAsync(d_idx + nblocks, h_block_off, (nblocks + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-    for (uint64_t c = 0; c < nchunks; ++c) {
+    const bool pageable = (b200_is_pageable(h_stream) || b200_is_pageable(h_out)) && n >= (8u << 20);
+    auto chunk_in = [&](uint64_t c) -> int {     // the chunk's tokens to the device (bounce ring for a pageable source)
         const uint64_t b0 = c * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
         const uint64_t s0 = h_block_off[b0], s1 = b1 < nblocks ? h_block_off[b1] : stream_bytes;
-        if (s1 < s0 || s1 > stream_bytes) { B200_SET_ERR("lz77: block offsets are not monotone / exceed the stream"); return B200_ERR_FORMAT; }
-        CUDA_TRY(cudaMemcpyAsync(d_stream + s0, h_stream + s0, s1 - s0, cudaMemcpyHostToDevice, ctx->s_in));
+        if (pageable) B200_TRY(b200_copy_in(ctx, d_stream + s0, h_stream + s0, s1 - s0, ctx->s_in));
+        else CUDA_TRY(cudaMemcpyAsync(d_stream + s0, h_stream + s0, s1 - s0, cudaMemcpyHostToDevice, ctx->s_in));
         CUDA_TRY(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
-    }
-    for (uint64_t c = 0; c < nchunks; ++c) {
+        return B200_OK;
+    };
+    auto chunk_kernels = [&](uint64_t c) -> int {
         const uint64_t b0 = c * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
         const uint64_t o = b0 * bs, len = b1 * bs < n ? (b1 - b0) * bs : n - o;
         // a chunk's decode is bound by the serial token chain of its blocks (about 4 ms whatever the chunk size), not
@@ -180,10 +192,40 @@ extern "C" int b200_lz77_decompress_host(b200_ctx* ctx, int variant, const uint8
         if (rc == B200_OK) rc = b200_lz77_decode_dev(ctx, variant, d_stream, d_idx + nblocks + b0, d_idx + b0, len, bs, d_out + o);
         if (rc == B200_OK && cudaEventRecord(ctx->ev_done[c], ctx->stream) != cudaSuccess) rc = B200_ERR_CUDA;
         ctx->stream = keep;
-        if (rc != B200_OK) { if (rc == B200_ERR_CUDA) B200_SET_ERR("lz77 decompress: stream/event call failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
-        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[c], 0));
-        CUDA_TRY(cudaMemcpyAsync(h_out + o, d_out + o, len, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (rc == B200_ERR_CUDA) B200_SET_ERR("lz77 decompress: stream/event call failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return rc;
+    };
+    std::atomic<uint64_t> fed(0);
+    std::atomic<int> feed_rc(B200_OK);
+    std::string feed_err;
+    std::thread feeder;
+    if (!pageable) {
+        for (uint64_t c = 0; c < nchunks; ++c) B200_TRY(chunk_in(c));
+    } else {
+        feeder = std::thread([&] {
+            cudaSetDevice(ctx->device);
+            for (uint64_t c = 0; c < nchunks; ++c) {
+                int rc = chunk_in(c);
+                if (rc == B200_OK) rc = chunk_kernels(c);
+                if (rc != B200_OK) { feed_err = b200_last_error(); feed_rc.store(rc); fed.store(nchunks); return; }
+                fed.store(c + 1);
+            }
+        });
     }
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{feeder};
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const uint64_t b0 = c * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
+        const uint64_t o = b0 * bs, len = b1 * bs < n ? (b1 - b0) * bs : n - o;
+        if (!pageable) B200_TRY(chunk_kernels(c));
+        else {
+            while (fed.load() <= c) std::this_thread::yield();
+            if (feed_rc.load() != B200_OK) { B200_SET_ERR("%s", feed_err.c_str()); return feed_rc.load(); }
+        }
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[c], 0));
+        if (pageable) B200_TRY(b200_copy_out(ctx, h_out + o, d_out + o, len, ctx->s_out));
+        else CUDA_TRY(cudaMemcpyAsync(h_out + o, d_out + o, len, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    if (feeder.joinable()) feeder.join();
     CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
     CUDA_TRY(cudaStreamSynchronize(ctx->s_aux));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -202,16 +244,16 @@ extern "C" int b200_huffman_compress_host(b200_ctx* ctx, const uint8_t* h_in, ui
     B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
     B200_TRY(b200_scratch(ctx, 11, cap * 4, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
-    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_in, h_in, n, ctx->stream));
     uint64_t total = 0; uint32_t worst = 0;
     B200_TRY(b200_huffman_encode_dev(ctx, d_in, n, block_size, d_words, cap, d_side, L.bytes, &total, &worst));
     if (h_total_words) *h_total_words = total;
     if (h_worst_status) *h_worst_status = worst;
     if (worst == 0) {
         if (total > words_capacity) { B200_SET_ERR("huffman: output needs %llu words, buffer has %llu", (unsigned long long)total, (unsigned long long)words_capacity); return B200_ERR_CAPACITY; }
-        CUDA_TRY(cudaMemcpyAsync(h_words, d_words, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        B200_TRY(b200_copy_out(ctx, h_words, d_words, total * 4, ctx->stream));
     }
-    if (h_side) CUDA_TRY(cudaMemcpyAsync(h_side, d_side, L.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_side) B200_TRY(b200_copy_out(ctx, h_side, d_side, L.bytes, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (worst) { B200_SET_ERR("huffman: input has a block the reference cannot encode (status %u)", worst); return B200_ERR_DOMAIN; }
     return B200_OK;
@@ -229,10 +271,10 @@ extern "C" int b200_huffman_decompress_host(b200_ctx* ctx, const uint32_t* h_wor
     B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_out)));
     B200_TRY(b200_scratch(ctx, 11, (total_words + 4) * 4, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
-    CUDA_TRY(cudaMemcpyAsync(d_words, h_words, total_words * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_side, h_side, L.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_words, h_words, total_words * 4, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_side, h_side, L.bytes, ctx->stream));
     B200_TRY(b200_huffman_decode_dev(ctx, d_words, total_words, d_side, L.bytes, n, block_size, d_out));
-    CUDA_TRY(cudaMemcpyAsync(h_out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_out, d_out, n, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
@@ -246,14 +288,14 @@ extern "C" int b200_huffman_decompress_serial_host(b200_ctx* ctx, const uint32_t
     B200_TRY(b200_scratch(ctx, 8, out_capacity + 64, reinterpret_cast<void**>(&d_out)));
     B200_TRY(b200_scratch(ctx, 11, (nwords + 4) * 4, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, 2048, reinterpret_cast<void**>(&d_tab)));
-    CUDA_TRY(cudaMemcpyAsync(d_words, h_words, nwords * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_tab, h_codes, 1024, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_tab + 1024, h_lens, 256, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_words, h_words, nwords * 4, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_tab, h_codes, 1024, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_tab + 1024, h_lens, 256, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(d_out, 0, out_capacity, ctx->stream));
     uint64_t cnt = 0;
     B200_TRY(b200_huffman_decode_serial_dev(ctx, d_words, nwords, buffer_size, reinterpret_cast<uint32_t*>(d_tab), d_tab + 1024,
                                             d_out, out_capacity, &cnt));
-    CUDA_TRY(cudaMemcpyAsync(h_out, d_out, cnt < out_capacity ? cnt : out_capacity, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_out, d_out, cnt < out_capacity ? cnt : out_capacity, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (h_count) *h_count = cnt;
     return B200_OK;
@@ -269,9 +311,9 @@ extern "C" int b200_huffman_tables_host(b200_ctx* ctx, const uint8_t* h_in, uint
     uint8_t *d_in, *d_side;
     B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
-    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_in, h_in, n, ctx->stream));
     B200_TRY(b200_huffman_tables_dev(ctx, d_in, n, block_size, d_side, L.bytes));
-    CUDA_TRY(cudaMemcpyAsync(h_side, d_side, L.off_block_bits, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_side, d_side, L.off_block_bits, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
@@ -293,15 +335,15 @@ extern "C" int b200_huffman_compress_codes_host(b200_ctx* ctx, const uint8_t* h_
     B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
     B200_TRY(b200_scratch(ctx, 11, cap * 4, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
-    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_in, h_in, n, ctx->stream));
     uint64_t total = 0; uint32_t worst = 0;
     B200_TRY(b200_huffman_encode_with_codes_dev(ctx, d_in, n, h_codes, h_lens, d_words, cap, d_side, L.bytes, &total, &worst));
     if (h_total_words) *h_total_words = total;
     if (h_worst_status) *h_worst_status = worst;
     if (worst) { B200_SET_ERR("huffman: a symbol of the input has no code (status %u)", worst); return B200_ERR_DOMAIN; }
     if (total > words_capacity) { B200_SET_ERR("huffman: output needs %llu words, buffer has %llu", (unsigned long long)total, (unsigned long long)words_capacity); return B200_ERR_CAPACITY; }
-    CUDA_TRY(cudaMemcpyAsync(h_words, d_words, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (h_side) CUDA_TRY(cudaMemcpyAsync(h_side, d_side, L.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_words, d_words, total * 4, ctx->stream));
+    if (h_side) B200_TRY(b200_copy_out(ctx, h_side, d_side, L.bytes, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
@@ -333,7 +375,7 @@ extern "C" int b200_fse_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64
     B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
     B200_TRY(b200_scratch(ctx, 11, cap * 8, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
-    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_in, h_in, n, ctx->stream));
     uint64_t total = 0;
     B200_TRY(b200_fse_encode_dev(ctx, d_in, n, block_size, seg_size, d_words, cap, d_side, L.bytes, &total));
     const uint64_t o_norm = 8, o_bits = o_norm + w8(L.nblocks * 512), o_stream = o_bits + w8(L.nsegs * 4);
@@ -342,9 +384,9 @@ extern "C" int b200_fse_compress_host(b200_ctx* ctx, const uint8_t* h_in, uint64
     const uint64_t hdr[8] = {FSE_MAGIC, n, bs_eff, seg_size, L.nblocks, L.nsegs, total, 0};
     memcpy(h_out, hdr, sizeof(hdr));
     if ((L.nsegs * 4) % 8) h_out[o_stream - 1] = 0;
-    CUDA_TRY(cudaMemcpyAsync(h_out + o_norm, d_side + L.off_norm, L.nblocks * 512, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(h_out + o_bits, d_side + L.off_seg_bits, L.nsegs * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(h_out + o_stream, d_words, total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_out + o_norm, d_side + L.off_norm, L.nblocks * 512, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_out + o_bits, d_side + L.off_seg_bits, L.nsegs * 4, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_out + o_stream, d_words, total * 8, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (h_total_words) *h_total_words = o_stream + total;
     return B200_OK;
@@ -389,15 +431,15 @@ extern "C" int b200_fse_decompress_host(b200_ctx* ctx, const uint64_t* h_contain
     B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_out)));
     B200_TRY(b200_scratch(ctx, 11, (total + 4) * 8, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
-    CUDA_TRY(cudaMemcpyAsync(d_side + L.off_norm, h_container + o_norm, nblocks * 512, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_side + L.off_seg_bits, h_container + o_bits, nsegs * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_words, h_container + o_stream, total * 8, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_side + L.off_norm, h_container + o_norm, nblocks * 512, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_side + L.off_seg_bits, h_container + o_bits, nsegs * 4, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_words, h_container + o_stream, total * 8, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(d_words + total, 0, 32, ctx->stream));
     B200_TRY(b200_fse_rebuild_index_dev(ctx, n, bs, seg, d_side, L.bytes));
     uint32_t bad = 0;
     B200_TRY(b200_fse_decode_dev(ctx, d_words, d_side, L.bytes, n, bs, seg, d_out, &bad));
     if (bad) { B200_SET_ERR("fse: %u corrupt segment streams", bad); return B200_ERR_FORMAT; }
-    CUDA_TRY(cudaMemcpyAsync(h_out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_out, d_out, n, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (h_n) *h_n = n;
     return B200_OK;
@@ -413,10 +455,10 @@ extern "C" int b200_fse_normalize_host(b200_ctx* ctx, const uint8_t* h_in, uint6
     uint8_t *d_in, *d_side;
     B200_TRY(b200_scratch(ctx, 8, n + 64, reinterpret_cast<void**>(&d_in)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
-    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_in, h_in, n, ctx->stream));
     B200_TRY(b200_fse_normalize_dev(ctx, d_in, n, 0, d_side, L.bytes));
-    if (h_freq) CUDA_TRY(cudaMemcpyAsync(h_freq, d_side + L.off_freq, 1024, cudaMemcpyDeviceToHost, ctx->stream));
-    if (h_norm) CUDA_TRY(cudaMemcpyAsync(h_norm, d_side + L.off_norm, 512, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_freq) B200_TRY(b200_copy_out(ctx, h_freq, d_side + L.off_freq, 1024, ctx->stream));
+    if (h_norm) B200_TRY(b200_copy_out(ctx, h_norm, d_side + L.off_norm, 512, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
@@ -440,7 +482,7 @@ extern "C" int b200_deflate_compress_host(b200_ctx* ctx, const uint8_t* h_in, ui
     B200_TRY(b200_scratch(ctx, 10, (2 * L.nblocks + 2) * 8, reinterpret_cast<void**>(&d_idx)));
     B200_TRY(b200_scratch(ctx, 11, cap * 4, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
-    CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_in, h_in, n, ctx->stream));
     uint64_t total = 0; uint32_t worst = 0;
     B200_TRY(b200_deflate_compress_dev(ctx, d_in, n, block_size, d_tok, tok_cap, d_idx, d_idx + L.nblocks, d_words, cap,
                                        d_side, L.bytes, &total, &worst));
@@ -448,8 +490,8 @@ extern "C" int b200_deflate_compress_host(b200_ctx* ctx, const uint8_t* h_in, ui
     if (h_worst_status) *h_worst_status = worst;
     if (worst) { B200_SET_ERR("deflate: a block needs a code longer than 32 bits (status %u)", worst); return B200_ERR_DOMAIN; }
     if (total > words_capacity) { B200_SET_ERR("deflate: output needs %llu words, buffer has %llu", (unsigned long long)total, (unsigned long long)words_capacity); return B200_ERR_CAPACITY; }
-    CUDA_TRY(cudaMemcpyAsync(h_words, d_words, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(h_side, d_side, L.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_words, d_words, total * 4, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_side, d_side, L.bytes, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }
@@ -468,10 +510,10 @@ extern "C" int b200_deflate_decompress_host(b200_ctx* ctx, const uint32_t* h_wor
     B200_TRY(b200_scratch(ctx, 9, tok_cap, reinterpret_cast<void**>(&d_tok)));
     B200_TRY(b200_scratch(ctx, 11, (total_words + 4) * 4, reinterpret_cast<void**>(&d_words)));
     B200_TRY(b200_scratch(ctx, 12, L.bytes, reinterpret_cast<void**>(&d_side)));
-    CUDA_TRY(cudaMemcpyAsync(d_words, h_words, total_words * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_side, h_side, L.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_words, h_words, total_words * 4, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_side, h_side, L.bytes, ctx->stream));
     B200_TRY(b200_deflate_decompress_dev(ctx, d_words, total_words, d_side, L.bytes, n, block_size, d_tok, d_out));
-    CUDA_TRY(cudaMemcpyAsync(h_out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_TRY(b200_copy_out(ctx, h_out, d_out, n, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }

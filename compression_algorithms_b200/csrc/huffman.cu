@@ -451,7 +451,7 @@ extern "C" int b200_huffman_encode_with_codes_dev(b200_ctx* ctx, const uint8_t* 
             if (nn >= 511) { B200_SET_ERR("huffman: the code table needs more than 511 tree nodes"); return B200_ERR_ARG; }
             kids[2 * v + c] = (int16_t)nn; kids[2 * nn] = -1; kids[2 * nn + 1] = 0; ++nn;
         }
-        CUDA_TRY(cudaMemcpyAsync(d_side + L.off_tree, kids, (size_t)nn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        B200_TRY(b200_copy_in(ctx, d_side + L.off_tree, kids, (size_t)nn * 4, ctx->stream));
     }
     const uint32_t tpb = (uint32_t)((L.chunks_per_block + TILE_CHUNKS - 1) / TILE_CHUNKS);
     byte_hist_kernel<<<tpb, 256, 0, ctx->stream>>>(d_in, n, eff_block(n, 0), tpb, reinterpret_cast<uint32_t*>(d_side + L.off_freq));
@@ -696,7 +696,7 @@ extern "C" int b200_zig_huffman_compress_host(b200_ctx* ctx, const uint8_t* h_in
     B200_TRY(b200_scratch(ctx, 12, LA.bytes, reinterpret_cast<void**>(&d_sideA)));
     // the read buffer as the reference sees it chunk by chunk: the data, and behind a short read what the previous
     // chunk left there (zero pages before the first chunk)
-    if (n) CUDA_TRY(cudaMemcpyAsync(d_aug, h_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) B200_TRY(b200_copy_in(ctx, d_aug, h_in, n, ctx->stream));
     {
         const uint64_t last = nz - 1, len_last = n - last * ZIG_CHUNK;
         if (last == 0) CUDA_TRY(cudaMemsetAsync(d_aug + len_last, 0, ZIG_CHUNK - len_last, ctx->stream));
@@ -757,7 +757,7 @@ extern "C" int b200_zig_huffman_compress_host(b200_ctx* ctx, const uint8_t* h_in
         memcpy(h_out + o, &hdr, 4); o += 4;
         if (pay) {
             if (o + pay > out_capacity) { B200_SET_ERR("zig huffman: output buffer too small"); return B200_ERR_CAPACITY; }
-            CUDA_TRY(cudaMemcpyAsync(h_out + o, reinterpret_cast<const uint8_t*>(d_words + bword[k]), pay, cudaMemcpyDeviceToHost, ctx->stream));
+            B200_TRY(b200_copy_out(ctx, h_out + o, reinterpret_cast<const uint8_t*>(d_words + bword[k]), pay, ctx->stream));
             o += pay;
         }
     }
@@ -829,7 +829,7 @@ extern "C" int b200_zig_huffman_decompress_host(b200_ctx* ctx, const uint8_t* h_
     uint64_t* d_off = reinterpret_cast<uint64_t*>(d_tab + ((nz * 511 * 4 + 7) & ~7ull));
     uint32_t* d_size = reinterpret_cast<uint32_t*>(d_off + nz);
     uint32_t* d_cnt = d_size + nz;
-    CUDA_TRY(cudaMemcpyAsync(d_pay, h_in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(b200_copy_in(ctx, d_pay, h_in, bytes, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(d_trees, trees.data(), nz * 511 * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(d_off, pay_off.data(), nz * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(d_size, pay_size.data(), nz * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -843,7 +843,7 @@ extern "C" int b200_zig_huffman_decompress_host(b200_ctx* ctx, const uint8_t* h_
     for (uint64_t k = 0; k < nz; ++k) {
         const uint64_t c = cnt[k] < ZIG_CHUNK ? cnt[k] : ZIG_CHUNK;
         if (o + c > out_capacity) { B200_SET_ERR("zig huffman: output needs more than %llu bytes", (unsigned long long)out_capacity); return B200_ERR_CAPACITY; }
-        if (c) CUDA_TRY(cudaMemcpyAsync(h_out + o, d_out + k * ZIG_CHUNK, c, cudaMemcpyDeviceToHost, ctx->stream));
+        if (c) B200_TRY(b200_copy_out(ctx, h_out + o, d_out + k * ZIG_CHUNK, c, ctx->stream));
         o += c;
     }
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

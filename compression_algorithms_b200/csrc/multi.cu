@@ -114,7 +114,7 @@ extern "C" int b200_lz77_compress_multi_host(b200_multi* m, int variant, const u
             RANK_TRY(b200_scratch(ctx, 8, len + 64, reinterpret_cast<void**>(&d_in)));
             RANK_TRY(b200_scratch(ctx, 9, cap + 64, reinterpret_cast<void**>(&d_out)));
             RANK_TRY(b200_scratch(ctx, 10, (2 * nb + 2) * 8, reinterpret_cast<void**>(&d_idx)));
-            RANK_CUDA(cudaMemcpyAsync(d_in, h_in + start, len, cudaMemcpyHostToDevice, ctx->stream));
+            RANK_TRY(b200_copy_in(ctx, d_in, h_in + start, len, ctx->stream));
             RANK_TRY(b200_lz77_encode_dev(ctx, variant, d_in, len, bs, d_out, cap, d_idx, d_idx + nb, &total));
         }
         // the one exchange of the path: every rank learns every shard's size
@@ -131,7 +131,7 @@ extern "C" int b200_lz77_compress_multi_host(b200_multi* m, int variant, const u
         totals[r] = sum;
         if (sum > out_capacity) { e.rc = B200_ERR_CAPACITY; e.msg = "lz77: the output buffer is smaller than the stream"; return; }
         if (len) {
-            RANK_CUDA(cudaMemcpyAsync(h_out + base, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+            RANK_TRY(b200_copy_out(ctx, h_out + base, d_out, total, ctx->stream));
             if (h_block_sizes) RANK_CUDA(cudaMemcpyAsync(h_block_sizes + b0, d_idx, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
             if (h_block_off) RANK_CUDA(cudaMemcpyAsync(h_block_off + b0, d_idx + nb, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
             RANK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -181,11 +181,11 @@ extern "C" int b200_lz77_decompress_multi_host(b200_multi* m, int variant, const
         std::vector<uint64_t> loc(nb + 1);
         for (uint64_t j = 0; j < nb; ++j) loc[j] = h_block_off[b0 + j] - s0;
         loc[nb] = s1 - s0;
-        RANK_CUDA(cudaMemcpyAsync(d_stream, h_stream + s0, s1 - s0, cudaMemcpyHostToDevice, ctx->stream));
+        RANK_TRY(b200_copy_in(ctx, d_stream, h_stream + s0, s1 - s0, ctx->stream));
         RANK_CUDA(cudaMemcpyAsync(d_idx, h_block_sizes + b0, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
         RANK_CUDA(cudaMemcpyAsync(d_idx + nb, loc.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
         RANK_TRY(b200_lz77_decode_dev(ctx, variant, d_stream, d_idx + nb, d_idx, len, bs, d_out));
-        RANK_CUDA(cudaMemcpyAsync(h_out + start, d_out, len, cudaMemcpyDeviceToHost, ctx->stream));
+        RANK_TRY(b200_copy_out(ctx, h_out + start, d_out, len, ctx->stream));
         RANK_CUDA(cudaStreamSynchronize(ctx->stream));
     };
     std::vector<std::thread> th;
