@@ -1,12 +1,13 @@
 #!/bin/bash
 # Runs ON THE GPU BOX (under gpurun): the bench line, the reference arm, the ncu launch lists and the ncu --set full
 # captures that tools/refresh_profiles.sh turns into profiles/. Usage: bash tools/evidence_run.sh <suffix>
-S=${1:-r01x}
+S=${1:-r02x}
 O=gpurun_out
 mkdir -p $O
 python bench.py > $O/${S}_bench.json 2> $O/${S}_bench.err || { echo "bench failed"; tail -5 $O/${S}_bench.err; exit 1; }
 python bench.py --impl reference --steps 2 --warmup 1 > $O/${S}_reference_arm.json 2> $O/${S}_reference_arm.err
 python tools/lz_stats.py 0 4 > $O/${S}_phase_cycles.txt 2>&1
+B200_LZ_V3=1 python tools/lz_stats3.py 0 4 1 > $O/${S}_v3_phase_cycles.txt 2>&1
 NCU="ncu --clock-control none"
 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/${S}_launches_deflate_100MB.csv python bench.py --bytes 100000000 --no-cpu --no-detail --steps 2 --warmup 1 > $O/${S}_ncu1.log 2>&1
 $NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file $O/${S}_launches_all_codecs_100MB.csv python tools/codec_run.py 100000000 1 > $O/${S}_ncu2.log 2>&1

@@ -2,26 +2,28 @@
 # Regenerates profiles/ from the files of the last evidence run under gpurun_out/ (suffix $1, e.g. r01d, and bench file $2).
 set -e
 cd "$(dirname "$0")/.."
-S=$1; B=$2
-cp gpurun_out/$B profiles/bench_r01_final.json
-[ -f gpurun_out/${S}_launches_deflate_100MB.csv ] && cp gpurun_out/${S}_launches_deflate_100MB.csv profiles/r01_launches_deflate_100MB.csv
-[ -f gpurun_out/${S}_launches_all_codecs_100MB.csv ] && cp gpurun_out/${S}_launches_all_codecs_100MB.csv profiles/r01_launches_all_codecs_100MB.csv
+S=$1; B=$2; R0=${3:-r02}   # R0: round prefix of the files written to profiles/
+cp gpurun_out/$B profiles/bench_${R0}_final.json
+[ -f gpurun_out/${S}_launches_deflate_100MB.csv ] && cp gpurun_out/${S}_launches_deflate_100MB.csv profiles/${R0}_launches_deflate_100MB.csv
+[ -f gpurun_out/${S}_launches_all_codecs_100MB.csv ] && cp gpurun_out/${S}_launches_all_codecs_100MB.csv profiles/${R0}_launches_all_codecs_100MB.csv
 R=gpurun_out/prof_lz77_${S}.ncu-rep
-ncu -i $R -k regex:lz77_v2 --page details > profiles/r01_lz77_v2_ncu_details.txt 2>/dev/null
-ncu -i $R -k regex:lz77_v2 --page raw --csv > profiles/r01_lz77_v2_ncu_raw.csv 2>/dev/null
-ncu -i $R -k regex:lz77_decode_units --page details > profiles/r01_lz77_decode_units_ncu_details.txt 2>/dev/null
-NCU_KERNEL=lz77_decode_units python tools/ncu_lines.py $R 25 > profiles/r01_lz77_decode_units_ncu_hot_lines.txt
-NCU_KERNEL=lz77_v2 python tools/ncu_phases.py $R > profiles/r01_lz77_v2_ncu_phases.txt
-NCU_KERNEL=lz77_v2 python tools/ncu_lines.py $R 40 > profiles/r01_lz77_v2_ncu_hot_lines.txt
-(python tools/ncu_kernel_summary.py $R; echo; [ -f gpurun_out/prof_dfl_${S}.ncu-rep ] && { echo "# ---- deflate token entropy stage"; python tools/ncu_kernel_summary.py gpurun_out/prof_dfl_${S}.ncu-rep | tail -n +2; }; echo; echo "# ---- Huffman / FSE and the compaction kernels (earlier capture of this round; its lz77_v2 / lz77_decode / dfl rows are superseded by the ones above)"; python tools/ncu_kernel_summary.py gpurun_out/prof_all_codecs.ncu-rep | tail -n +2) > profiles/r01_all_kernels_ncu_summary.txt
-python - <<'PY'
+ncu -i $R -k regex:lz77_v2 --page details > profiles/${R0}_lz77_v2_ncu_details.txt 2>/dev/null
+ncu -i $R -k regex:lz77_v2 --page raw --csv > profiles/${R0}_lz77_v2_ncu_raw.csv 2>/dev/null
+ncu -i $R -k regex:lz77_decode_units --page details > profiles/${R0}_lz77_decode_units_ncu_details.txt 2>/dev/null
+NCU_KERNEL=lz77_decode_units python tools/ncu_lines.py $R 25 > profiles/${R0}_lz77_decode_units_ncu_hot_lines.txt
+NCU_KERNEL=lz77_v2 python tools/ncu_phases.py $R > profiles/${R0}_lz77_v2_ncu_phases.txt
+NCU_KERNEL=lz77_v2 python tools/ncu_lines.py $R 40 > profiles/${R0}_lz77_v2_ncu_hot_lines.txt
+(python tools/ncu_kernel_summary.py $R; echo; [ -f gpurun_out/prof_dfl_${S}.ncu-rep ] && { echo "# ---- deflate token entropy stage"; python tools/ncu_kernel_summary.py gpurun_out/prof_dfl_${S}.ncu-rep | tail -n +2; }; echo; echo "# ---- Huffman / FSE and the compaction kernels (earlier capture of this round; its lz77_v2 / lz77_decode / dfl rows are superseded by the ones above)"; python tools/ncu_kernel_summary.py gpurun_out/prof_all_codecs.ncu-rep | tail -n +2) > profiles/${R0}_all_kernels_ncu_summary.txt
+R0=$R0 python - <<'PY'
 import csv, json
-rows=list(csv.reader(open('profiles/r01_lz77_v2_ncu_raw.csv')))
+import os
+R0=os.environ.get('R0','r02')
+rows=list(csv.reader(open('profiles/%s_lz77_v2_ncu_raw.csv' % R0)))
 h,u,r=rows[0],rows[1],rows[2]
 def g(n):
     i=h.index(n); return float(r[i].replace(',',''))*{'byte':1,'Kbyte':1e3,'Mbyte':1e6,'Gbyte':1e9}[u[i]]
 rd,wr=g('dram__bytes_read.sum'),g('dram__bytes_write.sum')
-json.dump({"_source":"profiles/r01_lz77_v2_ncu_raw.csv (ncu --set full, one launch of lz77_v2_kernel<1> over a 100 000 000-byte enwik-shaped shard, 1 526 blocks of 64 KiB; final kernel of round 1)",
+json.dump({"_source":"profiles/%s_lz77_v2_ncu_raw.csv (ncu --set full, one launch of lz77_v2_kernel<1> over a 100 000 000-byte enwik-shaped shard, 1 526 blocks of 64 KiB)" % R0,
  "lz77_v2_kernel<1>":{"input_bytes":100000000,"dram_bytes_read":int(rd),"dram_bytes_write":int(wr),"dram_bytes_per_launch":int(rd+wr),"dram_bytes_per_input_byte":round((rd+wr)/1e8,3)}},open('profiles/roofline_traffic.json','w'),indent=1)
 PY
 python tools/sass_summary.py > /dev/null
