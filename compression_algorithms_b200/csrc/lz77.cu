@@ -427,6 +427,11 @@ inline uint64_t round16(uint64_t x) { return (x + 15) & ~(uint64_t)15; }
 
 bool lz77_v2_supported(uint64_t bs);
 int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
+                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok,
+                   const uint32_t* blist = nullptr, const uint32_t* bcount = nullptr);
+// deflate variant, blocks of at most 65536 bytes (two expiry phases): cluster-local placement by slot sweeps (lz77_v4.cu);
+// blocks it cannot take are listed and go through lz77_v2_launch
+int lz77_v4_launch(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
                    uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok);
 // blocks of at most 65536 bytes: occupancy-decided finds + lane-serial simulation of the mixed clusters (lz77_v3.cu)
 int lz77_v3_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
@@ -462,7 +467,8 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
     if (use_v2) {
         if (dbg_tok && bs > 65536) { B200_SET_ERR("lz77: token dump needs blocks <= 65536"); return B200_ERR_ARG; }
         B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
-        if (bs <= 65536 && getenv("B200_LZ_V3")) B200_TRY(lz77_v3_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
+        if (bs <= 65536 && variant == 1 && getenv("B200_LZ_V4")) B200_TRY(lz77_v4_launch(ctx, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
+        else if (bs <= 65536 && getenv("B200_LZ_V3")) B200_TRY(lz77_v3_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
         else B200_TRY(lz77_v2_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
         B200_TIMED_END(ctx);
     } else {

@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                                                              uint8_t* __restrict__ carry_all,
                                                              uint8_t* __restrict__ scratch, uint64_t stride,
                                                              uint64_t* __restrict__ block_sizes, uint64_t* __restrict__ block_bytes,
-                                                             uint32_t* __restrict__ dbg_tok) {
+                                                             uint32_t* __restrict__ dbg_tok,
+                                                             const uint32_t* __restrict__ blist, const uint32_t* __restrict__ bcount) {
     constexpr uint32_t W = Cfg<V>::W, MAXLEN = Cfg<V>::MAXLEN;
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* data = smem + OFF_DATA;
@@ -212,7 +213,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
     uint32_t* ccar = cs + MAXB;                                                   // [32768] compact slot of every carried position (NONE = none)
 
     uint32_t* dbg_stats = dbg_tok ? dbg_tok + (uint64_t)nblocks * MAXB : nullptr;   // [block][8 phase stamps + 32 warps x 4]
-    for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    // blist != nullptr: only the blocks the v4 kernel (lz77_v4.cu) handed back, listed in blist[0 .. *bcount)
+    const uint32_t nb_eff = blist ? *bcount : nblocks;
+    for (uint32_t bi = blockIdx.x; bi < nb_eff; bi += gridDim.x) {
+        const uint32_t b = blist ? blist[bi] : bi;
         const long long t_begin = CLK();
 #define PHASE_STAMP(k) do { if (DBG && dbg_stats && tid == 0) dbg_stats[(uint64_t)b * 136 + (k)] = (uint32_t)(clock64() - t_begin); } while (0)
         const uint8_t* bsrc = in + (uint64_t)b * bs;
@@ -975,7 +979,8 @@ bool lz77_v2_supported(uint64_t bs) { return bs <= (1ull << 31); }
 
 // scratch slots: 13 = lists, 14 = tok
 int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
-                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok) {
+                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok,
+                   const uint32_t* blist, const uint32_t* bcount) {
     static bool attr_done_dev[64] = {};   // the attribute is per device
     bool& attr_done = attr_done_dev[ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0];
     if (!attr_done) {
@@ -991,7 +996,7 @@ int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, 
     B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 13), (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&lists)));
     B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 14), (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&tok)));
     B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 15), bs > MAXB ? (size_t)grid * CARRY_BYTES + 64 : 64, reinterpret_cast<void**>(&carry)));
-#define LZ_V2_LAUNCH(V, D) lz77_v2_kernel<V, D><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, lists, tok, carry, scratch, stride, d_block_sizes, block_bytes, dbg_tok)
+#define LZ_V2_LAUNCH(V, D) lz77_v2_kernel<V, D><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, lists, tok, carry, scratch, stride, d_block_sizes, block_bytes, dbg_tok, blist, bcount)
     if (dbg_tok) { if (variant == 0) LZ_V2_LAUNCH(0, true); else LZ_V2_LAUNCH(1, true); }
     else { if (variant == 0) LZ_V2_LAUNCH(0, false); else LZ_V2_LAUNCH(1, false); }
     CUDA_TRY(cudaGetLastError());

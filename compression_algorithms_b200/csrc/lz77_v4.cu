@@ -1,0 +1,997 @@
+// LZ77 v4: the deflate-variant match finder (algorithms/deflate/lz77.c:44-174,199-280) for blocks of at most
+// 65536 bytes, slot-exact like v2 (lz77_v2.cu) but without a time-ordered table simulation.
+//
+// What makes it possible (DESIGN.md "LZ77 v4"):
+//  * A block of len <= 2 W positions has only TWO expiry phases. Entry i is live at time P iff i + W >= P
+//    (deflate/lz77.c:120-139 as lazy expiry), so while P <= W nothing is dead ("phase 1", entries 0..W), and an
+//    entry placed at P > W ("phase 2") outlives the block. Every slot therefore has at most two occupants:
+//    e1 (placed in phase 1, dead from e1 + W + 1 on) and e2 (placed in phase 2, never dead).
+//  * In the no-expiry occupancy (built with atomicOr probing exactly as in v2) clusters never interact, a
+//    cluster has as many entries as slots, and the atomicOr of P1 hands every entry a private slot of ITS OWN
+//    cluster. Scattering the entries to the rank of that slot groups them by cluster without any sort or partition.
+//  * Inside a cluster the sequential first-fit is a slot sweep: slot j goes to the EARLIEST entry that is still
+//    unplaced, whose home is at/before j and for which j is dead (phase 1: always; phase 2: arrival >= release
+//    time of e1[j]). Between two consecutive homes the candidates are a fixed time-ordered pool, so phase 1
+//    hands the next slots to the next pool entries, and phase 2 is the recurrence
+//    idx_j = max(idx_{j-1} + 1, lower_bound(pool, release_j)) = one prefix maximum (release times rise along a
+//    run of phase-1 slots because those were filled in time order).
+//  * find(p) only ever looks at the slots [home(p), slot(p)): all live at time p by construction, so the find is a
+//    bounded scan for the first occupant (e1 if still live, else e2) with p's pattern. No liveness test, no table.
+//  * Clusters of up to 8 entries (80 % of the non-trivial ones) are simulated by ONE thread in registers
+//    (liveness mask + FIFO expiry pointer); 9..64 by a warp, larger ones by a team of four warps, with the sweeps
+//    above; a cluster of one entry (a third of text positions) is a literal candidate and costs nothing.
+//  * Blocks this kernel does not take (a cluster touching slot 0 or the table end: the reference's early slot-0
+//    clear and the wrapping insert; a cluster above 16383 entries) are listed and run through lz77_v2_kernel.
+//
+// Phases per block (one persistent CTA of 1024 threads per SM):
+//   P0 load | P1 occupancy bitmap, claimed slot per position | P2 rank prefix, cluster-start flags
+//   P3 rank of the claimed slot -> (compact slot, displacement) per position; loners marked
+//   per chunk of <= 17408 compact slots: scatter entries into shared memory by compact slot, small clusters by
+//   threads, larger ones by warps / four-warp teams -> F(p) (u16, global, L2 resident)
+//   P5 token candidates (match extension) + greedy parse | P6 token emission   (as v2)
+#include "common.cuh"
+#include "../../include/b200comp.h"
+
+namespace {
+
+constexpr uint32_t SLOTS = 1u << 20;
+constexpr uint32_t GUARD_BITS = 65536u;
+constexpr uint32_t BM_WORDS = (SLOTS + GUARD_BITS) / 32;     // 34816
+constexpr uint32_t PRE_CHUNK = 8;
+constexpr uint32_t PRE_N = BM_WORDS / PRE_CHUNK;             // 4352
+constexpr uint32_t LONER = 0xFFFFFFFFu;
+constexpr uint32_t NONE16 = 0xFFFFu;
+constexpr uint32_t MAXB = 65536;
+constexpr uint32_t NTHREADS = 1024;
+constexpr uint32_t W = 1u << 15, MAXLEN = 31;
+constexpr uint32_t CH = 17408;                               // compact slots per chunk
+constexpr uint32_t TMIN = 256;                               // clusters above this: four-warp teams; LMAX+1 .. TMIN: one warp
+constexpr uint32_t LMAX = 64;                                // largest cluster simulated by one lane (above 16: sorted by the warp first)
+constexpr uint32_t WL_CAP = 6656;                             // clusters of 2+ entries per chunk (work list entries)
+constexpr uint32_t CL_MAX = 16383;                           // largest cluster (home offsets are 14 bits)
+constexpr uint32_t PLACED = 0x80000000u, ISHOME = 0x40000000u;
+
+constexpr uint32_t OFF_DATA = 0;
+constexpr uint32_t SZ_DATA = MAXB + 128;
+constexpr uint32_t OFF_BIG = OFF_DATA + SZ_DATA;
+constexpr uint32_t SZ_BIG = BM_WORDS * 4;                    // 139264: bitmap | S + E1 + E2 | adv + exit
+constexpr uint32_t OFF_PRE = OFF_BIG + SZ_BIG;
+constexpr uint32_t SZ_PRE = PRE_N * 4 + 16;                  // rank prefix (u16 per 4 words) | work queues | chunk entry / offsets
+constexpr uint32_t OFF_FLAGS = OFF_PRE + SZ_PRE;
+constexpr uint32_t SZ_FLAGS = 8192 + 64;                     // one bit per compact slot: starts a cluster (+ sentinel)
+constexpr uint32_t OFF_MISC = OFF_FLAGS + SZ_FLAGS;
+constexpr uint32_t SZ_MISC = 1792;
+constexpr uint32_t SMEM_BYTES = OFF_MISC + SZ_MISC;
+static_assert(SMEM_BYTES <= 232448, "shared memory layout too large");
+static_assert(CH * 8 <= SZ_BIG, "chunk does not fit");
+static_assert(WL_CAP * 2 + 32 * 32 * 4 <= SZ_PRE, "work list + warp scratch do not fit");
+
+constexpr uint32_t PADDED = MAXB + (MAXB >> 6) * 4;          // 69632
+#define PADX(p) ((p) + (((p) >> 6) << 2))
+
+struct Misc {
+    uint32_t scan[34];
+    uint32_t p1_next, fallback, ce, pad0;
+    uint32_t ccnt[7], cbase[8], cfill[7], next_t, next_w, next_l;   // work list by size class: teams | 17..64 | 9..16 | 5..8 | 3..4 | 2
+    uint32_t tpick[8];
+    uint32_t tscr[8][2][4];      // cross-warp scan scratch of the eight four-warp teams
+    uint8_t  sexit[32][32];
+    uint8_t  sentry[36];
+};
+static_assert(sizeof(Misc) <= SZ_MISC, "misc region too small");
+
+__device__ __forceinline__ uint32_t sm_word(const uint8_t* data, uint32_t p) {
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(data + (p & ~3u));
+    return __funnelshift_r(a[0], a[1], (p & 3u) * 8);
+}
+
+__device__ __forceinline__ uint32_t match_len(const uint8_t* data, uint32_t m, uint32_t q) {
+    uint32_t l = 4;
+#pragma unroll 1
+    while (l < MAXLEN) {
+        const uint32_t x = sm_word(data, m + l) ^ sm_word(data, q + l);
+        if (x) { l += (uint32_t)(__ffs(x) - 1) >> 3; break; }
+        l += 4;
+    }
+    return l < MAXLEN ? l : MAXLEN;
+}
+
+__device__ __forceinline__ uint32_t bm_rank(const uint32_t* bm, const uint16_t* pre16, uint32_t s) {
+    const uint32_t wi = s >> 5, j = wi & 3u;
+    const uint4 q = *reinterpret_cast<const uint4*>(bm + (wi & ~3u));
+    const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+    uint32_t r = pre16[wi >> 2];
+    const uint32_t below = (1u << (s & 31)) - 1u;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) r += __popc(wd[k] & (k < j ? 0xFFFFFFFFu : (k == j ? below : 0u)));
+    return r;
+}
+
+// ---- clusters of 2 .. LMAX entries: ONE LANE per cluster, general FIFO expiry (any number of phases).
+// S[0 .. m): entry = position | compact home << 16, sorted by position; cstart = compact slot of the cluster's first slot.
+// PACKED (m <= 16): occupant of every slot / slot of every entry as 4-bit fields of two 64-bit registers;
+// otherwise (m <= 64) in the cluster's own E1 / E2 words.
+template <bool PACKED>
+__device__ __forceinline__ void lane_cluster(const uint32_t* S, uint16_t* E1x, uint16_t* E2x, uint32_t m, uint32_t cstart,
+                                             const uint8_t* data, uint16_t* fres) {
+    unsigned long long live = 0, slotpack = 0, occpack = 0;
+    uint32_t ex = 0;
+    for (uint32_t i = 0; i < m; ++i) {
+        const uint32_t e = S[i], p = e & 0xFFFFu, o = (e >> 16) - cstart;
+        while (ex < i) {                                     // entries expire in the order they came
+            const uint32_t tex = S[ex] & 0xFFFFu;
+            if (tex + W >= p) break;
+            const uint32_t sl = PACKED ? (uint32_t)(slotpack >> (4 * ex)) & 15u : (uint32_t)E2x[ex];
+            live &= ~(1ull << sl);
+            ++ex;
+        }
+        const uint32_t dead = o + (uint32_t)(__ffsll((long long)(~live >> o)) - 1);   // first dead slot at/after the home: p's own slot
+        uint32_t f = NONE16;
+        if (dead > o) {
+            const uint32_t w = sm_word(data, p);
+            for (uint32_t j = o; j < dead; ++j) {
+                const uint32_t y = PACKED ? (uint32_t)(occpack >> (4 * j)) & 15u : (uint32_t)E1x[j];
+                const uint32_t ty = S[y] & 0xFFFFu;
+                if (sm_word(data, ty) == w) { f = ty; break; }
+            }
+        }
+        fres[p] = (uint16_t)f;
+        live |= 1ull << dead;
+        if (PACKED) {
+            occpack = (occpack & ~(15ull << (4 * dead))) | ((unsigned long long)i << (4 * dead));
+            slotpack |= (unsigned long long)dead << (4 * i);
+        } else { E1x[dead] = (uint16_t)i; E2x[i] = (uint16_t)dead; }
+    }
+}
+
+__device__ __forceinline__ void lane_sort(uint32_t* S, uint32_t m) {   // insertion sort by position (m <= 16)
+    for (uint32_t i = 1; i < m; ++i) {
+        const uint32_t e = S[i];
+        uint32_t j = i;
+        while (j > 0) { const uint32_t f = S[j - 1]; if ((f & 0xFFFFu) <= (e & 0xFFFFu)) break; S[j] = f; --j; }
+        S[j] = e;
+    }
+}
+
+// one warp sorts up to 64 entries by position: bitonic network over two registers per lane
+// (the compact homes become offsets inside the cluster, so that no key equals the padding)
+__device__ __forceinline__ void warp_sort64(uint32_t* Sx, uint32_t m, uint32_t cstart) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t x0 = 0xFFFFFFFFu, x1 = 0xFFFFFFFFu;                                      // position in the high half
+    if (lane < m) { const uint32_t e = Sx[lane]; x0 = (e << 16) | ((e >> 16) - cstart); }
+    if (lane + 32 < m) { const uint32_t e = Sx[lane + 32]; x1 = (e << 16) | ((e >> 16) - cstart); }
+#pragma unroll
+    for (uint32_t k = 2; k <= 64; k <<= 1) {
+        if (k == 64) { const uint32_t lo = min(x0, x1), hi = max(x0, x1); x0 = lo; x1 = hi; }
+#pragma unroll
+        for (uint32_t j = (k == 64 ? 16 : k >> 1); j > 0; j >>= 1) {
+            const uint32_t y0 = __shfl_xor_sync(0xffffffffu, x0, j), y1 = __shfl_xor_sync(0xffffffffu, x1, j);
+            const bool lower = (lane & j) == 0;
+            const bool up0 = k < 32 ? (lane & k) == 0 : true;            // k == 32: register 0 ascending, register 1 descending
+            const bool up1 = k < 32 ? (lane & k) == 0 : (k == 64);
+            x0 = (lower == up0) ? min(x0, y0) : max(x0, y0);
+            x1 = (lower == up1) ? min(x1, y1) : max(x1, y1);
+        }
+    }
+    if (lane < m) Sx[lane] = __byte_perm(x0, 0, 0x1032);
+    if (lane + 32 < m) Sx[lane + 32] = __byte_perm(x1, 0, 0x1032);
+}
+
+// ---- team primitives (TEAM = 32: one warp; TEAM = 128: four warps on a named barrier)
+template <int TEAM> struct Team {
+    uint32_t tt;        // thread in team
+    uint32_t bar;       // named barrier (TEAM == 128)
+    uint32_t* scr;      // [2][4] cross-warp scratch (TEAM == 128)
+    uint32_t par;
+    __device__ __forceinline__ void sync() {
+        if (TEAM == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(TEAM) : "memory");
+    }
+    __device__ __forceinline__ uint32_t exscan(uint32_t v, uint32_t& tot) {
+        const uint32_t incl = warp_incl_scan_u32(v);
+        if (TEAM == 32) { tot = __shfl_sync(0xffffffffu, incl, 31); return incl - v; }
+        uint32_t* s = scr + par * 4; par ^= 1u;
+        if ((tt & 31u) == 31u) s[tt >> 5] = incl;
+        sync();
+        uint32_t off = 0, t = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < 4; ++w) { const uint32_t x = s[w]; if (w < (tt >> 5)) off += x; t += x; }
+        tot = t;
+        return off + incl - v;
+    }
+    // inclusive running maximum; last = maximum over the whole team
+    __device__ __forceinline__ int maxscan(int v, int& last) {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, d); if ((int)(tt & 31u) >= d) v = max(v, t); }
+        if (TEAM == 32) { last = __shfl_sync(0xffffffffu, v, 31); return v; }
+        int* s = reinterpret_cast<int*>(scr + par * 4); par ^= 1u;
+        if ((tt & 31u) == 31u) s[tt >> 5] = v;
+        sync();
+        int pre = -(1 << 30), t = -(1 << 30);
+#pragma unroll
+        for (uint32_t w = 0; w < 4; ++w) { const int x = s[w]; if (w < (tt >> 5)) pre = max(pre, x); t = max(t, x); }
+        last = t;
+        return max(v, pre);
+    }
+    __device__ __forceinline__ uint32_t tmin(uint32_t v) {
+        v = __reduce_min_sync(0xffffffffu, v);
+        if (TEAM == 32) return v;
+        uint32_t* s = scr + par * 4; par ^= 1u;
+        if ((tt & 31u) == 0u) s[tt >> 5] = v;
+        sync();
+        return min(min(s[0], s[1]), min(s[2], s[3]));
+    }
+};
+
+// ---- clusters above LMAX entries: slot sweeps, two expiry phases.
+// Sx[i]: entry i = position | home offset << 16 (14 bits) | PLACED; bit ISHOME of Sx[j]: slot j is some entry's home.
+// E1x[j] / E2x[j]: index of the phase-1 / phase-2 occupant of slot j (NONE16 = none). E2x[lo ..] also holds the
+// candidate pool of the sub-segment being swept (a slot's final value overwrites a pool entry no later slot needs).
+template <int TEAM>
+__device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t* E2x, uint32_t m, uint32_t cstart,
+                            const uint8_t* data, uint16_t* fres, uint32_t* scr) {
+    const uint32_t tt = T.tt;
+    for (uint32_t i = tt; i < m; i += TEAM) { const uint32_t e = Sx[i]; Sx[i] = (e & 0xFFFFu) | (((e >> 16) - cstart) << 16); }
+    T.sync();
+    // bitonic sort by position (all comparators ascending, so the virtual +inf padding behind m never moves)
+    uint32_t P = 2; while (P < m) P <<= 1;
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        const uint32_t half = k >> 1;
+        for (uint32_t idx = tt; idx < (P >> 1); idx += TEAM) {
+            const uint32_t l = ((idx & ~(half - 1u)) << 1) | (idx & (half - 1u));
+            const uint32_t r = l ^ (k - 1u);
+            if (r < m) { const uint32_t a = Sx[l], b = Sx[r]; if ((a & 0xFFFFu) > (b & 0xFFFFu)) { Sx[l] = b; Sx[r] = a; } }
+        }
+        T.sync();
+        for (uint32_t j = k >> 2; j >= 1; j >>= 1) {
+            for (uint32_t idx = tt; idx < (P >> 1); idx += TEAM) {
+                const uint32_t l = ((idx & ~(j - 1u)) << 1) | (idx & (j - 1u));
+                const uint32_t r = l + j;
+                if (r < m) { const uint32_t a = Sx[l], b = Sx[r]; if ((a & 0xFFFFu) > (b & 0xFFFFu)) { Sx[l] = b; Sx[r] = a; } }
+            }
+            T.sync();
+        }
+    }
+    for (uint32_t i = tt; i < m; i += TEAM) atomicOr(&Sx[(Sx[i] >> 16) & 0x3FFFu], ISHOME);
+    T.sync();
+    uint32_t n1;                                             // phase-1 entries: positions 0 .. W
+    { uint32_t a = 0, b = m; while (a < b) { const uint32_t mid = (a + b) >> 1; if ((Sx[mid] & 0xFFFFu) <= W) a = mid + 1; else b = mid; } n1 = a; }
+    auto next_home = [&](uint32_t x) -> uint32_t {
+        for (uint32_t base = x + 1; base < m; base += TEAM) {
+            const uint32_t j = base + tt;
+            const uint32_t v = (j < m && (Sx[j] & ISHOME)) ? j : m;
+            const uint32_t r = T.tmin(v);
+            if (r < m) return r;
+        }
+        return m;
+    };
+    // find of the entry at position p (pattern of p, home o) that got slot j: first occupant of [o, j) with p's pattern.
+    // Every slot of that range is live at time p (phase 1: by an earlier phase-1 entry; phase 2: by e1 if it has not
+    // expired, else by e2). A few slots by the lane itself, the rest of a long range 32 slots per step by its warp.
+    auto occ_pos = [&](uint32_t jj, uint32_t p, bool ph2) -> uint32_t {
+        const uint32_t y1 = E1x[jj];
+        if (!ph2) return Sx[y1] & 0xFFFFu;
+        if (y1 != NONE16) { const uint32_t ty = Sx[y1] & 0xFFFFu; if (ty + W >= p) return ty; }
+        const uint32_t y2 = E2x[jj];
+        return y2 == NONE16 ? NONE16 : (Sx[y2] & 0xFFFFu);   // (a live slot always has an occupant)
+    };
+    auto find = [&](bool active, uint32_t o, uint32_t j, uint32_t p, bool ph2) -> uint32_t {
+        uint32_t f = NONE16, cur = o, w = 0;
+        if (active && o < j) {
+            w = sm_word(data, p);
+            const uint32_t lim = o + 6 < j ? o + 6 : j;
+            for (; cur < lim; ++cur) {
+                const uint32_t ty = occ_pos(cur, p, ph2);
+                if (ty != NONE16 && sm_word(data, ty) == w) { f = ty; break; }
+            }
+        }
+        uint32_t lm = __ballot_sync(0xffffffffu, active && f == NONE16 && cur < j);
+        while (lm) {
+            const int srcl = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const uint32_t bc = __shfl_sync(0xffffffffu, cur, srcl), bj = __shfl_sync(0xffffffffu, j, srcl);
+            const uint32_t bp = __shfl_sync(0xffffffffu, p, srcl), bw = __shfl_sync(0xffffffffu, w, srcl);
+            uint32_t res = NONE16;
+            for (uint32_t base = bc; base < bj; base += 32) {
+                const uint32_t sl = base + (tt & 31u);
+                uint32_t ty = NONE16;
+                if (sl < bj) ty = occ_pos(sl, bp, ph2);
+                const uint32_t hm = __ballot_sync(0xffffffffu, ty != NONE16 && sm_word(data, ty) == bw);
+                if (hm) { res = __shfl_sync(0xffffffffu, ty, __ffs(hm) - 1); break; }
+            }
+            if ((int)(tt & 31u) == srcl) f = res;
+        }
+        return f;
+    };
+    // ---- clusters whose entries of either phase fit 32 x 32 bits: ONE warp, the candidate pool as a bit mask per lane
+    // (lane l: entries 32 l .. 32 l + 31 of the phase, in time order). "eligible" = unplaced and home at/before the segment;
+    // a sub-segment ranks / selects in the mask as it was at its start (the pool of the recurrence is fixed), the slots it
+    // hands out are cleared through 32 words of scratch. No compaction, no barriers.
+    if (n1 <= 1024u && m - n1 <= 1024u) {
+        if (TEAM != 32 && tt >= 32u) return;
+        const uint32_t lane = tt;
+        auto next_home_w = [&](uint32_t x) -> uint32_t {
+            for (uint32_t base = x + 1; base < m; base += 32) {
+                const uint32_t j = base + lane;
+                const uint32_t r = __reduce_min_sync(0xffffffffu, (j < m && (Sx[j] & ISHOME)) ? j : m);
+                if (r < m) return r;
+            }
+            return m;
+        };
+        for (uint32_t ph = 0; ph < 2; ++ph) {
+            const uint32_t ebase = ph ? n1 : 0u, cntp = ph ? m - n1 : n1;
+            uint16_t* Ex = ph ? E2x : E1x;
+            if (cntp == 0) {
+                for (uint32_t j = lane; j < m; j += 32) Ex[j] = (uint16_t)NONE16;
+                __syncwarp();
+                continue;
+            }
+            uint32_t elig = 0, pend = 0;
+            for (uint32_t b0 = 0; b0 < 32; ++b0) {
+                const uint32_t bq = (b0 + lane) & 31u, g = 32u * lane + bq;     // rotated: no bank conflicts
+                if (g < cntp) { if (((Sx[ebase + g] >> 16) & 0x3FFFu) == 0u) elig |= 1u << bq; else pend |= 1u << bq; }
+            }
+            uint32_t x = 0;
+            while (x < m) {
+                const uint32_t xe = next_home_w(x);
+                if (x > 0 && __any_sync(0xffffffffu, pend != 0u)) {       // entries whose home the sweep has reached join the pool
+                    uint32_t pb = pend;
+                    while (pb) {
+                        const uint32_t bq = (uint32_t)(__ffs(pb) - 1);
+                        pb &= pb - 1;
+                        if (((Sx[ebase + 32u * lane + bq] >> 16) & 0x3FFFu) <= x) { elig |= 1u << bq; pend &= ~(1u << bq); }
+                    }
+                }
+                uint32_t used = xe;
+                if (ph) { uint32_t a = x, b = xe; while (a < b) { const uint32_t mid = (a + b) >> 1; if (E1x[mid] != NONE16) a = mid + 1; else b = mid; } used = a; }
+                for (uint32_t part = 0; part < (ph ? 2u : 1u); ++part) {
+                    const uint32_t lo = ph ? (part ? used : x) : x, hi = ph ? (part ? xe : used) : xe;
+                    if (lo >= hi) continue;
+                    const bool use_rel = ph && part == 0;
+                    const uint32_t elig0 = elig, pc = __popc(elig0);
+                    const uint32_t incl = warp_incl_scan_u32(pc), pre = incl - pc, np = __shfl_sync(0xffffffffu, incl, 31);
+                    if (np == 0) {
+                        for (uint32_t j = lo + lane; j < hi; j += 32) Ex[j] = (uint16_t)NONE16;
+                        __syncwarp();
+                        continue;
+                    }
+                    int carry = 0;
+                    for (uint32_t i0 = 0; i0 < hi - lo; i0 += 32) {
+                        const uint32_t i = i0 + lane, j = lo + i;
+                        const bool valid = j < hi;
+                        uint32_t G = 0;
+                        if (valid && use_rel) {
+                            const uint32_t rel = (Sx[E1x[j]] & 0xFFFFu) + W + 1u;
+                            uint32_t a = 0, b = cntp;
+                            while (a < b) { const uint32_t mid = (a + b) >> 1; if ((Sx[ebase + mid] & 0xFFFFu) >= rel) b = mid; else a = mid + 1; }
+                            G = a;
+                        }
+                        const uint32_t wd = G >> 5;
+                        const uint32_t pw = __shfl_sync(0xffffffffu, pre, wd & 31u), ew = __shfl_sync(0xffffffffu, elig0, wd & 31u);
+                        const uint32_t lbp = wd >= 32u ? np : pw + __popc(ew & ((1u << (G & 31u)) - 1u));
+                        int v = valid ? (int)lbp - (int)i : -(1 << 28);
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane >= d) v = max(v, t2); }
+                        const int last = __shfl_sync(0xffffffffu, v, 31);
+                        const int u = max(v, carry);
+                        carry = max(carry, last);
+                        const uint32_t idx = i + (uint32_t)u;
+                        const bool take = valid && idx < np;
+                        uint32_t t = 0;
+#pragma unroll
+                        for (uint32_t st = 16; st > 0; st >>= 1) {
+                            const uint32_t c = t + st;
+                            const uint32_t pcand = __shfl_sync(0xffffffffu, pre, c & 31u);
+                            if (c < 32u && pcand <= idx) t = c;
+                        }
+                        const uint32_t pt = __shfl_sync(0xffffffffu, pre, t), et = __shfl_sync(0xffffffffu, elig0, t);
+                        const uint32_t g = take ? 32u * t + __fns(et, 0u, (int)(idx - pt + 1u)) : 0u;
+                        const uint32_t ent = take ? ebase + g : NONE16;
+                        if (valid) Ex[j] = (uint16_t)ent;
+                        if (take) atomicOr(&scr[g >> 5], 1u << (g & 31u));
+                        __syncwarp();
+                        elig &= ~scr[lane];
+                        __syncwarp();
+                        scr[lane] = 0;
+                        __syncwarp();
+                        {
+                            uint32_t p = 0, o = 0;
+                            if (take) { const uint32_t e = Sx[ent]; p = e & 0xFFFFu; o = (e >> 16) & 0x3FFFu; }
+                            const uint32_t f = find(take, o, j, p, ph != 0u);
+                            if (take) fres[p] = (uint16_t)f;
+                        }
+                        if ((int)(i0 + 32u) + carry >= (int)np) {
+                            for (uint32_t j2 = lo + i0 + 32u + lane; j2 < hi; j2 += 32) Ex[j2] = (uint16_t)NONE16;
+                            break;
+                        }
+                    }
+                    __syncwarp();
+                }
+                x = xe;
+            }
+        }
+        return;
+    }
+    // ---- phase 1: between two homes the next slots go to the next unplaced entries whose home is at/before the segment
+    {
+        uint32_t x = 0, fu = 0;
+        while (x < m) {
+            const uint32_t xe = next_home(x);
+            const uint32_t seglen = xe - x;
+            uint32_t filled = 0;
+            for (uint32_t base = fu; base < n1 && filled < seglen; base += TEAM) {
+                const uint32_t i = base + tt;
+                const uint32_t e = i < n1 ? Sx[i] : 0xFFFFFFFFu;
+                const bool elig = i < n1 && !(e & PLACED) && ((e >> 16) & 0x3FFFu) <= x;
+                uint32_t tot;
+                const uint32_t r = T.exscan(elig ? 1u : 0u, tot);
+                if (elig && filled + r < seglen) { E1x[x + filled + r] = (uint16_t)i; Sx[i] = e | PLACED; }
+                filled += tot;
+            }
+            if (filled > seglen) filled = seglen;
+            for (uint32_t j = x + filled + tt; j < xe; j += TEAM) E1x[j] = (uint16_t)NONE16;
+            T.sync();
+            for (;;) {                                       // first entry that is still unplaced
+                const uint32_t i = fu + tt;
+                const uint32_t r = T.tmin((i < n1 && !(Sx[i] & PLACED)) ? i : n1);
+                if (r < n1 || fu + TEAM >= n1) { fu = r; break; }
+                fu += TEAM;
+            }
+            x = xe;
+        }
+    }
+    for (uint32_t base = 0; base < m; base += TEAM) {
+        const uint32_t j = base + tt;
+        const uint32_t i = j < m ? (uint32_t)E1x[j] : NONE16;
+        const bool act = i != NONE16;
+        uint32_t p = 0, o = 0;
+        if (act) { const uint32_t e = Sx[i]; p = e & 0xFFFFu; o = (e >> 16) & 0x3FFFu; }
+        const uint32_t f = find(act, o, j, p, false);
+        if (act) fres[p] = (uint16_t)f;
+    }
+    if (n1 == m) return;
+    // ---- phase 2
+    uint32_t x = 0, fu2 = n1;
+    while (x < m) {
+        const uint32_t xe = next_home(x);
+        uint32_t used;                                       // the phase-1 slots of a segment are a prefix of it
+        { uint32_t a = x, b = xe; while (a < b) { const uint32_t mid = (a + b) >> 1; if (E1x[mid] != NONE16) a = mid + 1; else b = mid; } used = a; }
+        for (uint32_t part = 0; part < 2; ++part) {
+            const uint32_t lo = part ? used : x, hi = part ? xe : used;
+            if (lo >= hi) continue;
+            uint32_t np = 0;                                 // pool: unplaced phase-2 entries with home at/before the segment, in time order
+            for (uint32_t base = fu2; base < m; base += TEAM) {
+                const uint32_t i = base + tt;
+                const uint32_t e = i < m ? Sx[i] : 0xFFFFFFFFu;
+                const bool elig = i < m && !(e & PLACED) && ((e >> 16) & 0x3FFFu) <= x;
+                uint32_t tot;
+                const uint32_t r = T.exscan(elig ? 1u : 0u, tot);
+                if (elig) E2x[lo + np + r] = (uint16_t)i;
+                np += tot;
+            }
+            T.sync();
+            if (np == 0) {
+                for (uint32_t j = lo + tt; j < hi; j += TEAM) E2x[j] = (uint16_t)NONE16;
+                T.sync();
+                continue;
+            }
+            int carry = 0;
+            for (uint32_t i0 = 0; i0 < hi - lo; i0 += TEAM) {
+                const uint32_t i = i0 + tt, j = lo + i;
+                const bool valid = j < hi;
+                int v = -(1 << 28);
+                if (valid) {
+                    uint32_t a = i0 < np ? i0 : np, b = np;
+                    if (part == 0) {
+                        const uint32_t rel = (Sx[E1x[j]] & 0xFFFFu) + W + 1u;     // first arrival time for which the slot is dead
+                        while (a < b) { const uint32_t mid = (a + b) >> 1; if ((Sx[E2x[lo + mid]] & 0xFFFFu) >= rel) b = mid; else a = mid + 1; }
+                    }
+                    v = (int)a - (int)i;
+                }
+                int last;
+                int u = T.maxscan(v, last);
+                u = max(u, carry);
+                carry = max(carry, last);
+                const uint32_t idx = i + (uint32_t)u;
+                const uint32_t ent = (valid && idx < np) ? E2x[lo + idx] : NONE16;
+                T.sync();                                    // every pool read of the group is done
+                if (valid) { E2x[j] = (uint16_t)ent; if (ent != NONE16) Sx[ent] |= PLACED; }
+                T.sync();
+                {                                            // find of the entry that just got slot j
+                    const bool act = valid && ent != NONE16;
+                    uint32_t p = 0, o = 0;
+                    if (act) { const uint32_t e = Sx[ent]; p = e & 0xFFFFu; o = (e >> 16) & 0x3FFFu; }
+                    const uint32_t f = find(act, o, j, p, true);
+                    if (act) fres[p] = (uint16_t)f;
+                }
+                if ((int)(i0 + TEAM) + carry >= (int)np) {   // the pool is used up: the remaining slots stay dead
+                    for (uint32_t j2 = lo + i0 + TEAM + tt; j2 < hi; j2 += TEAM) E2x[j2] = (uint16_t)NONE16;
+                    break;
+                }
+            }
+            T.sync();
+            for (;;) {
+                const uint32_t i = fu2 + tt;
+                const uint32_t r = T.tmin((i < m && !(Sx[i] & PLACED)) ? i : m);
+                if (r < m || fu2 + TEAM >= m) { fu2 = r; break; }
+                fu2 += TEAM;
+            }
+        }
+        x = xe;
+    }
+}
+
+__device__ __forceinline__ long long clk_ordered() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
+#define CLK() (DBG ? clk_ordered() : 0ll)
+template <bool DBG>
+__global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t bs, uint32_t nblocks,
+                                                             uint16_t* __restrict__ fres_all, uint32_t* __restrict__ tok_all,
+                                                             uint8_t* __restrict__ scratch, uint64_t stride,
+                                                             uint64_t* __restrict__ block_sizes, uint64_t* __restrict__ block_bytes,
+                                                             uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_cnt,
+                                                             uint32_t* __restrict__ dbg_tok) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* data = smem + OFF_DATA;
+    uint8_t* big = smem + OFF_BIG;
+    uint32_t* bm = reinterpret_cast<uint32_t*>(big);
+    uint32_t* pre = reinterpret_cast<uint32_t*>(smem + OFF_PRE);
+    uint16_t* pre16 = reinterpret_cast<uint16_t*>(smem + OFF_PRE);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(smem + OFF_FLAGS);
+    Misc* ms = reinterpret_cast<Misc*>(smem + OFF_MISC);
+    uint32_t* S = reinterpret_cast<uint32_t*>(big);
+    uint16_t* E1 = reinterpret_cast<uint16_t*>(big + CH * 4);
+    uint16_t* E2 = E1 + CH;
+    uint16_t* wl = reinterpret_cast<uint16_t*>(smem + OFF_PRE);   // work list: local start of every cluster of 2+ entries, largest classes first
+    uint32_t* wscr = reinterpret_cast<uint32_t*>(smem + OFF_PRE + WL_CAP * 2);   // 32 words per warp (zero between uses)
+    uint8_t* adv = big;
+    uint8_t* exitof = big + PADDED;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint16_t* fres = fres_all + (uint64_t)blockIdx.x * MAXB;
+    uint32_t* tokb = tok_all + (uint64_t)blockIdx.x * MAXB;
+    uint32_t* dbg_stats = dbg_tok ? dbg_tok + (uint64_t)nblocks * MAXB : nullptr;
+
+    for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const long long t_begin = CLK();
+        if (DBG && dbg_stats && tid < 128) dbg_stats[(uint64_t)b * 136 + 8 + tid] = 0;
+#define PHASE_STAMP(k) do { if (DBG && dbg_stats && tid == 0) dbg_stats[(uint64_t)b * 136 + (k)] = (uint32_t)(clk_ordered() - t_begin); } while (0)
+        const uint8_t* src = in + (uint64_t)b * bs;
+        const uint32_t len = (uint32_t)(n - (uint64_t)b * bs < bs ? n - (uint64_t)b * bs : bs);
+
+        // ---------------- P0: block -> shared memory (zero pad behind it, U1), zero bitmap / summary / flags
+        {
+            const bool al = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+            for (uint32_t i = tid * 16; i < len + 128 && i < SZ_DATA; i += NTHREADS * 16) {
+                if (al && i + 16 <= len) *reinterpret_cast<uint4*>(data + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
+                else for (uint32_t k = 0; k < 16 && i + k < SZ_DATA; ++k) data[i + k] = (i + k < len) ? __ldg(src + i + k) : 0;
+            }
+            for (uint32_t i = tid; i < BM_WORDS; i += NTHREADS) bm[i] = 0;
+            for (uint32_t i = tid; i < BM_WORDS / 32; i += NTHREADS) pre[i] = 0;
+            for (uint32_t i = tid; i < SZ_FLAGS / 4; i += NTHREADS) flags[i] = 0;
+            if (tid == 0) { ms->p1_next = 0; ms->fallback = 0; }
+        }
+        __syncthreads();
+        PHASE_STAMP(0);
+        // ---------------- P1: no-expiry occupancy by atomic linear probing (as v2); the slot an entry wins is ITS slot
+        {
+            uint32_t* summ = pre;
+            bool wrapped = false;
+            for (;;) {
+                uint32_t row = 0;
+                if (lane == 0) row = atomicAdd(&ms->p1_next, 32u);
+                row = __shfl_sync(0xffffffffu, row, 0);
+                if (row >= len) break;
+                const uint32_t i = row + lane;
+                if (i >= len) continue;
+                const uint32_t h = lz_hash(sm_word(data, i));
+                uint32_t s = h, cl;
+                for (;;) {
+                    const uint32_t wi = s >> 5;
+                    const uint32_t free_bits = ~bm[wi] & (0xFFFFFFFFu << (s & 31));
+                    if (free_bits) {
+                        const uint32_t bp = (uint32_t)(__ffs(free_bits) - 1), bit = 1u << bp;
+                        const uint32_t old = atomicOr(&bm[wi], bit);
+                        if (!(old & bit)) {
+                            if ((old | bit) == 0xFFFFFFFFu) atomicOr(&summ[wi >> 5], 1u << (wi & 31));
+                            cl = (wi << 5) + bp;
+                            break;
+                        }
+                        continue;
+                    }
+                    uint32_t nw = wi + 1;
+                    uint32_t open = ~summ[nw >> 5] & (0xFFFFFFFFu << (nw & 31));
+                    while (!open) { nw = ((nw >> 5) + 1) << 5; open = ~summ[nw >> 5]; }
+                    s = ((nw & ~31u) + (uint32_t)(__ffs(open) - 1)) << 5;
+                    if (s >= SLOTS) { s = 0; wrapped = true; }        // the wrapping insert (deflate/lz77.c:99-101): not here
+                }
+                const uint32_t d = cl - h;
+                tokb[i] = cl | ((d < 4095u ? d : 4095u) << 20);
+            }
+            if (wrapped) ms->fallback = 1u;
+        }
+        __syncthreads();
+        PHASE_STAMP(1);
+        // ---------------- P2: rank prefix per 4 words, cluster-start flag per compact slot
+        {
+            const uint32_t c0 = tid * 5;
+            uint32_t part[5], half[5], mine = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const uint32_t ch = c0 + k;
+                uint32_t s = 0, s4 = 0;
+                if (ch < PRE_N) {
+                    const uint4 qa = *reinterpret_cast<const uint4*>(bm + ch * PRE_CHUNK), qb = *reinterpret_cast<const uint4*>(bm + ch * PRE_CHUNK + 4);
+                    s4 = __popc(qa.x) + __popc(qa.y) + __popc(qa.z) + __popc(qa.w);
+                    s = s4 + __popc(qb.x) + __popc(qb.y) + __popc(qb.z) + __popc(qb.w);
+                }
+                part[k] = s; half[k] = s4; mine += s;
+            }
+            const uint32_t incl = warp_incl_scan_u32(mine);
+            if (lane == 31) ms->scan[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t t = ms->scan[lane];
+                const uint32_t ti = warp_incl_scan_u32(t);
+                ms->scan[lane] = ti - t;
+            }
+            if (tid == 32 && ((bm[0] & 1u) || (bm[SLOTS / 32 - 1] >> 31))) ms->fallback = 1u;   // slot 0 / the table end is in use
+            __syncthreads();
+            uint32_t run = ms->scan[warp] + incl - mine;
+            uint32_t fw = 0xFFFFFFFFu, fbits = 0;
+#pragma unroll 1
+            for (int k = 0; k < 5; ++k) {
+                const uint32_t ch = c0 + k;
+                if (ch >= PRE_N) break;
+                pre16[2 * ch] = (uint16_t)run; pre16[2 * ch + 1] = (uint16_t)(run + half[k]);
+                if (part[k]) {
+                    uint32_t rw = run;
+                    for (uint32_t wq_ = 0; wq_ < PRE_CHUNK; ++wq_) {
+                        const uint32_t widx = ch * PRE_CHUNK + wq_;
+                        const uint32_t xw = bm[widx];
+                        if (xw) {
+                            const uint32_t prev = widx ? bm[widx - 1] >> 31 : 0u;
+                            uint32_t st = xw & ~((xw << 1) | prev);
+                            while (st) {
+                                const uint32_t bp = (uint32_t)(__ffs(st) - 1);
+                                st &= st - 1;
+                                const uint32_t u = rw + __popc(xw & ((1u << bp) - 1u));
+                                if ((u >> 5) != fw) { if (fbits) atomicOr(&flags[fw], fbits); fw = u >> 5; fbits = 0; }
+                                fbits |= 1u << (u & 31);
+                            }
+                            rw += __popc(xw);
+                        }
+                    }
+                }
+                run += part[k];
+            }
+            if (fbits) atomicOr(&flags[fw], fbits);
+            if (tid == 0) atomicOr(&flags[len >> 5], 1u << (len & 31));   // sentinel behind the last compact slot
+        }
+        __syncthreads();
+        const bool fb0 = ms->fallback != 0;
+        PHASE_STAMP(2);
+        // ---------------- P3: compact slot of the claimed slot, displacement from the home; loners
+        if (!fb0) {
+            for (uint32_t i0 = tid; i0 < len; i0 += 8 * NTHREADS) {
+                uint32_t tv[8];
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) { const uint32_t i = i0 + k * NTHREADS; tv[k] = i < len ? tokb[i] : 0u; }
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) {
+                    const uint32_t i = i0 + k * NTHREADS;
+                    if (i >= len) break;
+                    const uint32_t cl = tv[k] & 0xFFFFFu, dd = tv[k] >> 20;
+                    const uint32_t h = dd < 4095u ? cl - dd : lz_hash(sm_word(data, i));
+                    const uint32_t d = cl - h;
+                    bool loner = false;
+                    if (d == 0) {
+                        const uint32_t wi = h >> 5, bi = h & 31u, wv = bm[wi];
+                        const uint32_t below = bi ? (wv >> (bi - 1u)) & 1u : (wi ? bm[wi - 1] >> 31 : 0u);
+                        const uint32_t above = bi != 31u ? (wv >> (bi + 1u)) & 1u : (bm[wi + 1] & 1u);
+                        loner = !below && !above;
+                    }
+                    tokb[i] = loner ? LONER : (bm_rank(bm, pre16, cl) | (d << 16));
+                    fres[i] = (uint16_t)NONE16;
+                }
+            }
+        }
+        __syncthreads();
+        PHASE_STAMP(3);
+        // ---------------- clusters, one chunk of the compact slot space at a time
+        uint32_t cb = 0;
+        long long dt_sc = 0, dt_c2 = 0, dt_w = 0, dt_t = 0, dt_wait = 0, t_mark = CLK();
+        uint32_t n_chunks = 0, n_wq = 0, n_tq = 0;
+#define SUBSTAMP(acc) do { if (DBG) { const long long t_now = clk_ordered(); acc += t_now - t_mark; t_mark = t_now; } } while (0)
+        while (!fb0 && cb < len) {
+            if (tid == 0) {
+                uint32_t ce = len;
+                if (len - cb > CH) {                         // last cluster start at/before cb + CH
+                    const uint32_t pos = cb + CH;
+                    uint32_t wi = pos >> 5;
+                    uint32_t xw = flags[wi] & (0xFFFFFFFFu >> (31u - (pos & 31u)));
+                    while (!xw) { --wi; xw = flags[wi]; }
+                    ce = (wi << 5) + 31u - (uint32_t)__clz(xw);
+                    if (ce <= cb) { ms->fallback = 1u; ce = len; }
+                }
+                ms->ce = ce; for (int c = 0; c < 7; ++c) { ms->ccnt[c] = 0; ms->cfill[c] = 0; }
+            }
+            __syncthreads();
+            if (ms->fallback) break;
+            const uint32_t ce = ms->ce, cnt = ce - cb;
+            for (uint32_t i0 = tid; i0 < len; i0 += 8 * NTHREADS) {           // entries of the chunk -> S[compact slot]
+                uint32_t tv[8];
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) { const uint32_t i = i0 + k * NTHREADS; tv[k] = i < len ? tokb[i] : LONER; }
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) {
+                    if (tv[k] != LONER) {
+                        const uint32_t u = tv[k] & 0xFFFFu, rel = u - cb;
+                        if (rel < cnt) S[rel] = (i0 + k * NTHREADS) | ((u - (tv[k] >> 16)) << 16);
+                    }
+                }
+            }
+            __syncthreads();
+            SUBSTAMP(dt_sc);
+            // work list: every thread looks at 17 compact slots, counts its clusters per size class, then files them
+            auto cls_of = [](uint32_t m) -> uint32_t { return m > TMIN ? 0u : m > LMAX ? 1u : m > 16 ? 2u : m > 8 ? 3u : m > 4 ? 4u : m > 2 ? 5u : 6u; };
+            const uint32_t lo17 = tid * 17;
+            uint32_t nlbits = 0;                              // starts of clusters of 2+ entries among my slots
+            if (lo17 < cnt) {
+                const uint32_t hi = lo17 + 17 < cnt ? lo17 + 17 : cnt;
+                const uint32_t a = cb + lo17;
+                const unsigned long long win = ((unsigned long long)flags[(a >> 5) + 1] << 32) | flags[a >> 5];
+                const uint32_t fb = (uint32_t)(win >> (a & 31u));        // flags of a .. a + 31 (18 are needed)
+                uint32_t bits = fb & ((1u << (hi - lo17)) - 1u) & ~(fb >> 1);   // a start directly followed by a start is a loner
+                nlbits = bits;
+                while (bits) {
+                    const uint32_t k = (uint32_t)(__ffs(bits) - 1);
+                    bits &= bits - 1;
+                    const uint32_t start = a + k, q = start + 1;
+                    uint32_t wi = q >> 5;
+                    uint32_t xw = flags[wi] & (0xFFFFFFFFu << (q & 31u));
+                    while (!xw) { ++wi; xw = flags[wi]; }
+                    const uint32_t m = (wi << 5) + (uint32_t)(__ffs(xw) - 1) - start;
+                    if (m > CL_MAX) { ms->fallback = 1u; continue; }
+                    E1[lo17 + k] = (uint16_t)m;
+                    atomicAdd(&ms->ccnt[cls_of(m)], 1u);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t run = 0;
+                for (int c = 0; c < 7; ++c) { ms->cbase[c] = run; run += ms->ccnt[c]; }
+                ms->cbase[7] = run; ms->next_t = 0; ms->next_w = ms->cbase[1]; ms->next_l = ms->cbase[2];
+                if (run > WL_CAP) ms->fallback = 1u;
+            }
+            wscr[tid] = 0;
+            __syncthreads();
+            while (nlbits) {
+                const uint32_t k = (uint32_t)(__ffs(nlbits) - 1);
+                nlbits &= nlbits - 1;
+                const uint32_t m = E1[lo17 + k];
+                if (m > CL_MAX || ms->fallback) continue;
+                const uint32_t c = cls_of(m);
+                wl[ms->cbase[c] + atomicAdd(&ms->cfill[c], 1u)] = (uint16_t)(lo17 + k);
+            }
+            __syncthreads();
+            SUBSTAMP(dt_c2);
+            if (!ms->fallback) {
+                const uint32_t tq_n = ms->cbase[1], wq_end = ms->cbase[2], total = ms->cbase[7];
+                if (DBG) { ++n_chunks; n_wq += total - tq_n; n_tq += tq_n; }
+                if (tq_n) {                                  // clusters above LMAX entries: slot sweeps by four-warp teams
+                    const uint32_t team = warp >> 2;
+                    Team<128> TT; TT.tt = tid & 127u; TT.bar = 1u + team; TT.scr = &ms->tscr[team][0][0]; TT.par = 0;
+                    for (;;) {
+                        if (TT.tt == 0) ms->tpick[team] = atomicAdd(&ms->next_t, 1u);
+                        TT.sync();
+                        const uint32_t qi = ms->tpick[team];
+                        TT.sync();
+                        if (qi >= tq_n) break;
+                        const uint32_t kl = wl[qi], m = E1[kl];
+                        TT.sync();                           // (E1 is about to be rewritten)
+                        const long long t_c0 = CLK();
+                        big_cluster<128>(TT, S + kl, E1 + kl, E2 + kl, m, cb + kl, data, fres, wscr + warp * 32);
+                        if (DBG && dbg_stats && TT.tt == 0) {
+                            const uint32_t dtc = (uint32_t)((clock64() - t_c0) >> 6);
+                            atomicMax(&dbg_stats[(uint64_t)b * 136 + 16], (dtc << 14) | m);
+                            atomicAdd(&dbg_stats[(uint64_t)b * 136 + 24 + team], dtc);
+                            atomicAdd(&dbg_stats[(uint64_t)b * 136 + 17], m);
+                        }
+                    }
+                }
+                if (DBG) SUBSTAMP(dt_t);
+                {                                            // LMAX+1 .. TMIN entries: slot sweeps by one warp
+                    Team<32> TW; TW.tt = lane; TW.bar = 0; TW.scr = nullptr; TW.par = 0;
+                    for (;;) {
+                        uint32_t qi = 0;
+                        if (lane == 0) qi = atomicAdd(&ms->next_w, 1u);
+                        qi = __shfl_sync(0xffffffffu, qi, 0);
+                        if (qi >= wq_end) break;
+                        const uint32_t kl = wl[qi], m = E1[kl];
+                        __syncwarp();
+                        big_cluster<32>(TW, S + kl, E1 + kl, E2 + kl, m, cb + kl, data, fres, wscr + warp * 32);
+                    }
+                }
+                for (;;) {                                   // 32 clusters of similar size per warp, one lane each
+                    uint32_t g = 0;
+                    if (lane == 0) g = atomicAdd(&ms->next_l, 32u);
+                    g = __shfl_sync(0xffffffffu, g, 0);
+                    if (g >= total) break;
+                    const uint32_t it = g + lane;
+                    const bool has = it < total;
+                    const uint32_t kl = has ? wl[it] : 0u;
+                    const uint32_t m = has ? E1[kl] : 0u;
+                    uint32_t coop = __ballot_sync(0xffffffffu, m > 16);
+                    while (coop) {                           // 17 .. 64 entries: the warp sorts, the lane simulates
+                        const int srcl = __ffs(coop) - 1;
+                        coop &= coop - 1;
+                        { const uint32_t kk = __shfl_sync(0xffffffffu, kl, srcl); warp_sort64(S + kk, __shfl_sync(0xffffffffu, m, srcl), cb + kk); }
+                    }
+                    __syncwarp();
+                    if (has) {
+                        if (m <= 16) { lane_sort(S + kl, m); lane_cluster<true>(S + kl, nullptr, nullptr, m, cb + kl, data, fres); }
+                        else lane_cluster<false>(S + kl, E1 + kl, E2 + kl, m, 0u, data, fres);
+                    }
+                }
+                if (DBG) SUBSTAMP(dt_w);
+            }
+            __syncthreads();
+            SUBSTAMP(dt_wait);
+            cb = ce;
+        }
+        if (DBG && dbg_stats && tid == 0) {
+            uint32_t* o = dbg_stats + (uint64_t)b * 136 + 8;
+            o[0] = (uint32_t)dt_sc; o[1] = (uint32_t)dt_c2; o[2] = (uint32_t)dt_w; o[3] = (uint32_t)dt_t; o[4] = n_chunks; o[5] = n_wq; o[6] = n_tq; o[7] = (uint32_t)dt_wait;
+        }
+        __syncthreads();
+        if (ms->fallback) {                                  // hand the block to lz77_v2_kernel
+            if (tid == 0) fb_list[atomicAdd(fb_cnt, 1u)] = b;
+            __syncthreads();
+            continue;
+        }
+        PHASE_STAMP(4);
+        // ---------------- P5: token candidates (reject rule deflate/lz77.c:222, extension :238-247), greedy parse as v2
+        for (uint32_t i0 = tid; i0 < len; i0 += 8 * NTHREADS) {
+            uint32_t fv[8];
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) { const uint32_t i = i0 + k * NTHREADS; fv[k] = i < len ? fres[i] : NONE16; }
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) {
+                const uint32_t i = i0 + k * NTHREADS;
+                if (i < len) {
+                    uint32_t tk = 0;
+                    if (fv[k] != NONE16 && i - fv[k] < W - 1u) tk = (i - fv[k]) | (match_len(data, fv[k], i) << 16);
+                    tokb[i] = tk;
+                    if (dbg_tok) dbg_tok[(uint64_t)b * MAXB + i] = tk;
+                    adv[PADX(i)] = (uint8_t)(tk ? (tk >> 16) : 1u);
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nchunks = (len + 63) >> 6;
+        if (tid < nchunks) {   // exit function of chunk tid by backward DP over its 64 positions
+            const uint32_t lo = tid << 6, cend = lo + 64;
+            const uint32_t hi = cend < len ? cend : len;
+            for (uint32_t p = hi; p-- > lo;) {
+                const uint32_t nx = p + adv[PADX(p)];
+                exitof[PADX(p)] = (uint8_t)(nx >= cend ? nx - cend : exitof[PADX(nx)]);
+            }
+        }
+        __syncthreads();
+        {   // entry offset of every chunk: 32 super-chunks of 32 chunks
+            uint32_t e = lane;
+            for (uint32_t k = 0; k < 32; ++k) {
+                const uint32_t ch = warp * 32 + k;
+                const uint32_t p = (ch << 6) + e;
+                if (ch < nchunks && p < len && e < 31) e = exitof[PADX(p)];
+            }
+            ms->sexit[warp][lane] = (uint8_t)e;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t e = 0;
+            for (uint32_t s = 0; s < 32; ++s) { ms->sentry[s] = (uint8_t)e; e = ms->sexit[s][e]; }
+        }
+        __syncthreads();
+        uint8_t* centry = reinterpret_cast<uint8_t*>(pre) + 8192;
+        if (lane == 0) {
+            uint32_t e = ms->sentry[warp];
+            for (uint32_t k = 0; k < 32; ++k) {
+                const uint32_t ch = warp * 32 + k;
+                centry[ch] = (uint8_t)e;
+                const uint32_t p = (ch << 6) + e;
+                if (ch < nchunks && p < len) e = exitof[PADX(p)];
+            }
+        }
+        __syncthreads();
+        uint8_t* orel = exitof;
+        for (uint32_t i = tid; i < (PADDED >> 2); i += NTHREADS) reinterpret_cast<uint32_t*>(orel)[i] = 0xFFFFFFFFu;
+        __syncthreads();
+        uint32_t my_units = 0;
+        if (tid < nchunks) {
+            const uint32_t cend = (tid << 6) + 64;
+            const uint32_t hi = cend < len ? cend : len;
+            for (uint32_t p = (tid << 6) + centry[tid]; p < hi; p += adv[PADX(p)]) {
+                orel[PADX(p)] = (uint8_t)(my_units >> 1);
+                my_units += adv[PADX(p)] == 1 ? 2u : 4u;
+            }
+        }
+        uint32_t my_off;
+        {
+            const uint32_t incl = warp_incl_scan_u32(my_units);
+            if (lane == 31) ms->scan[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t t = ms->scan[lane];
+                const uint32_t ti = warp_incl_scan_u32(t);
+                ms->scan[lane] = ti - t;
+                if (lane == 31) ms->scan[32] = ti;
+            }
+            __syncthreads();
+            my_off = ms->scan[warp] + incl - my_units;
+        }
+        const uint32_t total_units = ms->scan[32];
+        uint8_t* out = scratch + (uint64_t)b * stride;
+        PHASE_STAMP(5);
+        // ---------------- P6: emission, one position per thread (deflate/lz77.c:176-197)
+        {
+            uint32_t* coff = pre + 3072;
+            if (tid < nchunks) coff[tid] = my_off;
+            __syncthreads();
+            for (uint32_t p0 = tid; p0 < len; p0 += 4 * NTHREADS) {
+                uint32_t tk[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) { const uint32_t p = p0 + k * NTHREADS; tk[k] = p < len ? tokb[p] : 0u; }
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                    const uint32_t p = p0 + k * NTHREADS;
+                    if (p >= len) break;
+                    const uint32_t r = orel[PADX(p)];
+                    if (r == 0xFFu) continue;
+                    const uint32_t o = coff[p >> 6] + 2u * r, t = tk[k];
+                    if (t == 0) *reinterpret_cast<uint16_t*>(out + o) = (uint16_t)((uint32_t)data[p] << 8);
+                    else {
+                        const uint32_t off = t & 0xFFFFu, ml = t >> 16;
+                        *reinterpret_cast<uint16_t*>(out + o) = (uint16_t)(1u | ((off & 0xFFu) << 8));
+                        *reinterpret_cast<uint16_t*>(out + o + 2) = (uint16_t)((off >> 8) | (ml << 8));
+                    }
+                }
+            }
+            if (tid == 0) { block_sizes[b] = total_units; block_bytes[b] = total_units; }
+        }
+        __syncthreads();
+        PHASE_STAMP(6);
+    }
+}
+
+}  // namespace
+
+int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
+                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok,
+                   const uint32_t* blist, const uint32_t* bcount);
+
+// scratch slots: 13 = F (u16 per position; v2's lists when it runs the handed-back blocks), 14 = tok, 18 = hand-back list
+int lz77_v4_launch(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
+                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok) {
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0];
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(lz77_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(lz77_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_done = true;
+    }
+    uint64_t grid = (uint64_t)ctx->sm_count;
+    if (grid > nblocks) grid = nblocks;
+    uint16_t* fres; uint32_t* tok; uint32_t* fb;
+    B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 13), (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&fres)));
+    B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 14), (size_t)grid * MAXB * 4 + 64, reinterpret_cast<void**>(&tok)));
+    B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 18), (size_t)(nblocks + 16) * 4, reinterpret_cast<void**>(&fb)));
+    CUDA_TRY(cudaMemsetAsync(fb, 0, 16, ctx->stream));
+    uint32_t* fb_cnt = fb; uint32_t* fb_list = fb + 4;
+    if (dbg_tok) lz77_v4_kernel<true><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, fres, tok, scratch, stride, d_block_sizes, block_bytes, fb_list, fb_cnt, dbg_tok);
+    else lz77_v4_kernel<false><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, fres, tok, scratch, stride, d_block_sizes, block_bytes, fb_list, fb_cnt, dbg_tok);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    // the blocks handed back (empty list: the kernel's CTAs return at once)
+    return lz77_v2_launch(ctx, 1, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok, fb_list, fb_cnt);
+}

@@ -1,0 +1,93 @@
+"""GPU parity of the experimental two-phase match finder (csrc/lz77_v4.cu, B200_LZ_V4=1; deflate variant, blocks of
+at most 65536 bytes): same oracle comparisons as tests/test_gpu_lz77.py, plus byte equality with the default kernel.
+Blocks it hands back (a cluster on slot 0 / the table end, a cluster above 16383 entries) run through lz77_v2_kernel,
+so the skewed / slot-0 cases below exercise the hand-back list."""
+import numpy as np
+import pytest
+
+from test_gpu_lz77 import _corpus, _encode_check, _to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _v4(monkeypatch):
+    monkeypatch.setenv("B200_LZ_V4", "1")
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("block", [65536, 32768, 4096, 50000])
+def test_block_parity(ctx, ob, kind, block):
+    _encode_check(ctx, ob, _corpus(1_000_003, kind, 11), 1, block)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 32, 33, 1000, 65535, 65536, 65537])
+def test_tiny_and_ragged(ctx, ob, n):
+    _encode_check(ctx, ob, _corpus(n, 0, 3), 1, 65536)
+    if n >= 33:
+        _encode_check(ctx, ob, _corpus(min(n, 5000), 1, 3), 1, 16)
+
+
+def test_single_chain_blocks(ctx, ob):
+    """constant and two-symbol input: one cluster holds (nearly) every entry of a block"""
+    _encode_check(ctx, ob, np.zeros(200_000, dtype=np.uint8), 1, 65536)
+    _encode_check(ctx, ob, np.full(70_000, 0x41, dtype=np.uint8), 1, 65536)
+    _encode_check(ctx, ob, _corpus(300_000, 2, 5), 1, 65536)
+
+
+def test_zero_bytes_and_overshoot(ctx, ob):
+    rng = np.random.default_rng(9)
+    data = rng.integers(0, 3, size=70000, dtype=np.uint8)
+    data[-40:] = 0
+    _encode_check(ctx, ob, data, 1, 65536)
+
+
+def test_slot0_pattern_is_handed_back(ctx, ob):
+    """pattern 0x01021578 hashes to slot 0 (U10): such blocks go through the default kernel"""
+    rng = np.random.default_rng(4)
+    n = 200_000
+    data = rng.integers(97, 123, size=n, dtype=np.uint8)
+    pat = np.array([0x78, 0x15, 0x02, 0x01], dtype=np.uint8)
+    for p in rng.integers(0, n - 8, size=3000):
+        data[p:p + 4] = pat
+    _encode_check(ctx, ob, data, 1, 65536)
+
+
+def test_periodic_inputs(ctx, ob):
+    """short periods: a handful of long chains whose clusters merge"""
+    for period in (1, 2, 3, 5, 7, 64, 255, 1000):
+        base = np.random.default_rng(period).integers(0, 256, size=period, dtype=np.uint8)
+        _encode_check(ctx, ob, np.tile(base, 140_000 // period + 1)[:140_000], 1, 65536)
+
+
+def test_equals_default_kernel(ctx, monkeypatch):
+    from compression_algorithms_b200 import device as dv
+    data = _corpus(40 * 65536 + 777, 0, 77)
+    d = _to_dev(ctx, data)
+    a = dv.lz77_encode(ctx, d, 1, 65536)
+    out_a = a.out[: a.total_bytes].cpu().numpy().copy(); sz_a = a.block_sizes.cpu().numpy().copy()
+    monkeypatch.delenv("B200_LZ_V4")
+    b = dv.lz77_encode(ctx, d, 1, 65536)
+    assert a.total_bytes == b.total_bytes
+    assert np.array_equal(sz_a, b.block_sizes.cpu().numpy())
+    assert np.array_equal(out_a, b.out[: b.total_bytes].cpu().numpy())
+
+
+def test_match_finder_candidates(ctx, ob):
+    from compression_algorithms_b200 import device as dv
+    data = _corpus(140_000, 0, 23)
+    st, tok = dv.lz77_encode_debug(ctx, _to_dev(ctx, data), 1, 65536)
+    tok = tok.cpu().numpy().view(np.uint32)
+    for b in range(2):
+        blk = data[b * 65536: (b + 1) * 65536]
+        F = ob.port_deflate_lz77_compress(blk, want_F=True)[1]
+        pad = np.concatenate([blk, np.zeros(64, dtype=np.uint8)])
+        for p in np.nonzero(F != 0xFFFFFFFE)[0]:
+            m = int(F[p])
+            want = 0
+            if not (m == 0xFFFFFFFF or p - m >= 32767):
+                l = 4
+                while l < 31 and pad[m + l] == pad[p + l]:
+                    l += 1
+                want = (p - m) | (l << 16)
+            assert int(tok[b, p]) == want, "block %d position %d" % (b, p)
