@@ -193,25 +193,65 @@ __global__ void __launch_bounds__(SEG_TILE) fse_encode_kernel(const uint8_t* __r
     seg_bits[gseg] = total;
 }
 
-// ------------------------------------------------------------ offsets (single CTA) + gather
-__global__ void __launch_bounds__(1024) fse_offsets_kernel(const uint32_t* __restrict__ seg_bits, uint64_t nsegs,
-                                                           uint64_t* __restrict__ seg_word, uint64_t capacity,
-                                                           uint64_t* __restrict__ info) {
+// ------------------------------------------------------------ offsets (two levels) + gather
+// Word offset of every segment = exclusive scan of ceil(bits / 64). Tiles of 2048 segments are scanned by many CTAs
+// (eight consecutive segments per thread, coalesced 32-byte reads), the few tile totals by one warp-sized step of one
+// CTA; the tile base is added where the offsets are consumed (gather) or by fse_add_base_kernel (decode index).
+constexpr uint32_t OFF_TILE = 2048;
+__global__ void __launch_bounds__(256) fse_tile_scan_kernel(const uint32_t* __restrict__ seg_bits, uint64_t nsegs,
+                                                            uint64_t* __restrict__ seg_word, uint64_t* __restrict__ tile_tot) {
+    __shared__ uint32_t wtot[8];
+    const uint64_t i0 = (uint64_t)blockIdx.x * OFF_TILE + (uint64_t)threadIdx.x * 8;
+    uint32_t v[8], sum = 0;
+    if (i0 + 8 <= nsegs) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(seg_bits + i0)), b = __ldg(reinterpret_cast<const uint4*>(seg_bits + i0 + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = i0 + k < nsegs ? seg_bits[i0 + k] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = (v[k] + 63u) >> 6; sum += v[k]; }
+    const uint32_t incl = warp_incl_scan_u32(sum);
+    if (lane_id() == 31) wtot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; ++w) { const uint32_t x = wtot[w]; if (w < (threadIdx.x >> 5)) base += x; tot += x; }
+    uint32_t run = base + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (i0 + k < nsegs) seg_word[i0 + k] = run; run += v[k]; }
+    if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
+}
+
+// exclusive scan of the tile totals (in place: tile_tot[t] becomes the base of tile t), total and capacity check
+__global__ void __launch_bounds__(1024) fse_tile_base_kernel(uint64_t* __restrict__ tile_tot, uint64_t ntiles, uint64_t nsegs,
+                                                             uint64_t* __restrict__ seg_word, uint64_t capacity, uint64_t* __restrict__ info) {
     __shared__ uint64_t warp_tot[33];
-    const uint64_t total = cta_exscan_1024(nsegs, warp_tot,
-        [&](uint64_t i) { return ((uint64_t)seg_bits[i] + 63) >> 6; }, [&](uint64_t i, uint64_t ex) { seg_word[i] = ex; });
+    const uint64_t total = cta_exscan_1024(ntiles, warp_tot,
+        [&](uint64_t i) { return tile_tot[i]; }, [&](uint64_t i, uint64_t ex) { tile_tot[i] = ex; });
     if (threadIdx.x == 0) { seg_word[nsegs] = total; info[0] = total; info[1] = total > capacity ? 1 : 0; }
 }
 
+__global__ void __launch_bounds__(256) fse_add_base_kernel(uint64_t* __restrict__ seg_word, uint64_t nsegs, const uint64_t* __restrict__ tile_base) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < nsegs) seg_word[i] += tile_base[i / OFF_TILE];
+}
+
+// one warp per segment: copies its words to their place in the stream and makes the segment's offset absolute
 __global__ void __launch_bounds__(256) fse_gather_kernel(const uint64_t* __restrict__ scratch, uint32_t stride_words,
-                                                         const uint32_t* __restrict__ seg_bits, const uint64_t* __restrict__ seg_word,
+                                                         const uint32_t* __restrict__ seg_bits, uint64_t* __restrict__ seg_word,
+                                                         const uint64_t* __restrict__ tile_base,
                                                          uint64_t nsegs, uint64_t* __restrict__ out, const uint64_t* __restrict__ info) {
-    if (info[1]) return;
     const uint64_t g = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (g >= nsegs) return;
+    const uint64_t off = seg_word[g] + tile_base[g / OFF_TILE];
+    __syncwarp();
+    if (lane_id() == 0) seg_word[g] = off;
+    if (info[1]) return;
     const uint32_t nw = (seg_bits[g] + 63) >> 6;
     const uint64_t* src = scratch + g * stride_words;
-    uint64_t* dst = out + seg_word[g];
+    uint64_t* dst = out + off;
     for (uint32_t i = lane_id(); i < nw; i += 32) dst[i] = src[i];
 }
 
@@ -243,17 +283,22 @@ __global__ void __launch_bounds__(SEG_TILE) fse_decode_kernel(const uint64_t* __
     const uint32_t T = seg_bits[gseg];
     uint8_t* o = out + start;
     if (T < 16) { atomicAdd(bad, 1u); return; }
-    // the stream is read from its end towards bit 8, as 32-bit words (the u64 words are little endian).
-    // Three of them are held in registers -- the one holding the cursor (wa), the one above (wb) and the
-    // one below (wc, fetched a word ahead) -- so a symbol costs one funnel shift and never waits for memory
+    // The stream is read from its end towards bit 8, as 32-bit words (the u64 words are little endian). hi:lo is a
+    // 64-bit window of the bits just below the cursor (bit 63 = the bit right below it), refilled one word at a time
+    // from a word fetched ahead: a symbol costs one table read, two funnel shifts and no wait for memory. A corrupt
+    // stream reads zeros below its first word and fails the final check (cursor back at bit 8 in state 0).
     const uint32_t* w32 = reinterpret_cast<const uint32_t*>(w);
     const uint32_t last32 = (T - 1) >> 5;
-    uint32_t pos = T - TLOG;
-    uint32_t j = pos >> 5;
-    uint32_t wa = __ldg(w32 + j);
-    uint32_t wb = j + 1 <= last32 ? __ldg(w32 + j + 1) : 0u;
-    uint32_t wc = j > 0 ? __ldg(w32 + j - 1) : 0u;
-    uint32_t u = __funnelshift_r(wa, wb, pos & 31u) & 0xFFu;
+    const uint32_t pos0 = T - TLOG;
+    const int jw = (int)(pos0 >> 5);
+    const uint32_t sh = pos0 & 31u;
+    auto ldw = [&](int k) -> uint32_t { return k >= 0 ? __ldg(w32 + k) : 0u; };
+    const uint32_t wA = ldw(jw), wB = ldw(jw - 1);
+    uint32_t u = __funnelshift_r(wA, (uint32_t)jw + 1u <= last32 ? __ldg(w32 + jw + 1) : 0u, sh) & 0xFFu;
+    uint32_t hi = __funnelshift_r(wB, wA, sh), lo = __funnelshift_r(0u, wB, sh);   // the sh bits of word jw below the cursor + word jw - 1
+    int nxi = jw - 2;
+    uint32_t nxt = ldw(nxi);
+    uint32_t avail = 32u + sh, consumed = 0;
     uint32_t i = 0;
     const bool aligned = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
     while (i + 1 < len) {
@@ -261,27 +306,30 @@ __global__ void __launch_bounds__(SEG_TILE) fse_decode_kernel(const uint64_t* __
         const uint32_t batch = len - 1 - i < 16 ? len - 1 - i : 16;
 #pragma unroll
         for (uint32_t q = 0; q < 16; ++q) {                   // fully unrolled: pack[] stays in registers
-            if (q < batch && u != 0x100) {
-                const uint32_t e = s_tt[u & 0xFF];
+            if (q < batch) {
+                const uint32_t e = s_tt[u & 0xFFu];
                 const uint32_t nb = e >> 24;
-                pack[q >> 2] |= (e & 0xFF) << (8 * (q & 3));
-                if (pos < 8 + nb) { pos = 0; u = 0x100; }     // corrupt stream: would read below the raw byte
-                else {
-                    pos -= nb;
-                    if ((pos >> 5) < j) {                     // the cursor moved into the word below
-                        --j;
-                        wb = wa; wa = wc;
-                        wc = j > 0 ? __ldg(w32 + j - 1) : 0u;
-                    }
-                    u = ((e >> 8) & 0xFFFF) + (__funnelshift_r(wa, wb, pos & 31u) & ((1u << nb) - 1u));
+                pack[q >> 2] |= (e & 0xFFu) << (8 * (q & 3));
+                const uint32_t bits = __funnelshift_l(hi, 0u, nb);          // the nb bits below the cursor
+                hi = __funnelshift_l(lo, hi, nb);
+                lo <<= nb;
+                avail -= nb; consumed += nb;
+                u = ((e >> 8) & 0xFFFFu) + bits;
+                if (avail <= 32) {
+                    const uint32_t s2 = 32u - avail;
+                    lo = nxt << s2;
+                    hi |= __funnelshift_l(nxt, 0u, s2);
+                    avail += 32;
+                    --nxi;
+                    nxt = ldw(nxi);
                 }
             }
         }
         if (batch == 16 && aligned) *reinterpret_cast<uint4*>(o + i) = make_uint4(pack[0], pack[1], pack[2], pack[3]);
         else for (uint32_t q = 0; q < batch; ++q) o[i + q] = (uint8_t)(pack[q >> 2] >> (8 * (q & 3)));
         i += batch;
-        if (u == 0x100) break;
     }
+    const uint32_t pos = consumed <= pos0 ? pos0 - consumed : 0xFFFFFFFFu;
     o[len - 1] = (uint8_t)(__ldg(w) & 0xFF);
     if (!(pos == 8 && u == 0)) atomicAdd(bad, 1u);   // a valid stream lands back on state 0 at bit 8
 }
@@ -363,9 +411,14 @@ extern "C" int b200_fse_encode_dev(b200_ctx* ctx, const uint8_t* d_in, uint64_t 
         d_in, n, bs, (uint32_t)seg_size, spb, tpb, reinterpret_cast<const uint16_t*>(d_side + L.off_norm),
         reinterpret_cast<const uint32_t*>(d_side + L.off_tt), scratch, stride, seg_bits);
     B200_TIMED_END(ctx);
-    fse_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(seg_bits, L.nsegs, seg_word, words_capacity, info);
-    fse_gather_kernel<<<(unsigned)((L.nsegs + 7) / 8), 256, 0, ctx->stream>>>(scratch, stride, seg_bits, seg_word, L.nsegs, d_words, info);
-    ctx->launches += 3;
+    const uint64_t ntiles = (L.nsegs + OFF_TILE - 1) / OFF_TILE;
+    uint64_t* tile_tot;
+    B200_TRY(b200_scratch(ctx, 6, 64 + (size_t)ntiles * 8 + 64, reinterpret_cast<void**>(&tile_tot)));
+    tile_tot += 8;   // (the first 64 bytes of slot 6 are the decoder's bad-segment counter)
+    fse_tile_scan_kernel<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(seg_bits, L.nsegs, seg_word, tile_tot);
+    fse_tile_base_kernel<<<1, 1024, 0, ctx->stream>>>(tile_tot, ntiles, L.nsegs, seg_word, words_capacity, info);
+    fse_gather_kernel<<<(unsigned)((L.nsegs + 7) / 8), 256, 0, ctx->stream>>>(scratch, stride, seg_bits, seg_word, tile_tot, L.nsegs, d_words, info);
+    ctx->launches += 4;
     CUDA_TRY(cudaGetLastError());
     if (h_total_words) {
         uint64_t* pin; B200_TRY(b200_pinned(ctx, 64, reinterpret_cast<void**>(&pin)));
@@ -419,9 +472,15 @@ extern "C" int b200_fse_rebuild_index_dev(b200_ctx* ctx, uint64_t n, uint64_t bl
     fse_tables_kernel<<<(unsigned)L.nblocks, 32, 0, ctx->stream>>>(nullptr, reinterpret_cast<const uint16_t*>(d_side + L.off_norm),
                                                                   reinterpret_cast<uint16_t*>(d_side + L.off_norm),
                                                                   reinterpret_cast<uint32_t*>(d_side + L.off_tt));
-    fse_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_side + L.off_seg_bits), L.nsegs,
-                                                    reinterpret_cast<uint64_t*>(d_side + L.off_seg_word), ~0ull, info);
-    ctx->launches += 2;
+    const uint64_t ntiles = (L.nsegs + OFF_TILE - 1) / OFF_TILE;
+    uint64_t* tile_tot;
+    B200_TRY(b200_scratch(ctx, 6, 64 + (size_t)ntiles * 8 + 64, reinterpret_cast<void**>(&tile_tot)));
+    tile_tot += 8;
+    uint64_t* seg_word = reinterpret_cast<uint64_t*>(d_side + L.off_seg_word);
+    fse_tile_scan_kernel<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_side + L.off_seg_bits), L.nsegs, seg_word, tile_tot);
+    fse_tile_base_kernel<<<1, 1024, 0, ctx->stream>>>(tile_tot, ntiles, L.nsegs, seg_word, ~0ull, info);
+    fse_add_base_kernel<<<(unsigned)((L.nsegs + 255) / 256), 256, 0, ctx->stream>>>(seg_word, L.nsegs, tile_tot);
+    ctx->launches += 4;
     CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }

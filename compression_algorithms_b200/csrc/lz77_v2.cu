@@ -45,6 +45,7 @@ constexpr uint32_t MAXB = 65536;                             // max block bytes 
 constexpr uint32_t NTHREADS = 1024;
 constexpr uint32_t CARRY_BYTES = (MAXB + 64) * 4 + 32768 * 4 + MAXB * 4 + 32768 * 4;
 constexpr uint32_t NR = 32;                                  // ranges == warps
+constexpr uint32_t MAXF = 16;                                // forced cuts (two per hot chain) at most
 constexpr uint32_t CROWD_MIN = 12;                           // same-home entries in a batch from which the slot-ordered placement is used
 constexpr uint32_t FULL_WORD_WEIGHT = 6;                      // extra cost units per slot of a fully occupied bitmap word (range balancing, P2)
 constexpr uint32_t RUN8_WEIGHT = 4;                           // extra cost units per slot beyond the seventh of a run of occupied slots
@@ -76,7 +77,7 @@ struct Misc {
     uint32_t cut[NR + 1];
     uint32_t top_start, sp_lo_end, sp_hi_start, pad0;
     uint32_t rstart[NR + 1];
-    uint32_t fcut[16], nfcut;    // cuts forced just before / after a hot chain
+    uint32_t fcut[MAXF], nfcut;  // cuts forced just before / after a hot chain
     uint32_t ncar, cq_h, cq_t, ecarry;   // slices of a large block: live carried entries, clear-queue cursors, parse carry
     uint32_t cnt[NR][NR];        // [warp][range]
     uint32_t clr[64];            // slot-0 clear times (warp 0)
@@ -345,8 +346,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 cost[k] = (c0 + k < PRE_N && !hot) ? part[k] + RUN8_WEIGHT * run8[k] + FULL_WORD_WEIGHT * 32u * fullw[k + 1] : 0u;
                 mine_cost += cost[k];
                 if (hot && c0 + k < PRE_N) {
-                    if (!hot_prev && c0 + k >= 1) { const uint32_t i = atomicAdd(&ms->nfcut, 1u); if (i < 16) ms->fcut[i] = free_at_or_after((c0 + k - 1) * PRE_CHUNK * 32); }
-                    if (!hot_next && c0 + k + 1 < PRE_N) { const uint32_t i = atomicAdd(&ms->nfcut, 1u); if (i < 16) ms->fcut[i] = free_at_or_after((c0 + k + 1) * PRE_CHUNK * 32); }
+                    if (!hot_prev && c0 + k >= 1) { const uint32_t i = atomicAdd(&ms->nfcut, 1u); if (i < MAXF) ms->fcut[i] = free_at_or_after((c0 + k - 1) * PRE_CHUNK * 32); }
+                    if (!hot_next && c0 + k + 1 < PRE_N) { const uint32_t i = atomicAdd(&ms->nfcut, 1u); if (i < MAXF) ms->fcut[i] = free_at_or_after((c0 + k + 1) * PRE_CHUNK * 32); }
                 }
             }
             const uint32_t incl = warp_incl_scan_u32(mine);
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 if (lane == 31) ms->scan[32] = ti;
             }
             __syncthreads();
-            const uint32_t nforced = ms->nfcut < 16 ? ms->nfcut : 16;
+            const uint32_t nforced = ms->nfcut < MAXF ? ms->nfcut : MAXF;
             const uint32_t nq = NR - nforced;                                    // ranges shared out by entry count
             {
                 const uint64_t ctot = ms->scan[32] ? ms->scan[32] : 1;
@@ -571,6 +572,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v2_kernel(const uint8_t* __r
                 cur += by;
                 pf = cur + 32 + lane < end ? lists[cur + 32 + lane] : 0u;
             };
+            // ---- a range that is ONE pure chain (every entry has the same home and the same 4-byte pattern: constant or
+            // few-symbol input, chains of tens of thousands of entries) needs no table: find() only looks at the home
+            // slot, whose occupant changes exactly when an entry arrives after the occupant has expired (that entry finds
+            // nothing and takes the slot: lz77.c:55-108 with first-fit from the home). Verified on the fly; any other
+            // entry in the list and the simulation below starts over (it rewrites every token candidate).
+            if (C == 0 && last_slice && end - cur >= 64) {
+                const uint32_t e0 = lists[cur];
+                const uint32_t kk0 = e0 >> 16, w0 = sm_word(data, e0 & 0xFFFFu);
+                bool pure = !(kk0 < sp_lo_end || kk0 >= sp_hi_start);
+                uint32_t occ = NONE;                                   // position of the home slot's occupant
+                for (uint32_t c2 = cur; pure && c2 < end; c2 += 32) {
+                    const bool in = c2 + lane < end;
+                    const uint32_t e = in ? lists[c2 + lane] : e0;
+                    const uint32_t q = e & 0xFFFFu;
+                    if (__any_sync(0xffffffffu, (e >> 16) != kk0 || sm_word(data, q) != w0)) { pure = false; break; }
+                    uint32_t m = NONE;
+                    bool res = !in;
+                    for (;;) {
+                        if (!res && occ != NONE && occ + W >= q) { m = occ; res = true; }   // the occupant is live: match
+                        const uint32_t un = __ballot_sync(0xffffffffu, !res);
+                        if (!un) break;
+                        const int f = __ffs(un) - 1;                   // first entry that finds the slot dead: literal, takes the slot
+                        occ = __shfl_sync(0xffffffffu, q, f);
+                        if ((int)lane == f) res = true;
+                    }
+                    if (in) {
+                        uint32_t tk = 0;
+                        const bool reject = (m == NONE) || (V ? (q - m >= W - 1) : (q - m == W));
+                        if (!reject) tk = (q - m) | (match_len<MAXLEN>(data, m, q) << 16);
+                        tokb[q] = tk;
+                    }
+                }
+                if (pure) cur = end;
+            }
             while (cur < end) {
                 const uint32_t lanes = end - cur < 32 ? end - cur : 32;
                 uint32_t q = 0, kk = 0;
