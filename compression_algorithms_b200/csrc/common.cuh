@@ -38,7 +38,7 @@ struct b200_ctx {
     bool         own_stream;
     int          sm_count;
     // named scratch buffers, grown on demand and kept
-    static const int kSlots = 40;   // two banks of 20: the host compress path runs consecutive chunks on two kernel streams
+    static const int kSlots = 64;   // two banks of 20: the host compress path runs consecutive chunks on two kernel streams
     int          bank = 0;         // 0 or 1: which bank B200_SLOT() names (only host_api.cu switches it)
     void*        buf[kSlots];
     size_t       cap[kSlots];

@@ -437,6 +437,10 @@ int lz77_v4_launch(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t bs, 
 int lz77_v3_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
                    uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok);
 
+// token-parallel decoder for any block size (lz77_pdec.cu)
+int lz77_pdec_launch(b200_ctx* ctx, int variant, const uint8_t* d_stream, const uint64_t* d_block_off, const uint64_t* d_block_sizes,
+                     uint64_t n, uint64_t bs, uint64_t nblocks, uint8_t* d_out);
+
 extern "C" uint64_t b200_lz77_block_stride(uint64_t block_size) { return round16(2 * block_size + 16); }
 
 // scratch slots used: 1 tables, 2 clear queues, 3 token scratch, 4 block_bytes/info/err
@@ -562,6 +566,20 @@ extern "C" int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d
     uint32_t G = nblocks * 32 > (uint64_t)ctx->sm_count * 2048 ? 16u : 32u;
     if (const char* e = getenv("B200_LZ_DEC_G")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) G = (uint32_t)v; }
     const char* seq = getenv("B200_LZ_DEC_SERIAL");     // keep the token-serial decoder reachable for comparison
+    {
+        // one warp per block starves the GPU when blocks are few and large (a 4 MiB block decoded at 0.5 GB/s, the whole
+        // buffer as one block at 15 MB/s): from PDEC_MIN_BLOCK bytes per block on, every kernel works on the whole stream
+        const char* pd = getenv("B200_LZ_PDEC");        // 0 / 1: never / always
+        uint64_t min_block = variant ? (1ull << 20) : (1ull << 17);
+        if (const char* e = getenv("B200_LZ_PDEC_MIN_BLOCK")) { const long long v = atoll(e); if (v > 0) min_block = (uint64_t)v; }
+        const bool use_pdec = pd ? pd[0] == '1' : (bs >= min_block && bs < (1ull << 30) && !(seq && seq[0] == '1'));
+        if (use_pdec) {
+            B200_TIMED_BEGIN(ctx, B200_K_LZ_DECODE);
+            const int rc = lz77_pdec_launch(ctx, variant, d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
+            B200_TIMED_END(ctx);
+            return rc;
+        }
+    }
     if (variant == 1 && !(seq && seq[0] == '1')) {
         B200_TIMED_BEGIN(ctx, B200_K_LZ_DECODE);
         lz77_decode_units_kernel<<<(unsigned)((nblocks + 3) / 4), 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
