@@ -163,10 +163,10 @@ __global__ void __launch_bounds__(256) huff_decode_kernel(const uint32_t* __rest
                                                           uint64_t n, uint64_t bs, uint32_t cpb, uint32_t tiles_per_block,
                                                           const int16_t* __restrict__ tree, const uint32_t* __restrict__ meta,
                                                           const uint64_t* __restrict__ chunk_off, const uint32_t* __restrict__ sub_off,
-                                                          uint8_t* __restrict__ out) {
-    __shared__ uint16_t lut[1u << LUT_BITS];
+                                                          uint8_t* __restrict__ out, const uint16_t* __restrict__ lut_g, int build_only) {
+    __shared__ __align__(16) uint16_t lut[1u << LUT_BITS];
     __shared__ int16_t  kids[511][2];          // {left, right}; leaf = {-1, symbol}
-    const uint64_t b = blockIdx.x / tiles_per_block, k = blockIdx.x % tiles_per_block;
+    const uint64_t b = build_only ? blockIdx.x : blockIdx.x / tiles_per_block, k = build_only ? 0 : blockIdx.x % tiles_per_block;
     {
         const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tree + b * 511 * 2);
         uint32_t* k32 = reinterpret_cast<uint32_t*>(&kids[0][0]);
@@ -174,12 +174,23 @@ __global__ void __launch_bounds__(256) huff_decode_kernel(const uint32_t* __rest
     }
     const uint32_t root = meta[b * 4 + 2];
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < (1u << LUT_BITS); i += 256) {
-        uint32_t v = root, d = 0;
-        while (d < LUT_BITS && kids[v][0] >= 0) { v = (uint32_t)kids[v][(i >> (LUT_BITS - 1 - d)) & 1u]; ++d; }
-        lut[i] = kids[v][0] < 0 ? (uint16_t)(0x8000u | (d << 8) | (uint32_t)(uint16_t)kids[v][1]) : (uint16_t)v;   // leaf | inner node after 12 bits
+    if (lut_g && !build_only) {        // the table of this block was built once (several CTAs share a table scope): copy it
+        const uint4* src = reinterpret_cast<const uint4*>(lut_g + b * (1u << LUT_BITS));
+        uint4* dst = reinterpret_cast<uint4*>(lut);
+        for (uint32_t i = threadIdx.x; i < (1u << LUT_BITS) / 8; i += 256) dst[i] = __ldg(src + i);
+    } else {
+        for (uint32_t i = threadIdx.x; i < (1u << LUT_BITS); i += 256) {
+            uint32_t v = root, d = 0;
+            while (d < LUT_BITS && kids[v][0] >= 0) { v = (uint32_t)kids[v][(i >> (LUT_BITS - 1 - d)) & 1u]; ++d; }
+            lut[i] = kids[v][0] < 0 ? (uint16_t)(0x8000u | (d << 8) | (uint32_t)(uint16_t)kids[v][1]) : (uint16_t)v;   // leaf | inner node after 12 bits
+        }
     }
     __syncthreads();
+    if (build_only) {
+        uint16_t* dstg = const_cast<uint16_t*>(lut_g) + b * (1u << LUT_BITS);
+        for (uint32_t i = threadIdx.x; i < (1u << LUT_BITS); i += 256) dstg[i] = lut[i];
+        return;
+    }
 
     const uint64_t chunk = b * cpb + (uint64_t)k * TILE_CHUNKS + (threadIdx.x >> 4);
     const uint64_t sub = chunk * SUBS_PER_CHUNK + (threadIdx.x & 15);
@@ -580,11 +591,21 @@ extern "C" int b200_huffman_decode_dev(b200_ctx* ctx, const uint32_t* d_words, u
     const uint64_t bs = eff_block(n, block_size);
     const uint32_t cpb = (uint32_t)L.chunks_per_block;
     const uint32_t tpb = (cpb + TILE_CHUNKS - 1) / TILE_CHUNKS;
+    // a table scope decoded by four or more CTAs: its lookup table is built once and copied, instead of rebuilt by every CTA
+    uint16_t* lut_g = nullptr;
+    if (tpb >= 4) {
+        B200_TRY(b200_scratch(ctx, 7, (size_t)L.nblocks * (1u << LUT_BITS) * 2 + 64, reinterpret_cast<void**>(&lut_g)));
+        huff_decode_kernel<<<(unsigned)L.nblocks, 256, 0, ctx->stream>>>(
+            d_words, total_words, n, bs, cpb, tpb, reinterpret_cast<const int16_t*>(d_side + L.off_tree),
+            reinterpret_cast<const uint32_t*>(d_side + L.off_meta),
+            reinterpret_cast<const uint64_t*>(d_side + L.off_chunk_off), reinterpret_cast<const uint32_t*>(d_side + L.off_sub_off), d_out, lut_g, 1);
+        ctx->launches += 1;
+    }
     B200_TIMED_BEGIN(ctx, B200_K_HUFF_DECODE);
     huff_decode_kernel<<<(unsigned)(L.nblocks * tpb), 256, 0, ctx->stream>>>(
         d_words, total_words, n, bs, cpb, tpb, reinterpret_cast<const int16_t*>(d_side + L.off_tree),
         reinterpret_cast<const uint32_t*>(d_side + L.off_meta),
-        reinterpret_cast<const uint64_t*>(d_side + L.off_chunk_off), reinterpret_cast<const uint32_t*>(d_side + L.off_sub_off), d_out);
+        reinterpret_cast<const uint64_t*>(d_side + L.off_chunk_off), reinterpret_cast<const uint32_t*>(d_side + L.off_sub_off), d_out, lut_g, 0);
     B200_TIMED_END(ctx);
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
