@@ -44,10 +44,13 @@ constexpr uint32_t NONE16 = 0xFFFFu;
 constexpr uint32_t MAXB = 65536;
 constexpr uint32_t NTHREADS = 1024;
 constexpr uint32_t W = 1u << 15, MAXLEN = 31;
-constexpr uint32_t CH = 17408;                               // compact slots per chunk
+constexpr uint32_t CH = 17408;                               // compact slots of the final stage (entries + two occupants per slot)
+constexpr uint32_t CHC = 34816;                              // compact slots per chunk of the lane stage (entries only)
 constexpr uint32_t TMIN = 256;                               // clusters above this: four-warp teams; LMAX+1 .. TMIN: one warp
-constexpr uint32_t LMAX = 64;                                // largest cluster simulated by one lane (above 16: sorted by the warp first)
-constexpr uint32_t WL_CAP = 6656;                             // clusters of 2+ entries per chunk (work list entries)
+constexpr uint32_t L2MAX = 64;                               // final stage: clusters of LMAX+1 .. L2MAX entries are sorted by the warp and simulated one lane each
+constexpr uint32_t LMAX = 16;                                // largest cluster simulated by one lane (above 16: sorted by the warp first)
+constexpr uint32_t NBIG = 512;                               // clusters above LMAX entries per block (kept for the final stage)
+constexpr uint32_t WL_CAP = 7680;                             // clusters of 2+ entries per chunk (work list entries)
 constexpr uint32_t CL_MAX = 16383;                           // largest cluster (home offsets are 14 bits)
 constexpr uint32_t PLACED = 0x80000000u, ISHOME = 0x40000000u;
 
@@ -64,7 +67,8 @@ constexpr uint32_t SZ_MISC = 1792;
 constexpr uint32_t SMEM_BYTES = OFF_MISC + SZ_MISC;
 static_assert(SMEM_BYTES <= 232448, "shared memory layout too large");
 static_assert(CH * 8 <= SZ_BIG, "chunk does not fit");
-static_assert(WL_CAP * 2 + 32 * 32 * 4 <= SZ_PRE, "work list + warp scratch do not fit");
+static_assert(WL_CAP * 2 + NBIG * 4 <= SZ_PRE && 4096 + 32 * 32 * 4 <= WL_CAP * 2, "work list + big-cluster list / rank prefix + warp scratch do not fit");
+static_assert(CHC * 4 <= SZ_BIG, "lane-stage chunk does not fit");
 
 constexpr uint32_t PADDED = MAXB + (MAXB >> 6) * 4;          // 69632
 #define PADX(p) ((p) + (((p) >> 6) << 2))
@@ -72,9 +76,10 @@ constexpr uint32_t PADDED = MAXB + (MAXB >> 6) * 4;          // 69632
 struct Misc {
     uint32_t scan[34];
     uint32_t p1_next, fallback, ce, pad0;
-    uint32_t ccnt[7], cbase[8], cfill[7], next_t, next_w, next_l;   // work list by size class: teams | 17..64 | 9..16 | 5..8 | 3..4 | 2
+    uint32_t ccnt[7], cbase[8], cfill[7], next_t, next_w, next_l;   // work list by size class: 17..64 | 9..16 | 5..8 | 3..4 | 2
+    uint32_t nbig, r0, r1, rdone;                                   // big-cluster list; the round of the final stage
     uint32_t tpick[8];
-    uint32_t tscr[8][2][4];      // cross-warp scan scratch of the eight four-warp teams
+    uint32_t tscr[8][12];        // per four-warp team: [2][4] cross-warp scan scratch, word 8 = phase-1 progress of a pipelined sweep
     uint8_t  sexit[32][32];
     uint8_t  sentry[36];
 };
@@ -94,6 +99,17 @@ __device__ __forceinline__ uint32_t match_len(const uint8_t* data, uint32_t m, u
         l += 4;
     }
     return l < MAXLEN ? l : MAXLEN;
+}
+
+// position of the n-th set bit of x (n = 0 .. popc(x) - 1): five popcount steps (__fns walks bit by bit)
+__device__ __forceinline__ uint32_t nth_set(uint32_t x, uint32_t n) {
+    uint32_t pos = 0, c;
+    c = __popc(x & 0xFFFFu); if (n >= c) { n -= c; pos = 16; x >>= 16; }
+    c = __popc(x & 0xFFu);   if (n >= c) { n -= c; pos += 8; x >>= 8; }
+    c = __popc(x & 0xFu);    if (n >= c) { n -= c; pos += 4; x >>= 4; }
+    c = __popc(x & 0x3u);    if (n >= c) { n -= c; pos += 2; x >>= 2; }
+    if (n >= (x & 1u)) pos += 1;
+    return pos;
 }
 
 __device__ __forceinline__ uint32_t bm_rank(const uint32_t* bm, const uint16_t* pre16, uint32_t s) {
@@ -229,12 +245,15 @@ template <int TEAM> struct Team {
 // candidate pool of the sub-segment being swept (a slot's final value overwrites a pool entry no later slot needs).
 template <int TEAM>
 __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t* E2x, uint32_t m, uint32_t cstart,
-                            const uint8_t* data, uint16_t* fres, uint32_t* scr) {
+                            const uint8_t* data, uint16_t* fres, uint32_t* scr, uint32_t* tdbg = nullptr) {
     const uint32_t tt = T.tt;
+    long long t_m = tdbg ? clock64() : 0;
+#define BC_STAMP(k) do { if (tdbg && tt == 0) { const long long t_n = clock64(); atomicAdd(&tdbg[k], (uint32_t)((t_n - t_m) >> 6)); t_m = t_n; } } while (0)
     for (uint32_t i = tt; i < m; i += TEAM) { const uint32_t e = Sx[i]; Sx[i] = (e & 0xFFFFu) | (((e >> 16) - cstart) << 16); }
     T.sync();
     // bitonic sort by position (all comparators ascending, so the virtual +inf padding behind m never moves)
     uint32_t P = 2; while (P < m) P <<= 1;
+    if (TEAM == 32 && m <= 64) { warp_sort64(Sx, m, 0u); __syncwarp(); P = 1; }   // two registers per lane instead of shared memory
     for (uint32_t k = 2; k <= P; k <<= 1) {
         const uint32_t half = k >> 1;
         for (uint32_t idx = tt; idx < (P >> 1); idx += TEAM) {
@@ -252,6 +271,7 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
             T.sync();
         }
     }
+    BC_STAMP(0);
     for (uint32_t i = tt; i < m; i += TEAM) atomicOr(&Sx[(Sx[i] >> 16) & 0x3FFFu], ISHOME);
     T.sync();
     uint32_t n1;                                             // phase-1 entries: positions 0 .. W
@@ -308,8 +328,11 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
     // a sub-segment ranks / selects in the mask as it was at its start (the pool of the recurrence is fixed), the slots it
     // hands out are cleared through 32 words of scratch. No compaction, no barriers.
     if (n1 <= 1024u && m - n1 <= 1024u) {
-        if (TEAM != 32 && tt >= 32u) return;
-        const uint32_t lane = tt;
+        const uint32_t lane = tt & 31u;
+        // TEAM == 128: warp 0 sweeps phase 1 and publishes how far its slots are final, warp 1 sweeps phase 2 right behind it
+        // (a sub-segment of phase 2 needs the phase-1 occupants of its own slots only); the whole team does the finds.
+        volatile uint32_t* prog = (TEAM == 32) ? nullptr : reinterpret_cast<volatile uint32_t*>(T.scr + 8);
+        if (TEAM != 32) { if (tt == 0) *prog = 0; T.sync(); }
         auto next_home_w = [&](uint32_t x) -> uint32_t {
             for (uint32_t base = x + 1; base < m; base += 32) {
                 const uint32_t j = base + lane;
@@ -321,9 +344,13 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
         for (uint32_t ph = 0; ph < 2; ++ph) {
             const uint32_t ebase = ph ? n1 : 0u, cntp = ph ? m - n1 : n1;
             uint16_t* Ex = ph ? E2x : E1x;
+            if (ph && TEAM == 32) BC_STAMP(1);
+            const bool sweeper = (TEAM == 32) ? true : ((tt >> 5) == ph);
+            if (!sweeper) continue;
             if (cntp == 0) {
                 for (uint32_t j = lane; j < m; j += 32) Ex[j] = (uint16_t)NONE16;
                 __syncwarp();
+                if (!ph && TEAM != 32 && lane == 0) { __threadfence_block(); *prog = m; }
                 continue;
             }
             uint32_t elig = 0, pend = 0;
@@ -342,6 +369,7 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                         if (((Sx[ebase + 32u * lane + bq] >> 16) & 0x3FFFu) <= x) { elig |= 1u << bq; pend &= ~(1u << bq); }
                     }
                 }
+                if (ph && TEAM != 32) { while (*prog < xe) { } __threadfence_block(); }   // phase 1 is past this segment
                 uint32_t used = xe;
                 if (ph) { uint32_t a = x, b = xe; while (a < b) { const uint32_t mid = (a + b) >> 1; if (E1x[mid] != NONE16) a = mid + 1; else b = mid; } used = a; }
                 for (uint32_t part = 0; part < (ph ? 2u : 1u); ++part) {
@@ -385,7 +413,7 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                             if (c < 32u && pcand <= idx) t = c;
                         }
                         const uint32_t pt = __shfl_sync(0xffffffffu, pre, t), et = __shfl_sync(0xffffffffu, elig0, t);
-                        const uint32_t g = take ? 32u * t + __fns(et, 0u, (int)(idx - pt + 1u)) : 0u;
+                        const uint32_t g = take ? 32u * t + nth_set(et, idx - pt) : 0u;
                         const uint32_t ent = take ? ebase + g : NONE16;
                         if (valid) Ex[j] = (uint16_t)ent;
                         if (take) atomicOr(&scr[g >> 5], 1u << (g & 31u));
@@ -394,12 +422,6 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                         __syncwarp();
                         scr[lane] = 0;
                         __syncwarp();
-                        {
-                            uint32_t p = 0, o = 0;
-                            if (take) { const uint32_t e = Sx[ent]; p = e & 0xFFFFu; o = (e >> 16) & 0x3FFFu; }
-                            const uint32_t f = find(take, o, j, p, ph != 0u);
-                            if (take) fres[p] = (uint16_t)f;
-                        }
                         if ((int)(i0 + 32u) + carry >= (int)np) {
                             for (uint32_t j2 = lo + i0 + 32u + lane; j2 < hi; j2 += 32) Ex[j2] = (uint16_t)NONE16;
                             break;
@@ -407,9 +429,27 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                     }
                     __syncwarp();
                 }
+                if (!ph && TEAM != 32) { __syncwarp(); if (lane == 0) { __threadfence_block(); *prog = xe; } }
                 x = xe;
             }
         }
+        BC_STAMP(3);
+        // post-pass (whole team): the finds, slot by slot (every occupant of [home, own slot) is final now; an e1 that had
+        // expired at p's time was followed by an e2 placed before p, or the slot would have been dead and p would sit there)
+        T.sync();
+        for (uint32_t base = 0; base < m; base += TEAM) {
+            const uint32_t j = base + tt;
+#pragma unroll
+            for (uint32_t ph = 0; ph < 2; ++ph) {
+                const uint32_t i = j < m ? (uint32_t)(ph ? E2x[j] : E1x[j]) : NONE16;
+                const bool act = i != NONE16;
+                uint32_t p = 0, o = 0;
+                if (act) { const uint32_t e = Sx[i]; p = e & 0xFFFFu; o = (e >> 16) & 0x3FFFu; }
+                const uint32_t f = find(act, o, j, p, ph != 0u);
+                if (act) fres[p] = (uint16_t)f;
+            }
+        }
+        BC_STAMP(4);
         return;
     }
     // ---- phase 1: between two homes the next slots go to the next unplaced entries whose home is at/before the segment
@@ -542,7 +582,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
     uint16_t* E1 = reinterpret_cast<uint16_t*>(big + CH * 4);
     uint16_t* E2 = E1 + CH;
     uint16_t* wl = reinterpret_cast<uint16_t*>(smem + OFF_PRE);   // work list: local start of every cluster of 2+ entries, largest classes first
-    uint32_t* wscr = reinterpret_cast<uint32_t*>(smem + OFF_PRE + WL_CAP * 2);   // 32 words per warp (zero between uses)
+    uint32_t* bigl = reinterpret_cast<uint32_t*>(smem + OFF_PRE + WL_CAP * 2);   // clusters above LMAX entries: compact start | size << 16
+    uint32_t* wscr = reinterpret_cast<uint32_t*>(smem + OFF_PRE + 4096);          // final stage only (behind its rank prefix): 32 words per warp, zero between uses
     uint8_t* adv = big;
     uint8_t* exitof = big + PADDED;
 
@@ -568,7 +609,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
             for (uint32_t i = tid; i < BM_WORDS; i += NTHREADS) bm[i] = 0;
             for (uint32_t i = tid; i < BM_WORDS / 32; i += NTHREADS) pre[i] = 0;
             for (uint32_t i = tid; i < SZ_FLAGS / 4; i += NTHREADS) flags[i] = 0;
-            if (tid == 0) { ms->p1_next = 0; ms->fallback = 0; }
+            if (tid == 0) { ms->p1_next = 0; ms->fallback = 0; ms->nbig = 0; }
         }
         __syncthreads();
         PHASE_STAMP(0);
@@ -700,13 +741,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
         // ---------------- clusters, one chunk of the compact slot space at a time
         uint32_t cb = 0;
         long long dt_sc = 0, dt_c2 = 0, dt_w = 0, dt_t = 0, dt_wait = 0, t_mark = CLK();
-        uint32_t n_chunks = 0, n_wq = 0, n_tq = 0;
+        uint32_t n_chunks = 0, n_wq = 0;
 #define SUBSTAMP(acc) do { if (DBG) { const long long t_now = clk_ordered(); acc += t_now - t_mark; t_mark = t_now; } } while (0)
         while (!fb0 && cb < len) {
             if (tid == 0) {
                 uint32_t ce = len;
-                if (len - cb > CH) {                         // last cluster start at/before cb + CH
-                    const uint32_t pos = cb + CH;
+                if (len - cb > CHC) {                        // last cluster start at/before cb + CHC
+                    const uint32_t pos = cb + CHC;
                     uint32_t wi = pos >> 5;
                     uint32_t xw = flags[wi] & (0xFFFFFFFFu >> (31u - (pos & 31u)));
                     while (!xw) { --wi; xw = flags[wi]; }
@@ -733,104 +774,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
             __syncthreads();
             SUBSTAMP(dt_sc);
             // work list: every thread looks at 17 compact slots, counts its clusters per size class, then files them
-            auto cls_of = [](uint32_t m) -> uint32_t { return m > TMIN ? 0u : m > LMAX ? 1u : m > 16 ? 2u : m > 8 ? 3u : m > 4 ? 4u : m > 2 ? 5u : 6u; };
-            const uint32_t lo17 = tid * 17;
-            uint32_t nlbits = 0;                              // starts of clusters of 2+ entries among my slots
-            if (lo17 < cnt) {
-                const uint32_t hi = lo17 + 17 < cnt ? lo17 + 17 : cnt;
-                const uint32_t a = cb + lo17;
-                const unsigned long long win = ((unsigned long long)flags[(a >> 5) + 1] << 32) | flags[a >> 5];
-                const uint32_t fb = (uint32_t)(win >> (a & 31u));        // flags of a .. a + 31 (18 are needed)
-                uint32_t bits = fb & ((1u << (hi - lo17)) - 1u) & ~(fb >> 1);   // a start directly followed by a start is a loner
-                nlbits = bits;
-                while (bits) {
-                    const uint32_t k = (uint32_t)(__ffs(bits) - 1);
-                    bits &= bits - 1;
-                    const uint32_t start = a + k, q = start + 1;
-                    uint32_t wi = q >> 5;
-                    uint32_t xw = flags[wi] & (0xFFFFFFFFu << (q & 31u));
-                    while (!xw) { ++wi; xw = flags[wi]; }
-                    const uint32_t m = (wi << 5) + (uint32_t)(__ffs(xw) - 1) - start;
-                    if (m > CL_MAX) { ms->fallback = 1u; continue; }
-                    E1[lo17 + k] = (uint16_t)m;
-                    atomicAdd(&ms->ccnt[cls_of(m)], 1u);
+            auto cls_of = [](uint32_t m) -> uint32_t { return m > 8 ? 3u : m > 4 ? 4u : m > 2 ? 5u : 6u; };
+            // (a thread looks at 2 x 17 compact slots; the size of a listed cluster is read from the flags again when it is worked)
+            auto csize = [&](uint32_t start) -> uint32_t {
+                const uint32_t q = start + 1;
+                uint32_t wi = q >> 5;
+                uint32_t xw = flags[wi] & (0xFFFFFFFFu << (q & 31u));
+                while (!xw) { ++wi; xw = flags[wi]; }
+                return (wi << 5) + (uint32_t)(__ffs(xw) - 1) - start;
+            };
+            uint32_t nlb[2] = {0, 0};                         // starts of clusters of 2 .. LMAX entries among my slots
+#pragma unroll
+            for (uint32_t h = 0; h < 2; ++h) {
+                const uint32_t lo17 = tid * 34 + h * 17;
+                if (lo17 < cnt) {
+                    const uint32_t hi = lo17 + 17 < cnt ? lo17 + 17 : cnt;
+                    const uint32_t a = cb + lo17;
+                    const unsigned long long win = ((unsigned long long)flags[(a >> 5) + 1] << 32) | flags[a >> 5];
+                    const uint32_t fb = (uint32_t)(win >> (a & 31u));        // flags of a .. a + 31 (18 are needed)
+                    uint32_t bits = fb & ((1u << (hi - lo17)) - 1u) & ~(fb >> 1);   // a start directly followed by a start is a loner
+                    nlb[h] = bits;
+                    while (bits) {
+                        const uint32_t k = (uint32_t)(__ffs(bits) - 1);
+                        bits &= bits - 1;
+                        const uint32_t start = a + k;
+                        const uint32_t m = csize(start);
+                        if (m > LMAX) {                          // kept for the final stage, where all of them run at once
+                            nlb[h] &= ~(1u << k);
+                            const uint32_t bi = m <= CL_MAX ? atomicAdd(&ms->nbig, 1u) : NBIG;
+                            if (bi < NBIG) bigl[bi] = start | (m << 16); else ms->fallback = 1u;
+                            continue;
+                        }
+                        atomicAdd(&ms->ccnt[cls_of(m)], 1u);
+                    }
                 }
             }
             __syncthreads();
             if (tid == 0) {
                 uint32_t run = 0;
                 for (int c = 0; c < 7; ++c) { ms->cbase[c] = run; run += ms->ccnt[c]; }
-                ms->cbase[7] = run; ms->next_t = 0; ms->next_w = ms->cbase[1]; ms->next_l = ms->cbase[2];
+                ms->cbase[7] = run; ms->next_l = 0;
                 if (run > WL_CAP) ms->fallback = 1u;
             }
-            wscr[tid] = 0;
             __syncthreads();
-            while (nlbits) {
-                const uint32_t k = (uint32_t)(__ffs(nlbits) - 1);
-                nlbits &= nlbits - 1;
-                const uint32_t m = E1[lo17 + k];
-                if (m > CL_MAX || ms->fallback) continue;
-                const uint32_t c = cls_of(m);
-                wl[ms->cbase[c] + atomicAdd(&ms->cfill[c], 1u)] = (uint16_t)(lo17 + k);
+#pragma unroll
+            for (uint32_t h = 0; h < 2; ++h) {
+                const uint32_t lo17 = tid * 34 + h * 17;
+                uint32_t nlbits = nlb[h];
+                while (nlbits && !ms->fallback) {
+                    const uint32_t k = (uint32_t)(__ffs(nlbits) - 1);
+                    nlbits &= nlbits - 1;
+                    const uint32_t c = cls_of(csize(cb + lo17 + k));
+                    wl[ms->cbase[c] + atomicAdd(&ms->cfill[c], 1u)] = (uint16_t)(lo17 + k);
+                }
             }
             __syncthreads();
             SUBSTAMP(dt_c2);
             if (!ms->fallback) {
-                const uint32_t tq_n = ms->cbase[1], wq_end = ms->cbase[2], total = ms->cbase[7];
-                if (DBG) { ++n_chunks; n_wq += total - tq_n; n_tq += tq_n; }
-                if (tq_n) {                                  // clusters above LMAX entries: slot sweeps by four-warp teams
-                    const uint32_t team = warp >> 2;
-                    Team<128> TT; TT.tt = tid & 127u; TT.bar = 1u + team; TT.scr = &ms->tscr[team][0][0]; TT.par = 0;
-                    for (;;) {
-                        if (TT.tt == 0) ms->tpick[team] = atomicAdd(&ms->next_t, 1u);
-                        TT.sync();
-                        const uint32_t qi = ms->tpick[team];
-                        TT.sync();
-                        if (qi >= tq_n) break;
-                        const uint32_t kl = wl[qi], m = E1[kl];
-                        TT.sync();                           // (E1 is about to be rewritten)
-                        const long long t_c0 = CLK();
-                        big_cluster<128>(TT, S + kl, E1 + kl, E2 + kl, m, cb + kl, data, fres, wscr + warp * 32);
-                        if (DBG && dbg_stats && TT.tt == 0) {
-                            const uint32_t dtc = (uint32_t)((clock64() - t_c0) >> 6);
-                            atomicMax(&dbg_stats[(uint64_t)b * 136 + 16], (dtc << 14) | m);
-                            atomicAdd(&dbg_stats[(uint64_t)b * 136 + 24 + team], dtc);
-                            atomicAdd(&dbg_stats[(uint64_t)b * 136 + 17], m);
-                        }
-                    }
-                }
-                if (DBG) SUBSTAMP(dt_t);
-                {                                            // LMAX+1 .. TMIN entries: slot sweeps by one warp
-                    Team<32> TW; TW.tt = lane; TW.bar = 0; TW.scr = nullptr; TW.par = 0;
-                    for (;;) {
-                        uint32_t qi = 0;
-                        if (lane == 0) qi = atomicAdd(&ms->next_w, 1u);
-                        qi = __shfl_sync(0xffffffffu, qi, 0);
-                        if (qi >= wq_end) break;
-                        const uint32_t kl = wl[qi], m = E1[kl];
-                        __syncwarp();
-                        big_cluster<32>(TW, S + kl, E1 + kl, E2 + kl, m, cb + kl, data, fres, wscr + warp * 32);
-                    }
-                }
+                const uint32_t total = ms->cbase[7];
+                if (DBG) { ++n_chunks; n_wq += total; }
                 for (;;) {                                   // 32 clusters of similar size per warp, one lane each
                     uint32_t g = 0;
                     if (lane == 0) g = atomicAdd(&ms->next_l, 32u);
                     g = __shfl_sync(0xffffffffu, g, 0);
                     if (g >= total) break;
                     const uint32_t it = g + lane;
-                    const bool has = it < total;
-                    const uint32_t kl = has ? wl[it] : 0u;
-                    const uint32_t m = has ? E1[kl] : 0u;
-                    uint32_t coop = __ballot_sync(0xffffffffu, m > 16);
-                    while (coop) {                           // 17 .. 64 entries: the warp sorts, the lane simulates
-                        const int srcl = __ffs(coop) - 1;
-                        coop &= coop - 1;
-                        { const uint32_t kk = __shfl_sync(0xffffffffu, kl, srcl); warp_sort64(S + kk, __shfl_sync(0xffffffffu, m, srcl), cb + kk); }
-                    }
-                    __syncwarp();
-                    if (has) {
-                        if (m <= 16) { lane_sort(S + kl, m); lane_cluster<true>(S + kl, nullptr, nullptr, m, cb + kl, data, fres); }
-                        else lane_cluster<false>(S + kl, E1 + kl, E2 + kl, m, 0u, data, fres);
+                    if (it < total) {
+                        const uint32_t kl = wl[it], m = csize(cb + kl);
+                        lane_sort(S + kl, m);
+                        lane_cluster<true>(S + kl, nullptr, nullptr, m, cb + kl, data, fres);
                     }
                 }
                 if (DBG) SUBSTAMP(dt_w);
@@ -839,9 +851,130 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
             SUBSTAMP(dt_wait);
             cb = ce;
         }
+        // ---------------- final stage: the clusters above LMAX entries, all at once (the largest decides, not their sum).
+        // Rounds of as many listed clusters as fit the chunk area; a bit per compact slot says "in a cluster of this round",
+        // the rank in that bit map is the slot's place in S.
+        while (!fb0 && !ms->fallback && ms->nbig) {
+            const uint32_t nbig = ms->nbig;
+            __syncthreads();
+            if (tid == 0) { ms->rdone = 0; }
+            {   // rank-sort the list by compact start (one thread per entry)
+                uint32_t v = 0, rk = 0;
+                if (tid < nbig) { v = bigl[tid]; for (uint32_t j = 0; j < nbig; ++j) rk += (bigl[j] & 0xFFFFu) < (v & 0xFFFFu) ? 1u : 0u; }
+                __syncthreads();
+                if (tid < nbig) bigl[rk] = v;
+            }
+            __syncthreads();
+            uint32_t r0 = 0;
+            while (r0 < nbig) {
+                if (tid == 0) {                                  // clusters r0 .. r1 of this round
+                    uint32_t r1 = r0, tot = 0;
+                    while (r1 < nbig && tot + (bigl[r1] >> 16) <= CH) { tot += bigl[r1] >> 16; ++r1; }
+                    ms->r0 = r0; ms->r1 = r1; ms->next_t = r0; ms->rdone = 0; ms->next_w = r0;
+                }
+                for (uint32_t i = tid; i < SZ_FLAGS / 4; i += NTHREADS) flags[i] = 0;
+                wscr[tid] = 0;
+                __syncthreads();
+                const uint32_t r1 = ms->r1;
+                for (uint32_t k = r0 + warp; k < r1; k += 32) {      // bits of the cluster's slots
+                    const uint32_t cs0 = bigl[k] & 0xFFFFu, m = bigl[k] >> 16;
+                    for (uint32_t w = (cs0 >> 5) + lane; w <= ((cs0 + m - 1) >> 5); w += 32) {
+                        uint32_t mask = 0xFFFFFFFFu;
+                        if (w == (cs0 >> 5)) mask &= 0xFFFFFFFFu << (cs0 & 31u);
+                        if (w == ((cs0 + m - 1) >> 5)) mask &= 0xFFFFFFFFu >> (31u - ((cs0 + m - 1) & 31u));
+                        atomicOr(&flags[w], mask);
+                    }
+                }
+                __syncthreads();
+                {   // rank prefix per word (u16 at pre16[0 .. 2048]: the work-list area is free now)
+                    const uint32_t w0 = flags[2 * tid], w1 = flags[2 * tid + 1];
+                    const uint32_t s2 = __popc(w0) + __popc(w1);
+                    const uint32_t incl = warp_incl_scan_u32(s2);
+                    if (lane == 31) ms->scan[warp] = incl;
+                    __syncthreads();
+                    if (warp == 0) { const uint32_t t = ms->scan[lane]; const uint32_t ti = warp_incl_scan_u32(t); ms->scan[lane] = ti - t; }
+                    __syncthreads();
+                    const uint32_t ex = ms->scan[warp] + incl - s2;
+                    pre16[2 * tid] = (uint16_t)ex; pre16[2 * tid + 1] = (uint16_t)(ex + __popc(w0));
+                }
+                __syncthreads();
+                auto brank = [&](uint32_t u) -> uint32_t { return pre16[u >> 5] + __popc(flags[u >> 5] & ((1u << (u & 31u)) - 1u)); };
+                for (uint32_t i0 = tid; i0 < len; i0 += 8 * NTHREADS) {
+                    uint32_t tv[8];
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; ++k) { const uint32_t i = i0 + k * NTHREADS; tv[k] = i < len ? tokb[i] : LONER; }
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; ++k) {
+                        if (tv[k] != LONER) {
+                            const uint32_t u = tv[k] & 0xFFFFu;
+                            if ((flags[u >> 5] >> (u & 31u)) & 1u) S[brank(u)] = (i0 + k * NTHREADS) | ((u - (tv[k] >> 16)) << 16);
+                        }
+                    }
+                }
+                __syncthreads();
+                {
+                    Team<128> TT; const uint32_t team = warp >> 2;
+                    TT.tt = tid & 127u; TT.bar = 1u + team; TT.scr = &ms->tscr[team][0]; TT.par = 0;
+                    Team<32> TW; TW.tt = lane; TW.bar = 0; TW.scr = nullptr; TW.par = 0;
+                    // clusters above TMIN entries by four-warp teams, largest first would be better still: list order
+                    for (;;) {
+                        if (TT.tt == 0) {
+                            uint32_t qi;
+                            for (;;) { qi = atomicAdd(&ms->next_t, 1u); if (qi >= r1 || (bigl[qi] >> 16) > TMIN) break; }
+                            ms->tpick[team] = qi;
+                        }
+                        TT.sync();
+                        const uint32_t qi = ms->tpick[team];
+                        TT.sync();
+                        if (qi >= r1) break;
+                        const uint32_t cs0 = bigl[qi] & 0xFFFFu, m = bigl[qi] >> 16, kl = brank(cs0);
+                        const long long t_c0 = CLK();
+                        big_cluster<128>(TT, S + kl, E1 + kl, E2 + kl, m, cs0, data, fres, wscr + warp * 32, (DBG && dbg_stats) ? dbg_stats + (uint64_t)b * 136 + 40 : nullptr);
+                        if (DBG && dbg_stats && TT.tt == 0) {
+                            const uint32_t dtc = (uint32_t)((clock64() - t_c0) >> 6);
+                            atomicMax(&dbg_stats[(uint64_t)b * 136 + 16], (dtc << 14) | m);
+                            atomicAdd(&dbg_stats[(uint64_t)b * 136 + 24 + team], dtc);
+                            atomicAdd(&dbg_stats[(uint64_t)b * 136 + 17], m);
+                            atomicAdd(&dbg_stats[(uint64_t)b * 136 + 14], 1u);
+                        }
+                    }
+                    for (;;) {                                   // L2MAX+1 .. TMIN entries: one warp each
+                        uint32_t qi = 0;
+                        if (lane == 0) { for (;;) { qi = atomicAdd(&ms->rdone, 1u) + r0; if (qi >= r1 || ((bigl[qi] >> 16) <= TMIN && (bigl[qi] >> 16) > L2MAX)) break; } }
+                        qi = __shfl_sync(0xffffffffu, qi, 0);
+                        if (qi >= r1) break;
+                        const uint32_t cs0 = bigl[qi] & 0xFFFFu, m = bigl[qi] >> 16, kl = brank(cs0);
+                        big_cluster<32>(TW, S + kl, E1 + kl, E2 + kl, m, cs0, data, fres, wscr + warp * 32);
+                    }
+                    for (;;) {                                   // LMAX+1 .. L2MAX entries: 32 listed clusters per warp, the warp sorts, a lane simulates
+                        uint32_t g = 0;
+                        if (lane == 0) g = atomicAdd(&ms->next_w, 32u);
+                        g = __shfl_sync(0xffffffffu, g, 0);
+                        if (g >= r1) break;
+                        const uint32_t qi = g + lane;
+                        const uint32_t ent = qi < r1 ? bigl[qi] : 0u;
+                        const uint32_t m = ent >> 16, cs0 = ent & 0xFFFFu;
+                        const bool mine = m > LMAX && m <= L2MAX;
+                        const uint32_t kl = mine ? brank(cs0) : 0u;
+                        uint32_t coop = __ballot_sync(0xffffffffu, mine);
+                        while (coop) {
+                            const int srcl = __ffs(coop) - 1;
+                            coop &= coop - 1;
+                            warp_sort64(S + __shfl_sync(0xffffffffu, kl, srcl), __shfl_sync(0xffffffffu, m, srcl), __shfl_sync(0xffffffffu, cs0, srcl));
+                        }
+                        __syncwarp();
+                        if (mine) lane_cluster<false>(S + kl, E1 + kl, E2 + kl, m, 0u, data, fres);
+                    }
+                }
+                __syncthreads();
+                r0 = r1;
+            }
+            break;
+        }
+        SUBSTAMP(dt_t);
         if (DBG && dbg_stats && tid == 0) {
             uint32_t* o = dbg_stats + (uint64_t)b * 136 + 8;
-            o[0] = (uint32_t)dt_sc; o[1] = (uint32_t)dt_c2; o[2] = (uint32_t)dt_w; o[3] = (uint32_t)dt_t; o[4] = n_chunks; o[5] = n_wq; o[6] = n_tq; o[7] = (uint32_t)dt_wait;
+            o[0] = (uint32_t)dt_sc; o[1] = (uint32_t)dt_c2; o[2] = (uint32_t)dt_w; o[3] = (uint32_t)dt_t; o[4] = n_chunks; o[5] = n_wq; o[7] = (uint32_t)dt_wait;
         }
         __syncthreads();
         if (ms->fallback) {                                  // hand the block to lz77_v2_kernel

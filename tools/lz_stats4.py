@@ -19,9 +19,11 @@ for k, nm in enumerate(names):
     dtk = ph[:, k] - prev; prev = ph[:, k]
     print("  %-16s median %8d  p90 %8d  max %8d cycles" % (nm, np.median(dtk), np.percentile(dtk, 90), dtk.max()))
 x = s[:, 8:16]
-for k, nm in enumerate(["scatter", "work list", "warp + lane tiers (thread 0)", "teams (thread 0)", "chunks", "warp/lane clusters", "team clusters", "wait at chunk end (thread 0)"]):
+for k, nm in enumerate(["scatter", "work list", "lane tiers (thread 0)", "final stage: clusters above 64 entries", "chunks", "warp/lane clusters", "team clusters (above 256)", "wait at chunk end (thread 0)"]):
     print("  %-26s median %8d  max %8d" % (nm, np.median(x[:, k]), x[:, k].max()))
 mx = s[:, 16]; print("  slowest team cluster: median %d cycles (m %d), max %d cycles (m %d); entries in team clusters median %d" % (np.median(mx >> 14) * 64, np.median(mx & 0x3FFF), (mx >> 14).max() * 64, (mx[np.argmax(mx >> 14)] & 0x3FFF), np.median(s[:, 17])))
 tt = s[:, 24:32] * 64; print("  per-team busy cycles: median of max %d, median of mean %d" % (np.median(tt.max(1)), np.median(tt.mean(1))))
 for bi in range(3):
     print("   block", bi, "slowest", (mx[bi] >> 14) * 64, "m", mx[bi] & 0x3FFF, "team busy", list(tt[bi]))
+tb = s[:, 40:45] * 64
+print("  team clusters, cycles summed over the block's clusters (median): sort %d, phase-1 sweep %d, release ranks %d, phase-2 sweep %d, finds %d" % tuple(np.median(tb[:, k]) for k in range(5)))
