@@ -332,7 +332,32 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
         // TEAM == 128: warp 0 sweeps phase 1 and publishes how far its slots are final, warp 1 sweeps phase 2 right behind it
         // (a sub-segment of phase 2 needs the phase-1 occupants of its own slots only); the whole team does the finds.
         volatile uint32_t* prog = (TEAM == 32) ? nullptr : reinterpret_cast<volatile uint32_t*>(T.scr + 8);
-        if (TEAM != 32) { if (tt == 0) *prog = 0; T.sync(); }
+        volatile uint32_t* progg = (TEAM == 32) ? nullptr : reinterpret_cast<volatile uint32_t*>(T.scr + 9);
+        if (TEAM != 32) { if (tt == 0) { *prog = 0; *progg = 0; } T.sync(); }
+        if (TEAM != 32 && (tt >> 5) == 2u && m - n1 > 0u) {
+            // warp 2: for every slot phase 1 has finished, how many phase-2 entries arrive before the slot is dead (lower bound
+            // of its release time in the time-ordered phase-2 entries); parked in E2x[j] until phase 2 reaches the slot
+            const uint32_t cnt2 = m - n1;
+            uint32_t donej = 0;
+            while (donej < m) {
+                uint32_t lim;
+                while ((lim = *prog) <= donej) { __nanosleep(40); }
+                __threadfence_block();
+                for (uint32_t j = donej + lane; j < lim; j += 32) {
+                    const uint32_t y1 = E1x[j];
+                    uint32_t a = 0;
+                    if (y1 != NONE16) {
+                        const uint32_t rel = (Sx[y1] & 0xFFFFu) + W + 1u;
+                        uint32_t b = cnt2;
+                        while (a < b) { const uint32_t mid = (a + b) >> 1; if ((Sx[n1 + mid] & 0xFFFFu) >= rel) b = mid; else a = mid + 1; }
+                    }
+                    E2x[j] = (uint16_t)a;
+                }
+                __syncwarp();
+                donej = lim;
+                if (lane == 0) { __threadfence_block(); *progg = donej; }
+            }
+        }
         auto next_home_w = [&](uint32_t x) -> uint32_t {
             for (uint32_t base = x + 1; base < m; base += 32) {
                 const uint32_t j = base + lane;
@@ -369,7 +394,7 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                         if (((Sx[ebase + 32u * lane + bq] >> 16) & 0x3FFFu) <= x) { elig |= 1u << bq; pend &= ~(1u << bq); }
                     }
                 }
-                if (ph && TEAM != 32) { while (*prog < xe) { } __threadfence_block(); }   // phase 1 is past this segment
+                if (ph && TEAM != 32) { while (*progg < xe) { __nanosleep(40); } __threadfence_block(); }   // phase 1 and the release ranks are past this segment
                 uint32_t used = xe;
                 if (ph) { uint32_t a = x, b = xe; while (a < b) { const uint32_t mid = (a + b) >> 1; if (E1x[mid] != NONE16) a = mid + 1; else b = mid; } used = a; }
                 for (uint32_t part = 0; part < (ph ? 2u : 1u); ++part) {
@@ -389,20 +414,26 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                         const bool valid = j < hi;
                         uint32_t G = 0;
                         if (valid && use_rel) {
-                            const uint32_t rel = (Sx[E1x[j]] & 0xFFFFu) + W + 1u;
-                            uint32_t a = 0, b = cntp;
-                            while (a < b) { const uint32_t mid = (a + b) >> 1; if ((Sx[ebase + mid] & 0xFFFFu) >= rel) b = mid; else a = mid + 1; }
-                            G = a;
+                            if (TEAM != 32) G = E2x[j];                                  // (warp 2)
+                            else {
+                                const uint32_t rel = (Sx[E1x[j]] & 0xFFFFu) + W + 1u;
+                                uint32_t a = 0, b = cntp;
+                                while (a < b) { const uint32_t mid = (a + b) >> 1; if ((Sx[ebase + mid] & 0xFFFFu) >= rel) b = mid; else a = mid + 1; }
+                                G = a;
+                            }
                         }
-                        const uint32_t wd = G >> 5;
-                        const uint32_t pw = __shfl_sync(0xffffffffu, pre, wd & 31u), ew = __shfl_sync(0xffffffffu, elig0, wd & 31u);
-                        const uint32_t lbp = wd >= 32u ? np : pw + __popc(ew & ((1u << (G & 31u)) - 1u));
-                        int v = valid ? (int)lbp - (int)i : -(1 << 28);
+                        int u = carry;
+                        if (use_rel) {                       // (warp-uniform) pool rank of the release bound, running maximum
+                            const uint32_t wd = G >> 5;
+                            const uint32_t pw = __shfl_sync(0xffffffffu, pre, wd & 31u), ew = __shfl_sync(0xffffffffu, elig0, wd & 31u);
+                            const uint32_t lbp = wd >= 32u ? np : pw + __popc(ew & ((1u << (G & 31u)) - 1u));
+                            int v = valid ? (int)lbp - (int)i : -(1 << 28);
 #pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane >= d) v = max(v, t2); }
-                        const int last = __shfl_sync(0xffffffffu, v, 31);
-                        const int u = max(v, carry);
-                        carry = max(carry, last);
+                            for (int d = 1; d < 32; d <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane >= d) v = max(v, t2); }
+                            const int last = __shfl_sync(0xffffffffu, v, 31);
+                            u = max(v, carry);
+                            carry = max(carry, last);
+                        }
                         const uint32_t idx = i + (uint32_t)u;
                         const bool take = valid && idx < np;
                         uint32_t t = 0;
@@ -416,7 +447,7 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                         const uint32_t g = take ? 32u * t + nth_set(et, idx - pt) : 0u;
                         const uint32_t ent = take ? ebase + g : NONE16;
                         if (valid) Ex[j] = (uint16_t)ent;
-                        if (take) atomicOr(&scr[g >> 5], 1u << (g & 31u));
+                        if (take) atomicOr(&scr[g >> 5], 1u << (g & 31u));    // clear the entries handed out (through the warp's scratch words)
                         __syncwarp();
                         elig &= ~scr[lane];
                         __syncwarp();
@@ -854,17 +885,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
         // ---------------- final stage: the clusters above LMAX entries, all at once (the largest decides, not their sum).
         // Rounds of as many listed clusters as fit the chunk area; a bit per compact slot says "in a cluster of this round",
         // the rank in that bit map is the slot's place in S.
+        long long dt_f[4] = {0, 0, 0, 0};
         while (!fb0 && !ms->fallback && ms->nbig) {
             const uint32_t nbig = ms->nbig;
             __syncthreads();
             if (tid == 0) { ms->rdone = 0; }
-            {   // rank-sort the list by compact start (one thread per entry)
-                uint32_t v = 0, rk = 0;
-                if (tid < nbig) { v = bigl[tid]; for (uint32_t j = 0; j < nbig; ++j) rk += (bigl[j] & 0xFFFFu) < (v & 0xFFFFu) ? 1u : 0u; }
-                __syncthreads();
-                if (tid < nbig) bigl[rk] = v;
-            }
-            __syncthreads();
             uint32_t r0 = 0;
             while (r0 < nbig) {
                 if (tid == 0) {                                  // clusters r0 .. r1 of this round
@@ -898,6 +923,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                     pre16[2 * tid] = (uint16_t)ex; pre16[2 * tid + 1] = (uint16_t)(ex + __popc(w0));
                 }
                 __syncthreads();
+                SUBSTAMP(dt_f[0]);
                 auto brank = [&](uint32_t u) -> uint32_t { return pre16[u >> 5] + __popc(flags[u >> 5] & ((1u << (u & 31u)) - 1u)); };
                 for (uint32_t i0 = tid; i0 < len; i0 += 8 * NTHREADS) {
                     uint32_t tv[8];
@@ -912,6 +938,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                     }
                 }
                 __syncthreads();
+                SUBSTAMP(dt_f[1]);
                 {
                     Team<128> TT; const uint32_t team = warp >> 2;
                     TT.tt = tid & 127u; TT.bar = 1u + team; TT.scr = &ms->tscr[team][0]; TT.par = 0;
@@ -966,7 +993,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                         if (mine) lane_cluster<false>(S + kl, E1 + kl, E2 + kl, m, 0u, data, fres);
                     }
                 }
+                SUBSTAMP(dt_f[2]);
                 __syncthreads();
+                SUBSTAMP(dt_f[3]);
                 r0 = r1;
             }
             break;
@@ -975,6 +1004,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
         if (DBG && dbg_stats && tid == 0) {
             uint32_t* o = dbg_stats + (uint64_t)b * 136 + 8;
             o[0] = (uint32_t)dt_sc; o[1] = (uint32_t)dt_c2; o[2] = (uint32_t)dt_w; o[3] = (uint32_t)dt_t; o[4] = n_chunks; o[5] = n_wq; o[7] = (uint32_t)dt_wait;
+            for (int k = 0; k < 4; ++k) dbg_stats[(uint64_t)b * 136 + 50 + k] = (uint32_t)dt_f[k];
         }
         __syncthreads();
         if (ms->fallback) {                                  // hand the block to lz77_v2_kernel

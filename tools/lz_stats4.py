@@ -27,3 +27,5 @@ for bi in range(3):
     print("   block", bi, "slowest", (mx[bi] >> 14) * 64, "m", mx[bi] & 0x3FFF, "team busy", list(tt[bi]))
 tb = s[:, 40:45] * 64
 print("  team clusters, cycles summed over the block's clusters (median): sort %d, phase-1 sweep %d, release ranks %d, phase-2 sweep %d, finds %d" % tuple(np.median(tb[:, k]) for k in range(5)))
+ff = s[:, 50:54]
+print("  final stage (thread 0): list + bitmap + prefix %d, scatter %d, own work %d, wait for the others %d" % tuple(np.median(ff[:, k]) for k in range(4)))
