@@ -644,12 +644,41 @@ def main():
         g_tok = st.out[: int(g_off[-1])].cpu().numpy()
         g_sizes = st.block_sizes[:nb].cpu().numpy()
         line["cpu_baseline"] = cpu_baseline(R["h_in"].numpy()[:n], CPU_SAMPLE, gpu_stream=(g_tok, g_off, g_sizes), one_core_bytes=16 << 20)
+    v4_line = None
     if rank == 0 and world == 1 and not args.no_detail:
+        # the experimental two-phase match finder (csrc/lz77_v4.cu, B200_LZ_V4=1) on the SAME buffer as the headline:
+        # its stream must equal the default kernel's byte for byte; both encode times by CUDA events
+        try:
+            st0 = R["st"]
+            ref_total = st0.total_bytes
+            ref_out = st0.out[: ref_total].clone(); ref_sizes = st0.block_sizes.clone()
+            def _enc_ms(reps=3):
+                ts = []
+                for _ in range(reps):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); dv.lz77_encode(ctx, R["d_in"], dv.LZ_DEFLATE, BLOCK, stream=st0, sync=False); e1.record()
+                    ctx.sync(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+                return min(ts)
+            t_def = _enc_ms()
+            os.environ["B200_LZ_V4"] = "1"
+            dv.lz77_encode(ctx, R["d_in"], dv.LZ_DEFLATE, BLOCK, stream=st0, sync=True)
+            t_v4 = _enc_ms()
+            st4 = dv.lz77_encode(ctx, R["d_in"], dv.LZ_DEFLATE, BLOCK, stream=st0, sync=True)
+            same = st4.total_bytes == ref_total and bool(torch.equal(st4.block_sizes, ref_sizes)) and bool(torch.equal(st4.out[: ref_total], ref_out))
+            v4_line = {"bytes": int(n), "default_kernel_encode_ms": t_def, "v4_encode_ms": t_v4, "stream_equals_default_kernel": same,
+                       "note": "whole encode call (match finder + size scan + compaction); v4 is opt-in (B200_LZ_V4=1): faster on text, "
+                               "slower on near-random input, DESIGN.md 5c"}
+            del ref_out, ref_sizes
+        except Exception as e:
+            v4_line = {"error": repr(e)}
+        finally:
+            os.environ.pop("B200_LZ_V4", None)
         h100 = R["h_in"][:100_000_000]
         d100 = R["d_in"][:100_000_000].contiguous()
         del R["st"], R["d_in"]
         try:
             line["detail"] = detail_codecs(ctx, dv, torch, d100, h100)
+            line["detail"]["lz77_v4_experimental"] = v4_line
         except Exception as e:  # secondary figures must never lose the headline line
             import traceback
             line["detail"] = {"error": repr(e), "trace": traceback.format_exc()[-600:]}

@@ -26,4 +26,14 @@ rd,wr=g('dram__bytes_read.sum'),g('dram__bytes_write.sum')
 json.dump({"_source":"profiles/%s_lz77_v2_ncu_raw.csv (ncu --set full, one launch of lz77_v2_kernel<1> over a 100 000 000-byte enwik-shaped shard, 1 526 blocks of 64 KiB)" % R0,
  "lz77_v2_kernel<1>":{"input_bytes":100000000,"dram_bytes_read":int(rd),"dram_bytes_write":int(wr),"dram_bytes_per_launch":int(rd+wr),"dram_bytes_per_input_byte":round((rd+wr)/1e8,3)}},open('profiles/roofline_traffic.json','w'),indent=1)
 PY
+for f in v4_phase_cycles v4_vs_default decoder_sweep dropin_lz77 fse_segment_sweep phase_cycles v3_phase_cycles; do [ -f gpurun_out/${S}_$f.txt ] && cp gpurun_out/${S}_$f.txt profiles/${R0}_$f.txt; done
+[ -f gpurun_out/${S}_reference_arm.json ] && cp gpurun_out/${S}_reference_arm.json profiles/${R0}_reference_arm.json
+if [ -f gpurun_out/prof_lz77v4_${S}.ncu-rep ]; then
+  ncu -i gpurun_out/prof_lz77v4_${S}.ncu-rep --page details > profiles/${R0}_lz77_v4_ncu_details.txt 2>/dev/null
+  NCU_KERNEL=lz77_v4 python tools/ncu_lines.py gpurun_out/prof_lz77v4_${S}.ncu-rep 40 > profiles/${R0}_lz77_v4_ncu_hot_lines.txt
+  (echo "# ---- lz77_v4_kernel (experimental, B200_LZ_V4=1), 296 blocks of 64 KiB"; python tools/ncu_kernel_summary.py gpurun_out/prof_lz77v4_${S}.ncu-rep | tail -n +2) >> profiles/${R0}_all_kernels_ncu_summary.txt
+fi
+if [ -f gpurun_out/prof_pdec_${S}.ncu-rep ]; then
+  (echo; echo "# ---- token-parallel LZ77 decoder (lz77_pdec.cu), deflate variant, 256 MiB in 1 MiB blocks"; python tools/ncu_kernel_summary.py gpurun_out/prof_pdec_${S}.ncu-rep | tail -n +2) >> profiles/${R0}_all_kernels_ncu_summary.txt
+fi
 python tools/sass_summary.py > /dev/null

@@ -2,7 +2,7 @@
 how a kernel uses the machine: shared-memory loads/stores/atomics, warp collectives, global accesses,
 barriers) plus registers / shared memory from `cuobjdump -res-usage`, and the full SASS of the hot kernels.
 
-    python tools/sass_summary.py            # writes profiles/r01_sass_summary.txt and profiles/sass/*.sass.gz
+    python tools/sass_summary.py            # writes profiles/r02_sass_summary.txt and profiles/sass/*.sass.gz
 """
 import collections
 import gzip
@@ -13,7 +13,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "compression_algorithms_b200", "libb200comp.so")
 OUT = os.path.join(ROOT, "profiles")
-HOT = ("lz77_v2_kernel", "lz77_decode_kernel", "huff_encode_kernel", "huff_decode_kernel", "fse_encode_kernel",
+HOT = ("lz77_v2_kernel", "lz77_v4_kernel", "pdec_", "lz77_decode_kernel", "huff_encode_kernel", "huff_decode_kernel", "fse_encode_kernel",
        "fse_decode_kernel", "dfl_encode_kernel", "dfl_decode_kernel")
 GROUPS = collections.OrderedDict([
     ("LDS", r"^LDS"), ("STS", r"^STS"), ("ATOMS", r"^ATOMS"), ("LDG", r"^LDG"), ("STG", r"^STG"), ("ATOMG/RED", r"^(ATOMG|RED|ATOM)\b"),
@@ -52,7 +52,7 @@ def main():
         elif name is not None:
             kernels[name].append(line)
     os.makedirs(os.path.join(OUT, "sass"), exist_ok=True)
-    with open(os.path.join(OUT, "r01_sass_summary.txt"), "w") as f:
+    with open(os.path.join(OUT, "r02_sass_summary.txt"), "w") as f:
         f.write("# SASS summary of libb200comp.so (sm_100a, nvcc 12.9, -O3 -lineinfo); regenerate with tools/sass_summary.py\n")
         f.write("# counts are static instructions; none of these kernels uses TMA or tcgen05 (byte/bit work, no dense contraction)\n")
         for k, lines in kernels.items():
@@ -76,7 +76,7 @@ def main():
                 with gzip.open(os.path.join(OUT, "sass", fn), "wt") as g:
                     g.write("// %s\n" % d)
                     g.write("\n".join(lines))
-    print("wrote", os.path.join(OUT, "r01_sass_summary.txt"), len(kernels), "kernels")
+    print("wrote", os.path.join(OUT, "r02_sass_summary.txt"), len(kernels), "kernels")
 
 
 if __name__ == "__main__":
