@@ -33,6 +33,31 @@ constexpr uint32_t CU = 1024;                  // 2-byte units per chunk (deflat
 
 __device__ __forceinline__ uint32_t ldw(const uint32_t* w, uint64_t i, uint64_t nwords) { return i < nwords ? __ldg(w + i) : 0u; }
 
+// A thread emits the pointer words of consecutive output positions: four of them (one aligned 16-byte group) are gathered
+// in registers and stored at once; a group it shares with the neighbouring chunk's thread goes out word by word.
+struct PWriter {
+    uint32_t* P; uint64_t grp; uint32_t v0, v1, v2, v3, mask;
+    __device__ __forceinline__ void init(uint32_t* p) { P = p; grp = ~0ull; mask = 0; v0 = v1 = v2 = v3 = 0; }
+    __device__ __forceinline__ void flush() {
+        if (mask == 15u) *reinterpret_cast<uint4*>(P + (grp << 2)) = make_uint4(v0, v1, v2, v3);
+        else {
+            if (mask & 1u) P[(grp << 2) + 0] = v0;
+            if (mask & 2u) P[(grp << 2) + 1] = v1;
+            if (mask & 4u) P[(grp << 2) + 2] = v2;
+            if (mask & 8u) P[(grp << 2) + 3] = v3;
+        }
+        mask = 0;
+    }
+    __device__ __forceinline__ void put(uint64_t pos, uint32_t val) {
+        const uint64_t g = pos >> 2;
+        if (g != grp) { if (mask) flush(); grp = g; }
+        const uint32_t k = (uint32_t)pos & 3u;
+        if (k == 0) v0 = val; else if (k == 1) v1 = val; else if (k == 2) v2 = val; else v3 = val;
+        mask |= 1u << k;
+    }
+    __device__ __forceinline__ void done() { if (mask) flush(); }
+};
+
 // ---------------------------------------------------------------- K1 (standalone variant)
 __global__ void __launch_bounds__(128) pdec_tables_v0_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ block_off,
                                                             const uint64_t* __restrict__ block_bits, uint64_t nblocks, uint32_t cpb,
@@ -93,19 +118,19 @@ __global__ void __launch_bounds__(128) pdec_tables_v1_kernel(const uint8_t* __re
     if (u0 >= U) return;
     const uint8_t* tk = stream + block_off[b];
     const uint32_t ulim = (uint32_t)(U - u0 < CU ? U - u0 : CU);
+    // both entry states in one pass over the units (they read the same bytes; after the first unit both walks see a token
+    // start they are the same walk)
     uint32_t res[2];
-#pragma unroll
-    for (uint32_t s0 = 0; s0 < 2; ++s0) {
-        uint32_t s = s0, o = 0;
-        for (uint32_t u = 0; u < ulim; ++u) {
-            if (s) { s = 0; continue; }
-            const uint8_t f = __ldg(tk + 2 * (u0 + u));
-            if (f) {                                                         // match head: needs its tail unit
-                if (u0 + u + 1 < U) { o += __ldg(tk + 2 * (u0 + u) + 3); s = 1; }
-            } else o += 1;
-        }
-        res[s0] = (s << 24) | o;
+    uint32_t sa = 0, sb = 1, oa = 0, ob = 0;
+    for (uint32_t u = 0; u < ulim; ++u) {
+        const uint8_t f = __ldg(tk + 2 * (u0 + u));
+        uint32_t ml = 0;
+        const bool head_ok = f != 0 && u0 + u + 1 < U;
+        if (head_ok && (!sa || !sb)) ml = __ldg(tk + 2 * (u0 + u) + 3);
+        if (sa) sa = 0; else if (f) { if (head_ok) { oa += ml; sa = 1; } } else oa += 1;
+        if (sb) sb = 0; else if (f) { if (head_ok) { ob += ml; sb = 1; } } else ob += 1;
     }
+    res[0] = (sa << 24) | oa; res[1] = (sb << 24) | ob;
     tables[c * TAB_WORDS + 0] = res[0]; tables[c * TAB_WORDS + 1] = res[1];
 }
 
@@ -219,20 +244,22 @@ __global__ void __launch_bounds__(128) pdec_emit_v0_kernel(const uint8_t* __rest
     const uint32_t* wbase = reinterpret_cast<const uint32_t*>(tk - mis);
     const uint64_t nwords = ((uint64_t)mis * 8 + T + 31) >> 5;
     const uint64_t q0 = (uint64_t)mis * 8 + cstart;
+    PWriter pw; pw.init(P);
     while (p < CB && o < len) {
         const uint64_t q = q0 + p;
         const uint32_t v = __funnelshift_r(ldw(wbase, q >> 5, nwords), ldw(wbase, (q >> 5) + 1, nwords), (uint32_t)(q & 31));
         const uint32_t flag = v & 1u, tl = flag ? 19u : 9u;
         if (cstart + p + tl > T) break;
-        if (!flag) { out[base + o] = (uint8_t)(v >> 1); P[base + o] = LIT; ++o; }
+        if (!flag) { out[base + o] = (uint8_t)(v >> 1); pw.put(base + o, LIT); ++o; }
         else {
             const uint32_t off = (v >> 1) & 0x3FFFu, ml = (v >> 15) & 15u;
             const bool ok = off != 0u && off <= o;                           // otherwise nothing is copied (as the serial decoders)
-            for (uint32_t k = 0; k < ml && o + k < len; ++k) P[base + o + k] = ok ? (uint32_t)(o + k - off) : LIT;
+            for (uint32_t k = 0; k < ml && o + k < len; ++k) pw.put(base + o + k, ok ? (uint32_t)(o + k - off) : LIT);
             o += ml;
         }
         p += tl;
     }
+    pw.done();
 }
 
 // ---------------------------------------------------------------- K3 (deflate variant)
@@ -255,17 +282,19 @@ __global__ void __launch_bounds__(128) pdec_emit_v1_kernel(const uint8_t* __rest
     const uint64_t len = n - base < bs ? n - base : bs;
     const uint8_t* tk = stream + block_off[b];
     const uint32_t ulim = (uint32_t)(U - u0 < CU ? U - u0 : CU);
+    PWriter pw; pw.init(P);
     for (uint32_t u = s; u < ulim && o < len; ++u) {
         const uint8_t* t = tk + 2 * (u0 + u);
         if (__ldg(t)) {
             if (u0 + u + 1 >= U) break;
             const uint32_t off = (uint32_t)__ldg(t + 1) | ((uint32_t)__ldg(t + 2) << 8), ml = __ldg(t + 3);
             const bool ok = off != 0u && off <= o;
-            for (uint32_t k = 0; k < ml && o + k < len; ++k) P[base + o + k] = ok ? (uint32_t)(o + k - off) : LIT;
+            for (uint32_t k = 0; k < ml && o + k < len; ++k) pw.put(base + o + k, ok ? (uint32_t)(o + k - off) : LIT);
             o += ml;
             ++u;
-        } else { out[base + o] = __ldg(t + 1); P[base + o] = LIT; ++o; }
+        } else { out[base + o] = __ldg(t + 1); pw.put(base + o, LIT); ++o; }
     }
+    pw.done();
 }
 
 // ---------------------------------------------------------------- K4: pointer chains
