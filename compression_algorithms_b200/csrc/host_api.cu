@@ -186,12 +186,13 @@ extern "C" int b200_lz77_decompress_host(b200_ctx* ctx, int variant, const uint8
         // a chunk's decode is bound by the serial token chain of its blocks (about 4 ms whatever the chunk size), not
         // by throughput: consecutive chunks go to two kernel streams so that their chains overlap
         cudaStream_t keep = ctx->stream;
-        if (c & 1) ctx->stream = ctx->s_aux;
+        const int keep_bank = ctx->bank;
+        if (c & 1) { ctx->stream = ctx->s_aux; ctx->bank = 1; }   // (the token-parallel decoder has scratch arrays: one bank per stream)
         int rc = B200_OK;
         if (cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0) != cudaSuccess) rc = B200_ERR_CUDA;
         if (rc == B200_OK) rc = b200_lz77_decode_dev(ctx, variant, d_stream, d_idx + nblocks + b0, d_idx + b0, len, bs, d_out + o);
         if (rc == B200_OK && cudaEventRecord(ctx->ev_done[c], ctx->stream) != cudaSuccess) rc = B200_ERR_CUDA;
-        ctx->stream = keep;
+        ctx->stream = keep; ctx->bank = keep_bank;
         if (rc == B200_ERR_CUDA) B200_SET_ERR("lz77 decompress: stream/event call failed: %s", cudaGetErrorString(cudaGetLastError()));
         return rc;
     };

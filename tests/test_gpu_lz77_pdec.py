@@ -75,3 +75,27 @@ def test_handmade_deflate_streams(ctx, ob, style, monkeypatch):
         got = dv.lz77_decode(ctx, st, out=torch.zeros(nn, dtype=torch.uint8, device=ctx.device)).cpu().numpy()
         d = first_diff(got, want)
         assert d == -1, "%s, block %d: differs at byte %d" % (style, block, d)
+
+
+@pytest.mark.parametrize("variant,block", [(0, 65536), (1, 1 << 20), (0, 1 << 18)])
+def test_host_pipeline_two_streams(ctx, monkeypatch, variant, block):
+    """b200_lz77_decompress_host decodes consecutive chunks on two kernel streams: the decoder's scratch arrays (pointer
+    words, chunk tables) must come from one bank per stream"""
+    import ctypes as C
+    import torch
+    from compression_algorithms_b200 import _lib, device as dv
+    monkeypatch.setenv("B200_LZ_PDEC", "1")
+    monkeypatch.setenv("B200_LZ_CHUNKS", "12")
+    lib = _lib.core()
+    n = 40 * (1 << 20) + 4321
+    data = _corpus(n, 0, 41)
+    st = dv.lz77_encode(ctx, _to_dev(ctx, data), variant, block)
+    stream = st.out[: st.total_bytes].cpu().numpy()
+    off = st.block_off.cpu().numpy().astype(np.uint64)
+    sz = st.block_sizes.cpu().numpy().astype(np.uint64)
+    out = np.empty(n, dtype=np.uint8)
+    _lib.check(lib.b200_lz77_decompress_host(ctx.handle, variant, stream.ctypes.data_as(C.c_void_p), C.c_uint64(stream.size),
+                                             off.ctypes.data_as(C.c_void_p), sz.ctypes.data_as(C.c_void_p), C.c_uint64(n),
+                                             C.c_uint64(block), out.ctypes.data_as(C.c_void_p)))
+    d = first_diff(out, data)
+    assert d == -1, "host pipeline decode differs at byte %d" % d
