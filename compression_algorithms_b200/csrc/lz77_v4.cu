@@ -79,7 +79,7 @@ struct Misc {
     uint32_t ccnt[7], cbase[8], cfill[7], next_t, next_w, next_l;   // work list by size class: 17..64 | 9..16 | 5..8 | 3..4 | 2
     uint32_t nbig, r0, r1, rdone;                                   // big-cluster list; the round of the final stage
     uint32_t tpick[8];
-    uint32_t tscr[8][12];        // per four-warp team: [2][4] cross-warp scan scratch, word 8 = phase-1 progress of a pipelined sweep
+    uint32_t tscr[8][12];        // per four-warp team: [2][4] cross-warp scan scratch, words 8 - 10 = progress / hand-over of the pipelined phases
     uint8_t  sexit[32][32];
     uint8_t  sentry[36];
 };
@@ -254,6 +254,40 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
     // bitonic sort by position (all comparators ascending, so the virtual +inf padding behind m never moves)
     uint32_t P = 2; while (P < m) P <<= 1;
     if (TEAM == 32 && m <= 64) { warp_sort64(Sx, m, 0u); __syncwarp(); P = 1; }   // two registers per lane instead of shared memory
+    if (TEAM == 128) {
+        // a team sorts by counting: 128 buckets of 512 positions (thread b owns bucket b), entries scattered into the cluster's
+        // still unused occupant arrays (position -> E1x, home -> E2x), then every thread sorts its own bucket back into Sx.
+        // Positions are distinct, so a bucket holds a handful of entries unless the cluster is a run of consecutive
+        // positions: above 24 entries in a bucket the bitonic network below runs instead.
+        uint32_t* C = scr - 32u * (tt >> 5);                  // the team's four scratch rows: 128 words, zero on entry and exit
+        for (uint32_t i = tt; i < m; i += TEAM) atomicAdd(&C[(Sx[i] & 0xFFFFu) >> 9], 1u);
+        T.sync();
+        const uint32_t mycount = C[tt];
+        uint32_t tot;
+        const uint32_t mystart = T.exscan(mycount, tot);
+        const uint32_t big = T.tmin(mycount <= 24u ? 1u : 0u);   // 0 if any bucket is too full (tmin ends with every thread past its reads)
+        T.sync();
+        C[tt] = big ? mystart : 0u;
+        T.sync();
+        if (big) {
+            for (uint32_t i = tt; i < m; i += TEAM) {
+                const uint32_t e = Sx[i];
+                const uint32_t pos = atomicAdd(&C[(e & 0xFFFFu) >> 9], 1u);
+                E1x[pos] = (uint16_t)e; E2x[pos] = (uint16_t)(e >> 16);
+            }
+            T.sync();
+            for (uint32_t a = 0; a < mycount; ++a) {          // insertion sort of my bucket, written back in order
+                const uint32_t t0 = E1x[mystart + a], h0 = E2x[mystart + a];
+                uint32_t j = a;
+                while (j > 0 && (uint32_t)E1x[mystart + j - 1] > t0) { E1x[mystart + j] = E1x[mystart + j - 1]; E2x[mystart + j] = E2x[mystart + j - 1]; --j; }
+                E1x[mystart + j] = (uint16_t)t0; E2x[mystart + j] = (uint16_t)h0;
+            }
+            for (uint32_t a = 0; a < mycount; ++a) Sx[mystart + a] = (uint32_t)E1x[mystart + a] | ((uint32_t)E2x[mystart + a] << 16);
+            P = 1;
+        }
+        C[tt] = 0;
+        T.sync();
+    }
     for (uint32_t k = 2; k <= P; k <<= 1) {
         const uint32_t half = k >> 1;
         for (uint32_t idx = tt; idx < (P >> 1); idx += TEAM) {
@@ -334,6 +368,75 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
         volatile uint32_t* prog = (TEAM == 32) ? nullptr : reinterpret_cast<volatile uint32_t*>(T.scr + 8);
         volatile uint32_t* progg = (TEAM == 32) ? nullptr : reinterpret_cast<volatile uint32_t*>(T.scr + 9);
         if (TEAM != 32) { if (tt == 0) { *prog = 0; *progg = 0; } T.sync(); }
+        // ---- phase 1 in TIME order for a team cluster (checked against the sweep on the CPU, tools/proto_v4.c). Nothing dies in
+        // phase 1, so the table is: T = the lowest free slot, plus the few slots taken AHEAD of it. An entry whose home is at or
+        // before T takes T ("chain-like": every home-0 entry, and most others once the chain has grown past their home); the k-th
+        // chain-like entry therefore sits in the k-th slot that is not an ahead slot. An entry whose home is beyond T takes the
+        // first slot from its home that no earlier ahead entry holds. Only the entries with a home other than the cluster's first
+        // slot need a look (one warp, in time order, <= 63 of them or the sweep below runs instead); everything else is a scatter.
+        bool p1_closed = false;
+        if (TEAM != 32 && n1 > 0u) {
+            uint16_t* IL = E2x;             // entries with home != 0, in time order
+            uint16_t* AH = E2x + 64;        // ahead slots, ascending
+            uint16_t* BI = E2x + 128;       // the entries that took them (ascending index = time order)
+            uint16_t* BS = E2x + 192;       // and which slot each took
+            volatile uint32_t* p1info = reinterpret_cast<volatile uint32_t*>(T.scr + 10);   // na | nB << 8 | ok << 31
+            if (tt < 32u) {
+                uint32_t q = 0;
+                for (uint32_t base = 0; base < n1; base += 32) {
+                    const uint32_t i = base + lane;
+                    const bool isI = i < n1 && ((Sx[i] >> 16) & 0x3FFFu) != 0u;
+                    const uint32_t mk = __ballot_sync(0xffffffffu, isI);
+                    if (isI) { const uint32_t r = q + __popc(mk & ((1u << lane) - 1u)); if (r < 64u) IL[r] = (uint16_t)i; }
+                    q += __popc(mk);
+                }
+                __syncwarp();
+                uint32_t na = 0, nB = 0;
+                const bool ok = q <= 63u;
+                for (uint32_t r = 0; ok && r < q; ++r) {
+                    const uint32_t idx = IL[r], o = (Sx[idx] >> 16) & 0x3FFFu;
+                    const uint32_t k = idx - nB;
+                    const uint32_t a0 = lane < na ? (uint32_t)AH[lane] : 0xFFFFFu, a1 = lane + 32 < na ? (uint32_t)AH[lane + 32] : 0xFFFFFu;
+                    const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, lane < na && a0 - lane <= k)) +
+                                         __popc(__ballot_sync(0xffffffffu, lane + 32 < na && a1 - (lane + 32) <= k));
+                    if (o > k + cnt) {                                    // lands ahead of the lowest free slot
+                        const uint32_t p0 = __popc(__ballot_sync(0xffffffffu, lane < na && a0 < o)) + __popc(__ballot_sync(0xffffffffu, lane + 32 < na && a1 < o));
+                        const unsigned long long run = (unsigned long long)__ballot_sync(0xffffffffu, lane >= p0 && lane < na && a0 == o + (lane - p0)) |
+                                                       ((unsigned long long)__ballot_sync(0xffffffffu, lane + 32 >= p0 && lane + 32 < na && a1 == o + (lane + 32 - p0)) << 32);
+                        const uint32_t rl = (uint32_t)(__ffsll((long long)~(run >> p0)) - 1);
+                        const uint32_t sl = o + rl, pos = p0 + rl;
+                        __syncwarp();
+                        if (lane >= pos && lane < na) AH[lane + 1] = (uint16_t)a0;
+                        if (lane + 32 >= pos && lane + 32 < na) AH[lane + 33] = (uint16_t)a1;
+                        if (lane == 0) { AH[pos] = (uint16_t)sl; BI[nB] = (uint16_t)idx; BS[nB] = (uint16_t)sl; }
+                        __syncwarp();
+                        ++na; ++nB;
+                    }
+                }
+                if (lane == 0) *p1info = na | (nB << 8) | (ok ? 0x80000000u : 0u);
+            }
+            T.sync();
+            const uint32_t info = *p1info;
+            if (info >> 31) {
+                p1_closed = true;
+                const uint32_t na = info & 0xFFu, nB = (info >> 8) & 0xFFu;
+                for (uint32_t j = tt; j < m; j += TEAM) E1x[j] = (uint16_t)NONE16;
+                T.sync();
+                for (uint32_t i = tt; i < n1; i += TEAM) {
+                    uint32_t lo2 = 0, hi2 = nB;                           // B entries with a smaller index
+                    while (lo2 < hi2) { const uint32_t mid = (lo2 + hi2) >> 1; if ((uint32_t)BI[mid] < i) lo2 = mid + 1; else hi2 = mid; }
+                    if (lo2 < nB && (uint32_t)BI[lo2] == i) E1x[BS[lo2]] = (uint16_t)i;
+                    else {
+                        const uint32_t k = i - lo2;
+                        uint32_t a = 0, b2 = na;                          // ahead slots with (slot - rank) <= k: they lie below the k-th other slot
+                        while (a < b2) { const uint32_t mid = (a + b2) >> 1; if ((uint32_t)AH[mid] - mid <= k) a = mid + 1; else b2 = mid; }
+                        E1x[k + a] = (uint16_t)i;
+                    }
+                }
+                T.sync();
+                if (tt == 0) { __threadfence_block(); *prog = m; }
+            }
+        }
         if (TEAM != 32 && (tt >> 5) == 2u && m - n1 > 0u) {
             // warp 2: for every slot phase 1 has finished, how many phase-2 entries arrive before the slot is dead (lower bound
             // of its release time in the time-ordered phase-2 entries); parked in E2x[j] until phase 2 reaches the slot
@@ -371,7 +474,7 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
             uint16_t* Ex = ph ? E2x : E1x;
             if (ph && TEAM == 32) BC_STAMP(1);
             const bool sweeper = (TEAM == 32) ? true : ((tt >> 5) == ph);
-            if (!sweeper) continue;
+            if (!sweeper || (!ph && p1_closed)) continue;
             if (cntp == 0) {
                 for (uint32_t j = lane; j < m; j += 32) Ex[j] = (uint16_t)NONE16;
                 __syncwarp();
@@ -892,9 +995,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
             if (tid == 0) { ms->rdone = 0; }
             uint32_t r0 = 0;
             while (r0 < nbig) {
+                if (tid == 0) ms->scan[33] = 0;
+                __syncthreads();
+                {                                                // entries of all listed clusters that are left: one round if they fit
+                    uint32_t mine = (r0 + tid < nbig) ? bigl[r0 + tid] >> 16 : 0u;
+                    mine = warp_sum_u32(mine);
+                    if (lane == 0 && mine) atomicAdd(&ms->scan[33], mine);
+                }
+                __syncthreads();
                 if (tid == 0) {                                  // clusters r0 .. r1 of this round
-                    uint32_t r1 = r0, tot = 0;
-                    while (r1 < nbig && tot + (bigl[r1] >> 16) <= CH) { tot += bigl[r1] >> 16; ++r1; }
+                    uint32_t r1 = nbig;
+                    if (ms->scan[33] > CH) { uint32_t tot = 0; r1 = r0; while (r1 < nbig && tot + (bigl[r1] >> 16) <= CH) { tot += bigl[r1] >> 16; ++r1; } }
                     ms->r0 = r0; ms->r1 = r1; ms->next_t = r0; ms->rdone = 0; ms->next_w = r0;
                 }
                 for (uint32_t i = tid; i < SZ_FLAGS / 4; i += NTHREADS) flags[i] = 0;
