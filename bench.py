@@ -598,11 +598,12 @@ def main():
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                per_byte = json.load(f).get("lz77_v2_kernel<1>", {}).get("dram_bytes_per_input_byte")
+                tj = json.load(f)
+                per_byte = (tj.get("lz77_v4_kernel") or tj.get("lz77_v2_kernel<1>", {})).get("dram_bytes_per_input_byte")
             traffic = int(per_byte * n) if per_byte else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "lz77_v2_kernel<1> (deflate-variant match finder: shared-memory table simulation + greedy parse + token emission), rank 0's shard",
+    roofline = {"bound": "hbm", "kernel": "deflate-variant match finder of the encode call: lz77_v4_kernel for text-like input (a byte-entropy sample decides), lz77_v2_kernel for the blocks it hands back and for other input; + greedy parse + token emission; rank 0's shard",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "static: dram__bytes of one ncu --set full capture at 100 MB (profiles/roofline_traffic.json), scaled to this launch's input; not re-measured per run",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": n + T, "avg_launch_ms": parse_avg,
@@ -646,8 +647,8 @@ def main():
         line["cpu_baseline"] = cpu_baseline(R["h_in"].numpy()[:n], CPU_SAMPLE, gpu_stream=(g_tok, g_off, g_sizes), one_core_bytes=16 << 20)
     v4_line = None
     if rank == 0 and world == 1 and not args.no_detail:
-        # the experimental two-phase match finder (csrc/lz77_v4.cu, B200_LZ_V4=1) on the SAME buffer as the headline:
-        # its stream must equal the default kernel's byte for byte; both encode times by CUDA events
+        # both match finders on the SAME buffer as the headline (lz77_v2_kernel: B200_LZ_V4=0, lz77_v4_kernel: =1): their streams
+        # must equal the headline's byte for byte; encode times by CUDA events
         try:
             st0 = R["st"]
             ref_total = st0.total_bytes
@@ -659,15 +660,19 @@ def main():
                     e0.record(); dv.lz77_encode(ctx, R["d_in"], dv.LZ_DEFLATE, BLOCK, stream=st0, sync=False); e1.record()
                     ctx.sync(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
                 return min(ts)
+            os.environ["B200_LZ_V4"] = "0"
+            dv.lz77_encode(ctx, R["d_in"], dv.LZ_DEFLATE, BLOCK, stream=st0, sync=True)
             t_def = _enc_ms()
+            st2 = dv.lz77_encode(ctx, R["d_in"], dv.LZ_DEFLATE, BLOCK, stream=st0, sync=True)
+            same_v2 = st2.total_bytes == ref_total and bool(torch.equal(st2.block_sizes, ref_sizes)) and bool(torch.equal(st2.out[: ref_total], ref_out))
             os.environ["B200_LZ_V4"] = "1"
             dv.lz77_encode(ctx, R["d_in"], dv.LZ_DEFLATE, BLOCK, stream=st0, sync=True)
             t_v4 = _enc_ms()
             st4 = dv.lz77_encode(ctx, R["d_in"], dv.LZ_DEFLATE, BLOCK, stream=st0, sync=True)
             same = st4.total_bytes == ref_total and bool(torch.equal(st4.block_sizes, ref_sizes)) and bool(torch.equal(st4.out[: ref_total], ref_out))
-            v4_line = {"bytes": int(n), "default_kernel_encode_ms": t_def, "v4_encode_ms": t_v4, "stream_equals_default_kernel": same,
-                       "note": "whole encode call (match finder + size scan + compaction); v4 is opt-in (B200_LZ_V4=1): faster on text, "
-                               "slower on near-random input, DESIGN.md 5c"}
+            v4_line = {"bytes": int(n), "v2_encode_ms": t_def, "v4_encode_ms": t_v4, "streams_equal": bool(same and same_v2),
+                       "note": "whole encode call (match finder + size scan + compaction) with B200_LZ_V4=0 / =1; the headline runs the default: a "
+                               "byte-entropy sample of the input picks lz77_v4_kernel for text-like input, lz77_v2_kernel otherwise (DESIGN.md 5c)"}
             del ref_out, ref_sizes
         except Exception as e:
             v4_line = {"error": repr(e)}
@@ -678,7 +683,7 @@ def main():
         del R["st"], R["d_in"]
         try:
             line["detail"] = detail_codecs(ctx, dv, torch, d100, h100)
-            line["detail"]["lz77_v4_experimental"] = v4_line
+            line["detail"]["lz77_match_finders"] = v4_line
         except Exception as e:  # secondary figures must never lose the headline line
             import traceback
             line["detail"] = {"error": repr(e), "trace": traceback.format_exc()[-600:]}

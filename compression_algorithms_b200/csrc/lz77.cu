@@ -432,7 +432,7 @@ int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, 
 // deflate variant, blocks of at most 65536 bytes (two expiry phases): cluster-local placement by slot sweeps (lz77_v4.cu);
 // blocks it cannot take are listed and go through lz77_v2_launch
 int lz77_v4_launch(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
-                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok);
+                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok, int mode);
 // blocks of at most 65536 bytes: occupancy-decided finds + lane-serial simulation of the mixed clusters (lz77_v3.cu)
 int lz77_v3_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
                    uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok);
@@ -471,7 +471,10 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
     if (use_v2) {
         if (dbg_tok && bs > 65536) { B200_SET_ERR("lz77: token dump needs blocks <= 65536"); return B200_ERR_ARG; }
         B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
-        if (bs <= 65536 && variant == 1 && getenv("B200_LZ_V4")) B200_TRY(lz77_v4_launch(ctx, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
+        // deflate variant, blocks of at most 64 KiB: B200_LZ_V4=1 lz77_v4_kernel, =0 lz77_v2_kernel, unset: a sample of the input decides
+        const char* v4e = getenv("B200_LZ_V4");
+        const int v4mode = (bs <= 65536 && variant == 1 && !getenv("B200_LZ_V3")) ? (v4e ? (v4e[0] == '1' ? 1 : 0) : 2) : 0;
+        if (v4mode) B200_TRY(lz77_v4_launch(ctx, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok, v4mode));
         else if (bs <= 65536 && getenv("B200_LZ_V3")) B200_TRY(lz77_v3_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
         else B200_TRY(lz77_v2_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
         B200_TIMED_END(ctx);

@@ -703,7 +703,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                                                              uint8_t* __restrict__ scratch, uint64_t stride,
                                                              uint64_t* __restrict__ block_sizes, uint64_t* __restrict__ block_bytes,
                                                              uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_cnt,
+                                                             const uint32_t* __restrict__ use_flag,
                                                              uint32_t* __restrict__ dbg_tok) {
+    if (use_flag && *use_flag == 0u) {       // the sample says this input is not text-like: every block goes to lz77_v2_kernel
+        if (threadIdx.x == 0) for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) fb_list[atomicAdd(fb_cnt, 1u)] = b;
+        return;
+    }
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* data = smem + OFF_DATA;
     uint8_t* big = smem + OFF_BIG;
@@ -1238,6 +1243,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
     }
 }
 
+// Which match finder? lz77_v4_kernel is 9 % faster on text and slower on near-random or few-symbol input (its fixed passes cost
+// more than v2's, and a block that is one long chain is handed back after its occupancy pass). One CTA estimates the byte entropy
+// of 32 768 bytes spread over the buffer: between 1.5 and 7.3 bits per byte the input goes to lz77_v4_kernel.
+__global__ void __launch_bounds__(1024) lz77_pick_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ flag) {
+    __shared__ uint32_t hist[256];
+    __shared__ float part[32];
+    const uint32_t tid = threadIdx.x;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const uint64_t S = n < 32768 ? n : 32768;
+    const uint64_t stride = n / S;
+    for (uint64_t i = tid; i < S; i += 1024) atomicAdd(&hist[__ldg(in + i * stride)], 1u);
+    __syncthreads();
+    float h = 0.f;
+    if (tid < 256) { const float c = (float)hist[tid]; if (c > 0.f) h = c * __log2f(c); }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+    if ((tid & 31) == 0) part[tid >> 5] = h;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += part[w];
+        const float H = __log2f((float)S) - t / (float)S;
+        *flag = (H >= 1.5f && H <= 7.3f) ? 1u : 0u;
+    }
+}
+
 }  // namespace
 
 int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
@@ -1245,8 +1277,9 @@ int lz77_v2_launch(b200_ctx* ctx, int variant, const uint8_t* d_in, uint64_t n, 
                    const uint32_t* blist, const uint32_t* bcount);
 
 // scratch slots: 13 = F (u16 per position; v2's lists when it runs the handed-back blocks), 14 = tok, 18 = hand-back list
+// mode: 1 = lz77_v4_kernel for every block it can take, 2 = decided by a sample of the input (lz77_pick_kernel)
 int lz77_v4_launch(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t bs, uint64_t nblocks,
-                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok) {
+                   uint8_t* scratch, uint64_t stride, uint64_t* d_block_sizes, uint64_t* block_bytes, uint32_t* dbg_tok, int mode) {
     static bool attr_done_dev[64] = {};
     bool& attr_done = attr_done_dev[ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0];
     if (!attr_done) {
@@ -1262,8 +1295,14 @@ int lz77_v4_launch(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t bs, 
     B200_TRY(b200_scratch(ctx, B200_SLOT(ctx, 18), (size_t)(nblocks + 16) * 4, reinterpret_cast<void**>(&fb)));
     CUDA_TRY(cudaMemsetAsync(fb, 0, 16, ctx->stream));
     uint32_t* fb_cnt = fb; uint32_t* fb_list = fb + 4;
-    if (dbg_tok) lz77_v4_kernel<true><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, fres, tok, scratch, stride, d_block_sizes, block_bytes, fb_list, fb_cnt, dbg_tok);
-    else lz77_v4_kernel<false><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, fres, tok, scratch, stride, d_block_sizes, block_bytes, fb_list, fb_cnt, dbg_tok);
+    uint32_t* use_flag = nullptr;
+    if (mode == 2) {
+        use_flag = fb + 1;
+        lz77_pick_kernel<<<1, 1024, 0, ctx->stream>>>(d_in, n, use_flag);
+        ctx->launches += 1;
+    }
+    if (dbg_tok) lz77_v4_kernel<true><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, fres, tok, scratch, stride, d_block_sizes, block_bytes, fb_list, fb_cnt, use_flag, dbg_tok);
+    else lz77_v4_kernel<false><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, fres, tok, scratch, stride, d_block_sizes, block_bytes, fb_list, fb_cnt, use_flag, dbg_tok);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     // the blocks handed back (empty list: the kernel's CTAs return at once)

@@ -1,5 +1,6 @@
-"""GPU parity of the experimental two-phase match finder (csrc/lz77_v4.cu, B200_LZ_V4=1; deflate variant, blocks of
-at most 65536 bytes): same oracle comparisons as tests/test_gpu_lz77.py, plus byte equality with the default kernel.
+"""GPU parity of the two-phase match finder (csrc/lz77_v4.cu; deflate variant, blocks of at most 65536 bytes; taken by
+default for text-like input, forced here with B200_LZ_V4=1): same oracle comparisons as tests/test_gpu_lz77.py, plus byte
+equality with lz77_v2_kernel (B200_LZ_V4=0).
 Blocks it hands back (a cluster on slot 0 / the table end, a cluster above 16383 entries) run through lz77_v2_kernel,
 so the skewed / slot-0 cases below exercise the hand-back list."""
 import numpy as np
@@ -66,7 +67,7 @@ def test_equals_default_kernel(ctx, monkeypatch):
     d = _to_dev(ctx, data)
     a = dv.lz77_encode(ctx, d, 1, 65536)
     out_a = a.out[: a.total_bytes].cpu().numpy().copy(); sz_a = a.block_sizes.cpu().numpy().copy()
-    monkeypatch.delenv("B200_LZ_V4")
+    monkeypatch.setenv("B200_LZ_V4", "0")
     b = dv.lz77_encode(ctx, d, 1, 65536)
     assert a.total_bytes == b.total_bytes
     assert np.array_equal(sz_a, b.block_sizes.cpu().numpy())
@@ -91,3 +92,17 @@ def test_match_finder_candidates(ctx, ob):
                     l += 1
                 want = (p - m) | (l << 16)
             assert int(tok[b, p]) == want, "block %d position %d" % (b, p)
+
+
+@pytest.mark.parametrize("kind,expect_v4", [(0, True), (1, True), (2, False), (3, False)])
+def test_default_choice_by_sample(ctx, ob, monkeypatch, kind, expect_v4):
+    """no override: a byte-entropy sample of the input picks the kernel (text-like -> v4); the stream is the oracle's either way.
+    The debug statistics tell which kernel ran: lz77_v4_kernel leaves its cluster counters behind stamp 8."""
+    from compression_algorithms_b200 import device as dv
+    monkeypatch.delenv("B200_LZ_V4")
+    data = _corpus(6 * 65536, kind, 9)
+    _encode_check(ctx, ob, data, 1, 65536)
+    st, tok = dv.lz77_encode_debug(ctx, _to_dev(ctx, data), 1, 65536)
+    stats = st.debug_stats.cpu().numpy()
+    ran_v4 = bool((stats[:, 12] == 2).any())       # v4: "chunks" counter of the lane stage (two per block)
+    assert ran_v4 == expect_v4

@@ -1,4 +1,5 @@
-import sys, numpy as np, torch
+import os, sys, numpy as np, torch
+os.environ["B200_LZ_V4"] = "0"   # phase statistics of lz77_v2_kernel
 sys.path.insert(0, '.')
 from compression_algorithms_b200 import corpus, device as dv
 ctx = dv.Context(0)
