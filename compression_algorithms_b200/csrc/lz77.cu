@@ -473,7 +473,10 @@ static int lz77_encode_impl(b200_ctx* ctx, int variant, const uint8_t* d_in, uin
         B200_TIMED_BEGIN(ctx, B200_K_LZ_PARSE);
         // deflate variant, blocks of at most 64 KiB: B200_LZ_V4=1 lz77_v4_kernel, =0 lz77_v2_kernel, unset: a sample of the input decides
         const char* v4e = getenv("B200_LZ_V4");
-        const int v4mode = (bs <= 65536 && variant == 1 && !getenv("B200_LZ_V3")) ? (v4e ? (v4e[0] == '1' ? 1 : 0) : 2) : 0;
+        // (below a few dozen blocks the sample kernel and the second launch cost more than the choice can gain)
+        uint64_t v4_min_blocks = 64;
+        if (const char* e = getenv("B200_LZ_V4_MIN_BLOCKS")) { const long long v = atoll(e); if (v >= 0) v4_min_blocks = (uint64_t)v; }
+        const int v4mode = (bs <= 65536 && variant == 1 && !getenv("B200_LZ_V3")) ? (v4e ? (v4e[0] == '1' ? 1 : 0) : (nblocks >= v4_min_blocks ? 2 : 0)) : 0;
         if (v4mode) B200_TRY(lz77_v4_launch(ctx, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok, v4mode));
         else if (bs <= 65536 && getenv("B200_LZ_V3")) B200_TRY(lz77_v3_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));
         else B200_TRY(lz77_v2_launch(ctx, variant, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok));

@@ -78,6 +78,7 @@ struct Misc {
     uint32_t p1_next, fallback, ce, pad0;
     uint32_t ccnt[7], cbase[8], cfill[7], next_t, next_w, next_l;   // work list by size class: 17..64 | 9..16 | 5..8 | 3..4 | 2
     uint32_t nbig, r0, r1, rdone;                                   // big-cluster list; the round of the final stage
+    uint32_t cut0, top_start, nsp, sp_pad;                          // the clusters on slot 0 / the table end: raw bounds, their entries
     uint32_t tpick[8];
     uint32_t tscr[8][12];        // per four-warp team: [2][4] cross-warp scan scratch, words 8 - 10 = progress / hand-over of the pipelined phases
     uint8_t  sexit[32][32];
@@ -755,7 +756,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
         // ---------------- P1: no-expiry occupancy by atomic linear probing (as v2); the slot an entry wins is ITS slot
         {
             uint32_t* summ = pre;
-            bool wrapped = false;
             for (;;) {
                 uint32_t row = 0;
                 if (lane == 0) row = atomicAdd(&ms->p1_next, 32u);
@@ -782,12 +782,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                     uint32_t open = ~summ[nw >> 5] & (0xFFFFFFFFu << (nw & 31));
                     while (!open) { nw = ((nw >> 5) + 1) << 5; open = ~summ[nw >> 5]; }
                     s = ((nw & ~31u) + (uint32_t)(__ffs(open) - 1)) << 5;
-                    if (s >= SLOTS) { s = 0; wrapped = true; }        // the wrapping insert (deflate/lz77.c:99-101): not here
+                    if (s >= SLOTS) s = 0;                            // the insert wraps (deflate/lz77.c:99-101)
                 }
                 const uint32_t d = cl - h;
                 tokb[i] = cl | ((d < 4095u ? d : 4095u) << 20);
             }
-            if (wrapped) ms->fallback = 1u;
         }
         __syncthreads();
         PHASE_STAMP(1);
@@ -814,7 +813,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                 const uint32_t ti = warp_incl_scan_u32(t);
                 ms->scan[lane] = ti - t;
             }
-            if (tid == 32 && ((bm[0] & 1u) || (bm[SLOTS / 32 - 1] >> 31))) ms->fallback = 1u;   // slot 0 / the table end is in use
+            if (tid == 32) {
+                // The cluster on slot 0 (the reference clears that slot early, U10) and the one that ends on the last slot (the
+                // insert wraps from there to slot 0, find does not) are simulated by one thread with the reference's own rules
+                // (special_clusters below); here: their raw bounds. More than 60 slots between them: the block is handed back.
+                uint32_t c0s = 0;
+                while (c0s < 64u && ((bm[c0s >> 5] >> (c0s & 31u)) & 1u)) ++c0s;
+                uint32_t ts = SLOTS;
+                while (ts > SLOTS - 64u && ((bm[(ts - 1) >> 5] >> ((ts - 1) & 31u)) & 1u)) --ts;
+                ms->cut0 = c0s; ms->top_start = ts; ms->nsp = 0;
+                if (c0s + (SLOTS - ts) > 60u) ms->fallback = 1u;
+            }
             __syncthreads();
             uint32_t run = ms->scan[warp] + incl - mine;
             uint32_t fw = 0xFFFFFFFFu, fbits = 0;
@@ -851,6 +860,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
         const bool fb0 = ms->fallback != 0;
         PHASE_STAMP(2);
         // ---------------- P3: compact slot of the claimed slot, displacement from the home; loners
+        const uint32_t sp_cut0 = ms->cut0, sp_top = ms->top_start;
+        uint16_t* spl = reinterpret_cast<uint16_t*>(&ms->sexit[0][0]);          // (the parse scratch is free until P5) [64] positions
         if (!fb0) {
             for (uint32_t i0 = tid; i0 < len; i0 += 8 * NTHREADS) {
                 uint32_t tv[8];
@@ -863,6 +874,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                     const uint32_t cl = tv[k] & 0xFFFFFu, dd = tv[k] >> 20;
                     const uint32_t h = dd < 4095u ? cl - dd : lz_hash(sm_word(data, i));
                     const uint32_t d = cl - h;
+                    if (h < sp_cut0 || h >= sp_top) {                     // entry of a special cluster: listed, kept out of everything else
+                        const uint32_t si = atomicAdd(&ms->nsp, 1u);
+                        if (si < 60u) spl[si] = (uint16_t)i; else ms->fallback = 1u;
+                        tokb[i] = LONER; fres[i] = (uint16_t)NONE16;
+                        continue;
+                    }
                     bool loner = false;
                     if (d == 0) {
                         const uint32_t wi = h >> 5, bi = h & 31u, wv = bm[wi];
@@ -873,6 +890,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                     tokb[i] = loner ? LONER : (bm_rank(bm, pre16, cl) | (d << 16));
                     fres[i] = (uint16_t)NONE16;
                 }
+            }
+        }
+        __syncthreads();
+        if (!fb0 && tid == 0 && !ms->fallback && ms->nsp) {
+            // ---- the special clusters, serially, exactly as the reference runs them (deflate/lz77.c:77-174 with lazy expiry):
+            // local slots [0, mt) = the run that ends on the table's last slot, [mt, mt + ml) = the run that starts on slot 0, so
+            // the wrapping insert just walks on; find stops at the table end; slot 0 (local mt) is wiped W inserts after every
+            // placement into it and once at insert W - 1 (the ring's zero-initialised entries, U10).
+            uint16_t* Tsp = spl + 64;                                            // [64] position + 1 of the occupant, 0 = none
+            uint32_t* clr = reinterpret_cast<uint32_t*>(spl + 128);              // [<= 64] pending wipe times of slot 0
+            const uint32_t ns = ms->nsp, mt = SLOTS - sp_top, ml = sp_cut0, tot = mt + ml;
+            for (uint32_t a = 1; a < ns; ++a) { const uint16_t v = spl[a]; uint32_t j = a; while (j > 0 && spl[j - 1] > v) { spl[j] = spl[j - 1]; --j; } spl[j] = v; }
+            for (uint32_t k = 0; k < 64; ++k) Tsp[k] = 0;
+            uint32_t qh = 0, qt = 0;
+            clr[qt++] = W - 1;
+            for (uint32_t a = 0; a < ns; ++a) {
+                const uint32_t q = spl[a], w = sm_word(data, q), h = lz_hash(w);
+                const uint32_t loc = h >= sp_top ? h - sp_top : mt + h;
+                while (qh < qt && clr[qh] < q) { if (ml) Tsp[mt] = 0; ++qh; }
+                const uint32_t dthr = q > W ? q - W : 0u;
+                uint32_t k = loc, m = 0xFFFFFFFFu;
+                bool ran_off = false;
+                for (;;) {
+                    const uint32_t v = Tsp[k];
+                    if (v <= dthr) break;
+                    if (sm_word(data, v - 1) == w) { m = v - 1; break; }
+                    if (loc < mt && k + 1 == mt) { ran_off = true; break; }   // find does not wrap (deflate/lz77.c:168)
+                    if (k + 1 >= tot) break;
+                    ++k;
+                }
+                uint32_t e = ran_off ? mt : k;                                // the wrapping insert continues at slot 0
+                while (e + 1 < tot && Tsp[e] > dthr) ++e;
+                if (q != 65535u) Tsp[e] = (uint16_t)(q + 1);
+                if (e == mt && ml && qt < 62u) clr[qt++] = q + W;
+                if (qh < qt && clr[qh] == q) { if (ml) Tsp[mt] = 0; ++qh; }
+                fres[q] = (uint16_t)(m == 0xFFFFFFFFu ? NONE16 : m);
             }
         }
         __syncthreads();
@@ -937,6 +990,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                         const uint32_t k = (uint32_t)(__ffs(bits) - 1);
                         bits &= bits - 1;
                         const uint32_t start = a + k;
+                        if (start < sp_cut0 || start >= len - (SLOTS - sp_top)) { nlb[h] &= ~(1u << k); continue; }   // a special cluster: done above
                         const uint32_t m = csize(start);
                         if (m > LMAX) {                          // kept for the final stage, where all of them run at once
                             nlb[h] &= ~(1u << k);

@@ -100,9 +100,24 @@ def test_default_choice_by_sample(ctx, ob, monkeypatch, kind, expect_v4):
     The debug statistics tell which kernel ran: lz77_v4_kernel leaves its cluster counters behind stamp 8."""
     from compression_algorithms_b200 import device as dv
     monkeypatch.delenv("B200_LZ_V4")
+    monkeypatch.setenv("B200_LZ_V4_MIN_BLOCKS", "1")    # (by default only calls of 64+ blocks are sampled at all)
     data = _corpus(6 * 65536, kind, 9)
     _encode_check(ctx, ob, data, 1, 65536)
     st, tok = dv.lz77_encode_debug(ctx, _to_dev(ctx, data), 1, 65536)
     stats = st.debug_stats.cpu().numpy()
     ran_v4 = bool((stats[:, 12] == 2).any())       # v4: "chunks" counter of the lane stage (two per block)
     assert ran_v4 == expect_v4
+
+
+@pytest.mark.parametrize("copies", [1, 3, 20])
+def test_small_special_clusters_inside_v4(ctx, ob, copies):
+    """a few occurrences of the pattern that hashes to slot 0 per block (U10: the early clear) and near-random filler whose
+    probes reach the table end: clusters of a few entries on slot 0 / the last slot are simulated by the kernel itself"""
+    rng = np.random.default_rng(100 + copies)
+    n = 12 * 65536
+    data = rng.integers(0, 256, size=n, dtype=np.uint8)
+    pat = np.array([0x78, 0x15, 0x02, 0x01], dtype=np.uint8)      # hashes to slot 0
+    for b in range(12):
+        for p in rng.integers(b * 65536, (b + 1) * 65536 - 8, size=copies):
+            data[p:p + 4] = pat
+    _encode_check(ctx, ob, data, 1, 65536)
