@@ -14,6 +14,7 @@ NCU_KERNEL=lz77_decode_units python tools/ncu_lines.py $R 25 > profiles/${R0}_lz
 NCU_KERNEL=lz77_v2 python tools/ncu_phases.py $R > profiles/${R0}_lz77_v2_ncu_phases.txt
 NCU_KERNEL=lz77_v2 python tools/ncu_lines.py $R 40 > profiles/${R0}_lz77_v2_ncu_hot_lines.txt
 (python tools/ncu_kernel_summary.py $R; echo; [ -f gpurun_out/prof_dfl_${S}.ncu-rep ] && { echo "# ---- deflate token entropy stage"; python tools/ncu_kernel_summary.py gpurun_out/prof_dfl_${S}.ncu-rep | tail -n +2; }; echo; echo "# ---- Huffman / FSE and the compaction kernels (earlier capture of this round; its lz77_v2 / lz77_decode / dfl rows are superseded by the ones above)"; python tools/ncu_kernel_summary.py gpurun_out/prof_all_codecs.ncu-rep | tail -n +2) > profiles/${R0}_all_kernels_ncu_summary.txt
+[ -f gpurun_out/prof_lz77v4_${S}.ncu-rep ] && ncu -i gpurun_out/prof_lz77v4_${S}.ncu-rep --page raw --csv > profiles/${R0}_lz77_v4_ncu_raw.csv 2>/dev/null
 R0=$R0 python - <<'PY'
 import csv, json
 import os
@@ -39,9 +40,8 @@ for f in v4_phase_cycles v4_vs_default decoder_sweep dropin_lz77 fse_segment_swe
 [ -f gpurun_out/${S}_reference_arm.json ] && cp gpurun_out/${S}_reference_arm.json profiles/${R0}_reference_arm.json
 if [ -f gpurun_out/prof_lz77v4_${S}.ncu-rep ]; then
   ncu -i gpurun_out/prof_lz77v4_${S}.ncu-rep --page details > profiles/${R0}_lz77_v4_ncu_details.txt 2>/dev/null
-  ncu -i gpurun_out/prof_lz77v4_${S}.ncu-rep --page raw --csv > profiles/${R0}_lz77_v4_ncu_raw.csv 2>/dev/null
   NCU_KERNEL=lz77_v4 python tools/ncu_lines.py gpurun_out/prof_lz77v4_${S}.ncu-rep 40 > profiles/${R0}_lz77_v4_ncu_hot_lines.txt
-  (echo "# ---- lz77_v4_kernel (experimental, B200_LZ_V4=1), 296 blocks of 64 KiB"; python tools/ncu_kernel_summary.py gpurun_out/prof_lz77v4_${S}.ncu-rep | tail -n +2) >> profiles/${R0}_all_kernels_ncu_summary.txt
+  (echo "# ---- lz77_v4_kernel (the default for text-like input), 296 blocks of 64 KiB"; python tools/ncu_kernel_summary.py gpurun_out/prof_lz77v4_${S}.ncu-rep | tail -n +2) >> profiles/${R0}_all_kernels_ncu_summary.txt
 fi
 if [ -f gpurun_out/prof_pdec_${S}.ncu-rep ]; then
   (echo; echo "# ---- token-parallel LZ77 decoder (lz77_pdec.cu), deflate variant, 256 MiB in 1 MiB blocks"; python tools/ncu_kernel_summary.py gpurun_out/prof_pdec_${S}.ncu-rep | tail -n +2) >> profiles/${R0}_all_kernels_ncu_summary.txt
