@@ -45,12 +45,13 @@ constexpr uint32_t MAXB = 65536;
 constexpr uint32_t NTHREADS = 1024;
 constexpr uint32_t W = 1u << 15, MAXLEN = 31;
 constexpr uint32_t CH = 17408;                               // compact slots of the final stage (entries + two occupants per slot)
-constexpr uint32_t CHC = 34816;                              // compact slots per chunk of the lane stage (entries only)
 constexpr uint32_t TMIN = 256;                               // clusters above this: four-warp teams; LMAX+1 .. TMIN: one warp
 constexpr uint32_t L2MAX = 64;                               // final stage: clusters of LMAX+1 .. L2MAX entries are sorted by the warp and simulated one lane each
 constexpr uint32_t LMAX = 16;                                // largest cluster simulated by one lane (above 16: sorted by the warp first)
 constexpr uint32_t NBIG = 512;                               // clusters above LMAX entries per block (kept for the final stage)
-constexpr uint32_t WL_CAP = 7680;                             // clusters of 2+ entries per chunk (work list entries)
+constexpr uint32_t WL_S16 = MAXB * 2;                           // lane stage: bare positions by compact slot (u16), the whole block
+constexpr uint32_t WL_PRE = 7680;                             // work-list entries inside the PRE region (the big-cluster list follows)
+constexpr uint32_t WL_CAP = WL_PRE + (BM_WORDS * 4 - WL_S16) / 2;   // ... plus the tail of BIG right before it; the rest spills to global memory
 constexpr uint32_t CL_MAX = 16383;                           // largest cluster (home offsets are 14 bits)
 constexpr uint32_t PLACED = 0x80000000u, ISHOME = 0x40000000u;
 
@@ -67,8 +68,8 @@ constexpr uint32_t SZ_MISC = 1792;
 constexpr uint32_t SMEM_BYTES = OFF_MISC + SZ_MISC;
 static_assert(SMEM_BYTES <= 232448, "shared memory layout too large");
 static_assert(CH * 8 <= SZ_BIG, "chunk does not fit");
-static_assert(WL_CAP * 2 + NBIG * 4 <= SZ_PRE && 4096 + 32 * 32 * 4 <= WL_CAP * 2, "work list + big-cluster list / rank prefix + warp scratch do not fit");
-static_assert(CHC * 4 <= SZ_BIG, "lane-stage chunk does not fit");
+static_assert(8192 + 4 * NBIG * 2 <= WL_PRE * 2 && WL_PRE * 2 + NBIG * 4 <= SZ_PRE && 4096 + 32 * 32 * 4 <= WL_PRE * 2 && OFF_PRE == OFF_BIG + SZ_BIG, "work list + big-cluster list / rank prefix + warp scratch do not fit");
+static_assert(WL_S16 <= SZ_BIG, "lane-stage positions do not fit");
 
 constexpr uint32_t PADDED = MAXB + (MAXB >> 6) * 4;          // 69632
 #define PADX(p) ((p) + (((p) >> 6) << 2))
@@ -80,6 +81,7 @@ struct Misc {
     uint32_t nbig, r0, r1, rdone;                                   // big-cluster list; the round of the final stage
     uint32_t cut0, top_start, nsp, sp_pad;                          // the clusters on slot 0 / the table end: raw bounds, their entries
     uint32_t tpick[8];
+    uint32_t ncls[4];            // final stage: listed clusters of the round by size class (teams | one warp, 129+ | one warp | lane batches)
     uint32_t tscr[8][12];        // per four-warp team: [2][4] cross-warp scan scratch, words 8 - 10 = progress / hand-over of the pipelined phases
     uint8_t  sexit[32][32];
     uint8_t  sentry[36];
@@ -128,13 +130,17 @@ __device__ __forceinline__ uint32_t bm_rank(const uint32_t* bm, const uint16_t* 
 // S[0 .. m): entry = position | compact home << 16, sorted by position; cstart = compact slot of the cluster's first slot.
 // PACKED (m <= 16): occupant of every slot / slot of every entry as 4-bit fields of two 64-bit registers;
 // otherwise (m <= 64) in the cluster's own E1 / E2 words.
-template <bool PACKED>
-__device__ __forceinline__ void lane_cluster(const uint32_t* S, uint16_t* E1x, uint16_t* E2x, uint32_t m, uint32_t cstart,
+template <bool PACKED, typename ST>
+__device__ __forceinline__ void lane_cluster(const ST* S, uint16_t* E1x, uint16_t* E2x, uint32_t m, uint32_t cstart,
                                              const uint8_t* data, uint16_t* fres) {
+    // PACKED: S holds bare positions (u16) and cstart is the RAW slot of the cluster's first slot (lane_sort16), the home
+    // offset of an entry is its hash minus that; otherwise entry = position | compact home << 16, cstart = compact start.
     unsigned long long live = 0, slotpack = 0, occpack = 0;
     uint32_t ex = 0;
     for (uint32_t i = 0; i < m; ++i) {
-        const uint32_t e = S[i], p = e & 0xFFFFu, o = (e >> 16) - cstart;
+        const uint32_t e = S[i], p = e & 0xFFFFu;
+        const uint32_t w = sm_word(data, p);
+        const uint32_t o = PACKED ? lz_hash(w) - cstart : (e >> 16) - cstart;
         while (ex < i) {                                     // entries expire in the order they came
             const uint32_t tex = S[ex] & 0xFFFFu;
             if (tex + W >= p) break;
@@ -144,13 +150,10 @@ __device__ __forceinline__ void lane_cluster(const uint32_t* S, uint16_t* E1x, u
         }
         const uint32_t dead = o + (uint32_t)(__ffsll((long long)(~live >> o)) - 1);   // first dead slot at/after the home: p's own slot
         uint32_t f = NONE16;
-        if (dead > o) {
-            const uint32_t w = sm_word(data, p);
-            for (uint32_t j = o; j < dead; ++j) {
-                const uint32_t y = PACKED ? (uint32_t)(occpack >> (4 * j)) & 15u : (uint32_t)E1x[j];
-                const uint32_t ty = S[y] & 0xFFFFu;
-                if (sm_word(data, ty) == w) { f = ty; break; }
-            }
+        for (uint32_t j = o; j < dead; ++j) {
+            const uint32_t y = PACKED ? (uint32_t)(occpack >> (4 * j)) & 15u : (uint32_t)E1x[j];
+            const uint32_t ty = S[y] & 0xFFFFu;
+            if (sm_word(data, ty) == w) { f = ty; break; }
         }
         fres[p] = (uint16_t)f;
         live |= 1ull << dead;
@@ -161,13 +164,18 @@ __device__ __forceinline__ void lane_cluster(const uint32_t* S, uint16_t* E1x, u
     }
 }
 
-__device__ __forceinline__ void lane_sort(uint32_t* S, uint32_t m) {   // insertion sort by position (m <= 16)
+// insertion sort of bare positions (m <= 16); returns the smallest hash = the raw slot the cluster starts on (the first
+// slot of a cluster is the home of the entry that sits in it, and no entry of the cluster has its home before it)
+__device__ __forceinline__ uint32_t lane_sort16(uint16_t* S, uint32_t m, const uint8_t* data) {
+    uint32_t hmin = lz_hash(sm_word(data, S[0]));
     for (uint32_t i = 1; i < m; ++i) {
         const uint32_t e = S[i];
+        hmin = min(hmin, lz_hash(sm_word(data, e)));
         uint32_t j = i;
-        while (j > 0) { const uint32_t f = S[j - 1]; if ((f & 0xFFFFu) <= (e & 0xFFFFu)) break; S[j] = f; --j; }
-        S[j] = e;
+        while (j > 0) { const uint32_t f = S[j - 1]; if (f <= e) break; S[j] = (uint16_t)f; --j; }
+        S[j] = (uint16_t)e;
     }
+    return hmin;
 }
 
 // one warp sorts up to 64 entries by position: bitonic network over two registers per lane
@@ -572,6 +580,7 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
         // post-pass (whole team): the finds, slot by slot (every occupant of [home, own slot) is final now; an e1 that had
         // expired at p's time was followed by an e2 placed before p, or the slot would have been dead and p would sit there)
         T.sync();
+        BC_STAMP(2);
         for (uint32_t base = 0; base < m; base += TEAM) {
             const uint32_t j = base + tt;
 #pragma unroll
@@ -721,14 +730,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
     uint32_t* S = reinterpret_cast<uint32_t*>(big);
     uint16_t* E1 = reinterpret_cast<uint16_t*>(big + CH * 4);
     uint16_t* E2 = E1 + CH;
-    uint16_t* wl = reinterpret_cast<uint16_t*>(smem + OFF_PRE);   // work list: local start of every cluster of 2+ entries, largest classes first
-    uint32_t* bigl = reinterpret_cast<uint32_t*>(smem + OFF_PRE + WL_CAP * 2);   // clusters above LMAX entries: compact start | size << 16
+    uint16_t* wl = reinterpret_cast<uint16_t*>(smem + OFF_BIG + WL_S16);   // work list: compact start of every cluster of 2 .. LMAX entries, largest classes first (tail of BIG + head of PRE)
+    uint32_t* bigl = reinterpret_cast<uint32_t*>(smem + OFF_PRE + WL_PRE * 2);   // clusters above LMAX entries: compact start | size << 16
+    uint16_t* clist = reinterpret_cast<uint16_t*>(smem + OFF_PRE + 8192);         // final stage only: [4][NBIG] indices into bigl by size class
     uint32_t* wscr = reinterpret_cast<uint32_t*>(smem + OFF_PRE + 4096);          // final stage only (behind its rank prefix): 32 words per warp, zero between uses
     uint8_t* adv = big;
     uint8_t* exitof = big + PADDED;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint16_t* fres = fres_all + (uint64_t)blockIdx.x * MAXB;
+    uint16_t* wlg = fres_all + ((uint64_t)gridDim.x + blockIdx.x) * MAXB;   // work-list spill (second half of the launch's F(p) allocation)
     uint32_t* tokb = tok_all + (uint64_t)blockIdx.x * MAXB;
     uint32_t* dbg_stats = dbg_tok ? dbg_tok + (uint64_t)nblocks * MAXB : nullptr;
 
@@ -931,43 +942,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
         __syncthreads();
         PHASE_STAMP(3);
         // ---------------- clusters, one chunk of the compact slot space at a time
-        uint32_t cb = 0;
         long long dt_sc = 0, dt_c2 = 0, dt_w = 0, dt_t = 0, dt_wait = 0, t_mark = CLK();
         uint32_t n_chunks = 0, n_wq = 0;
 #define SUBSTAMP(acc) do { if (DBG) { const long long t_now = clk_ordered(); acc += t_now - t_mark; t_mark = t_now; } } while (0)
-        while (!fb0 && cb < len) {
-            if (tid == 0) {
-                uint32_t ce = len;
-                if (len - cb > CHC) {                        // last cluster start at/before cb + CHC
-                    const uint32_t pos = cb + CHC;
-                    uint32_t wi = pos >> 5;
-                    uint32_t xw = flags[wi] & (0xFFFFFFFFu >> (31u - (pos & 31u)));
-                    while (!xw) { --wi; xw = flags[wi]; }
-                    ce = (wi << 5) + 31u - (uint32_t)__clz(xw);
-                    if (ce <= cb) { ms->fallback = 1u; ce = len; }
-                }
-                ms->ce = ce; for (int c = 0; c < 7; ++c) { ms->ccnt[c] = 0; ms->cfill[c] = 0; }
-            }
-            __syncthreads();
-            if (ms->fallback) break;
-            const uint32_t ce = ms->ce, cnt = ce - cb;
-            for (uint32_t i0 = tid; i0 < len; i0 += 8 * NTHREADS) {           // entries of the chunk -> S[compact slot]
+        if (!fb0 && !ms->fallback) {
+            // ---- lane stage: every entry's bare position at S16[compact slot] (131072 bytes: the whole block at once; the home
+            // offsets come back from the hashes, lane_sort16), clusters of 2 .. LMAX entries one lane each
+            uint16_t* S16 = reinterpret_cast<uint16_t*>(big);
+            if (tid == 0) { for (int c = 0; c < 7; ++c) { ms->ccnt[c] = 0; ms->cfill[c] = 0; } }
+            for (uint32_t i0 = tid; i0 < len; i0 += 8 * NTHREADS) {
                 uint32_t tv[8];
 #pragma unroll
                 for (uint32_t k = 0; k < 8; ++k) { const uint32_t i = i0 + k * NTHREADS; tv[k] = i < len ? tokb[i] : LONER; }
 #pragma unroll
-                for (uint32_t k = 0; k < 8; ++k) {
-                    if (tv[k] != LONER) {
-                        const uint32_t u = tv[k] & 0xFFFFu, rel = u - cb;
-                        if (rel < cnt) S[rel] = (i0 + k * NTHREADS) | ((u - (tv[k] >> 16)) << 16);
-                    }
-                }
+                for (uint32_t k = 0; k < 8; ++k)
+                    if (tv[k] != LONER) S16[tv[k] & 0xFFFFu] = (uint16_t)(i0 + k * NTHREADS);
             }
             __syncthreads();
             SUBSTAMP(dt_sc);
-            // work list: every thread looks at 17 compact slots, counts its clusters per size class, then files them
+            // work list: every thread looks at the 64 compact slots of two flag words, counts its clusters per size class, then
+            // files them (the size of a listed cluster is read from the flags again when it is worked)
             auto cls_of = [](uint32_t m) -> uint32_t { return m > 8 ? 3u : m > 4 ? 4u : m > 2 ? 5u : 6u; };
-            // (a thread looks at 2 x 17 compact slots; the size of a listed cluster is read from the flags again when it is worked)
             auto csize = [&](uint32_t start) -> uint32_t {
                 const uint32_t q = start + 1;
                 uint32_t wi = q >> 5;
@@ -975,22 +970,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                 while (!xw) { ++wi; xw = flags[wi]; }
                 return (wi << 5) + (uint32_t)(__ffs(xw) - 1) - start;
             };
+            auto wl_put = [&](uint32_t i, uint32_t v) { if (i < WL_CAP) wl[i] = (uint16_t)v; else wlg[i - WL_CAP] = (uint16_t)v; };
+            auto wl_get = [&](uint32_t i) -> uint32_t { return i < WL_CAP ? wl[i] : wlg[i - WL_CAP]; };
+            const uint32_t sp_hi = len - (SLOTS - sp_top);
             uint32_t nlb[2] = {0, 0};                         // starts of clusters of 2 .. LMAX entries among my slots
 #pragma unroll
             for (uint32_t h = 0; h < 2; ++h) {
-                const uint32_t lo17 = tid * 34 + h * 17;
-                if (lo17 < cnt) {
-                    const uint32_t hi = lo17 + 17 < cnt ? lo17 + 17 : cnt;
-                    const uint32_t a = cb + lo17;
-                    const unsigned long long win = ((unsigned long long)flags[(a >> 5) + 1] << 32) | flags[a >> 5];
-                    const uint32_t fb = (uint32_t)(win >> (a & 31u));        // flags of a .. a + 31 (18 are needed)
-                    uint32_t bits = fb & ((1u << (hi - lo17)) - 1u) & ~(fb >> 1);   // a start directly followed by a start is a loner
+                const uint32_t a = (2 * tid + h) * 32;
+                if (a < len) {
+                    const uint32_t fb = flags[a >> 5], nx = flags[(a >> 5) + 1];
+                    uint32_t bits = fb & ~((fb >> 1) | (nx << 31));              // a start directly followed by a start is a loner
+                    if (len - a < 32u) bits &= (1u << (len - a)) - 1u;           // (the sentinel behind the last slot is no cluster)
                     nlb[h] = bits;
                     while (bits) {
                         const uint32_t k = (uint32_t)(__ffs(bits) - 1);
                         bits &= bits - 1;
                         const uint32_t start = a + k;
-                        if (start < sp_cut0 || start >= len - (SLOTS - sp_top)) { nlb[h] &= ~(1u << k); continue; }   // a special cluster: done above
+                        if (start < sp_cut0 || start >= sp_hi) { nlb[h] &= ~(1u << k); continue; }   // a special cluster: done above
                         const uint32_t m = csize(start);
                         if (m > LMAX) {                          // kept for the final stage, where all of them run at once
                             nlb[h] &= ~(1u << k);
@@ -1007,18 +1003,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                 uint32_t run = 0;
                 for (int c = 0; c < 7; ++c) { ms->cbase[c] = run; run += ms->ccnt[c]; }
                 ms->cbase[7] = run; ms->next_l = 0;
-                if (run > WL_CAP) ms->fallback = 1u;
             }
             __syncthreads();
 #pragma unroll
             for (uint32_t h = 0; h < 2; ++h) {
-                const uint32_t lo17 = tid * 34 + h * 17;
+                const uint32_t a = (2 * tid + h) * 32;
                 uint32_t nlbits = nlb[h];
                 while (nlbits && !ms->fallback) {
                     const uint32_t k = (uint32_t)(__ffs(nlbits) - 1);
                     nlbits &= nlbits - 1;
-                    const uint32_t c = cls_of(csize(cb + lo17 + k));
-                    wl[ms->cbase[c] + atomicAdd(&ms->cfill[c], 1u)] = (uint16_t)(lo17 + k);
+                    const uint32_t c = cls_of(csize(a + k));
+                    wl_put(ms->cbase[c] + atomicAdd(&ms->cfill[c], 1u), a + k);
                 }
             }
             __syncthreads();
@@ -1033,16 +1028,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                     if (g >= total) break;
                     const uint32_t it = g + lane;
                     if (it < total) {
-                        const uint32_t kl = wl[it], m = csize(cb + kl);
-                        lane_sort(S + kl, m);
-                        lane_cluster<true>(S + kl, nullptr, nullptr, m, cb + kl, data, fres);
+                        const uint32_t kl = wl_get(it), m = csize(kl);
+                        const uint32_t hmin = lane_sort16(S16 + kl, m, data);
+                        lane_cluster<true>(S16 + kl, nullptr, nullptr, m, hmin, data, fres);
                     }
                 }
                 if (DBG) SUBSTAMP(dt_w);
             }
             __syncthreads();
             SUBSTAMP(dt_wait);
-            cb = ce;
         }
         // ---------------- final stage: the clusters above LMAX entries, all at once (the largest decides, not their sum).
         // Rounds of as many listed clusters as fit the chunk area; a bit per compact slot says "in a cluster of this round",
@@ -1065,12 +1059,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                 if (tid == 0) {                                  // clusters r0 .. r1 of this round
                     uint32_t r1 = nbig;
                     if (ms->scan[33] > CH) { uint32_t tot = 0; r1 = r0; while (r1 < nbig && tot + (bigl[r1] >> 16) <= CH) { tot += bigl[r1] >> 16; ++r1; } }
-                    ms->r0 = r0; ms->r1 = r1; ms->next_t = r0; ms->rdone = 0; ms->next_w = r0;
+                    ms->r0 = r0; ms->r1 = r1; ms->next_t = 0; ms->rdone = 0; ms->next_w = 0;
+                    ms->ncls[0] = 0; ms->ncls[1] = 0; ms->ncls[2] = 0; ms->ncls[3] = 0;
                 }
                 for (uint32_t i = tid; i < SZ_FLAGS / 4; i += NTHREADS) flags[i] = 0;
                 wscr[tid] = 0;
                 __syncthreads();
                 const uint32_t r1 = ms->r1;
+                {   // the round's clusters by size class (one pick = one atomic, the larger ones of a tier first)
+                    const uint32_t k = r0 + tid;
+                    const uint32_t mk = k < r1 ? bigl[k] >> 16 : 0u;
+                    const uint32_t c = mk > TMIN ? 0u : mk > 128u ? 1u : mk > L2MAX ? 2u : 3u;
+#pragma unroll
+                    for (uint32_t cc = 0; cc < 4; ++cc) {
+                        const uint32_t bal = __ballot_sync(0xffffffffu, mk != 0u && c == cc);
+                        if (bal) {
+                            uint32_t base = 0;
+                            if (lane == 0) base = atomicAdd(&ms->ncls[cc], (uint32_t)__popc(bal));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (mk != 0u && c == cc) clist[cc * NBIG + base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)k;
+                        }
+                    }
+                }
                 for (uint32_t k = r0 + warp; k < r1; k += 32) {      // bits of the cluster's slots
                     const uint32_t cs0 = bigl[k] & 0xFFFFu, m = bigl[k] >> 16;
                     for (uint32_t w = (cs0 >> 5) + lane; w <= ((cs0 + m - 1) >> 5); w += 32) {
@@ -1081,6 +1091,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                     }
                 }
                 __syncthreads();
+                if (tid == 992 && ms->ncls[0] <= 32u) {            // the team tier starts with its largest cluster
+                    const uint32_t nt = ms->ncls[0];
+                    for (uint32_t a = 1; a < nt; ++a) {
+                        const uint16_t v = clist[a]; const uint32_t mv = bigl[v] >> 16;
+                        uint32_t j = a;
+                        while (j > 0 && (bigl[clist[j - 1]] >> 16) < mv) { clist[j] = clist[j - 1]; --j; }
+                        clist[j] = v;
+                    }
+                }
                 {   // rank prefix per word (u16 at pre16[0 .. 2048]: the work-list area is free now)
                     const uint32_t w0 = flags[2 * tid], w1 = flags[2 * tid + 1];
                     const uint32_t s2 = __popc(w0) + __popc(w1);
@@ -1116,9 +1135,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                     // clusters above TMIN entries by four-warp teams, largest first would be better still: list order
                     for (;;) {
                         if (TT.tt == 0) {
-                            uint32_t qi;
-                            for (;;) { qi = atomicAdd(&ms->next_t, 1u); if (qi >= r1 || (bigl[qi] >> 16) > TMIN) break; }
-                            ms->tpick[team] = qi;
+                            const uint32_t q = atomicAdd(&ms->next_t, 1u);
+                            ms->tpick[team] = q < ms->ncls[0] ? (uint32_t)clist[q] : r1;
                         }
                         TT.sync();
                         const uint32_t qi = ms->tpick[team];
@@ -1137,7 +1155,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                     }
                     for (;;) {                                   // L2MAX+1 .. TMIN entries: one warp each
                         uint32_t qi = 0;
-                        if (lane == 0) { for (;;) { qi = atomicAdd(&ms->rdone, 1u) + r0; if (qi >= r1 || ((bigl[qi] >> 16) <= TMIN && (bigl[qi] >> 16) > L2MAX)) break; } }
+                        if (lane == 0) { const uint32_t q = atomicAdd(&ms->rdone, 1u), na = ms->ncls[1]; qi = q < na ? (uint32_t)clist[NBIG + q] : q - na < ms->ncls[2] ? (uint32_t)clist[2 * NBIG + q - na] : r1; }
                         qi = __shfl_sync(0xffffffffu, qi, 0);
                         if (qi >= r1) break;
                         const uint32_t cs0 = bigl[qi] & 0xFFFFu, m = bigl[qi] >> 16, kl = brank(cs0);
@@ -1147,11 +1165,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                         uint32_t g = 0;
                         if (lane == 0) g = atomicAdd(&ms->next_w, 32u);
                         g = __shfl_sync(0xffffffffu, g, 0);
-                        if (g >= r1) break;
-                        const uint32_t qi = g + lane;
-                        const uint32_t ent = qi < r1 ? bigl[qi] : 0u;
+                        if (g >= ms->ncls[3]) break;
+                        const uint32_t ent = g + lane < ms->ncls[3] ? bigl[clist[3 * NBIG + g + lane]] : 0u;
                         const uint32_t m = ent >> 16, cs0 = ent & 0xFFFFu;
-                        const bool mine = m > LMAX && m <= L2MAX;
+                        const bool mine = m != 0u;
                         const uint32_t kl = mine ? brank(cs0) : 0u;
                         uint32_t coop = __ballot_sync(0xffffffffu, mine);
                         while (coop) {

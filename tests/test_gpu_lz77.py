@@ -257,8 +257,15 @@ def _random_token_block(rng, out_len, style):
     o = 0
     while o < out_len:
         r = rng.random()
-        if o == 0 or r < (0.15 if style == "matches" else 0.6):
+        if o == 0 or r < (0.15 if style == "matches" else 0.93 if style == "sparse" else 0.6):
             tok += bytes((0, int(rng.integers(0, 256)))); o += 1
+            continue
+        if style == "sparse":
+            # literal-heavy (stream above 1.1 x block: the decoder's byte-per-lane instantiation) with short matches that
+            # read what the same 32-unit step has just produced: offsets 1 .. 40, overlapping copies included
+            off = int(rng.integers(1, min(o, 40) + 1))
+            ln = min(int(rng.integers(0, 12)), out_len - o)
+            tok += bytes((1, off & 0xFF, off >> 8, ln)); o += ln
             continue
         if style == "rle":
             off = int(rng.integers(1, min(o, 4) + 1))
@@ -272,12 +279,12 @@ def _random_token_block(rng, out_len, style):
     return bytes(tok)
 
 
-@pytest.mark.parametrize("style", ["mixed", "matches", "rle", "far"])
+@pytest.mark.parametrize("style", ["mixed", "matches", "rle", "far", "sparse"])
 def test_decoder_on_handmade_streams(ctx, ob, style, monkeypatch):
     """both deflate-variant decoders (token-parallel units, token-serial) against the oracle's byte-serial decoder"""
     import torch
     from compression_algorithms_b200 import device as dv
-    rng = np.random.default_rng({"mixed": 1, "matches": 2, "rle": 3, "far": 4}[style])
+    rng = np.random.default_rng({"mixed": 1, "matches": 2, "rle": 3, "far": 4, "sparse": 5}[style])
     block = 4096
     lens = [block] * 6 + [1, 2, 33, 777]
     n = sum(lens)
@@ -297,3 +304,18 @@ def test_decoder_on_handmade_streams(ctx, ob, style, monkeypatch):
             got = dv.lz77_decode(ctx, st, out=torch.zeros(nn, dtype=torch.uint8, device=ctx.device)).cpu().numpy()
             d = first_diff(got, want)
             assert d == -1, "%s decoder (%s) differs at byte %d" % ("serial" if serial == "1" else "unit", style, d)
+
+
+def test_decoder_mixed_block_kinds(ctx):
+    """one call whose 64 KiB blocks alternate between literal-heavy (text, random) and match-heavy (acgt, two-symbol) content:
+    the two instantiations of lz77_decode_units_kernel share the blocks by stream size and together restore the input"""
+    import torch
+    from compression_algorithms_b200 import device as dv
+    parts = [_corpus(65536, kind, 40 + i) for i, kind in enumerate([0, 1, 3, 2, 1, 0, 2, 3, 0, 0, 1])] + [_corpus(12345, 0, 77)]
+    data = np.concatenate(parts)
+    d = _to_dev(ctx, data)
+    st = dv.lz77_encode(ctx, d, dv.LZ_DEFLATE, 65536)
+    sizes = st.block_sizes.cpu().numpy()
+    assert (sizes[:11] * 10 >= 65536 * 11).any() and (sizes[:11] * 10 < 65536 * 11).any()      # both kinds of block are present
+    got = dv.lz77_decode(ctx, st, out=torch.full((data.size,), 0xEE, dtype=torch.uint8, device=ctx.device)).cpu().numpy()
+    assert first_diff(got, data) == -1

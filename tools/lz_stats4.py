@@ -26,6 +26,6 @@ tt = s[:, 24:32] * 64; print("  per-team busy cycles: median of max %d, median o
 for bi in range(3):
     print("   block", bi, "slowest", (mx[bi] >> 14) * 64, "m", mx[bi] & 0x3FFF, "team busy", list(tt[bi]))
 tb = s[:, 40:45] * 64
-print("  team clusters, cycles summed over the block's clusters (median): sort %d, phase-1 sweep on warp 0 %d, then waiting for the pipelined phase 2 + finds %d" % (np.median(tb[:, 0]), np.median(tb[:, 3]), np.median(tb[:, 4])))
+print("  team clusters, cycles summed over the block's clusters (median): sort %d, phase-1 sweep on warp 0 %d, then waiting for the pipelined phase 2 %d, finds %d" % (np.median(tb[:, 0]), np.median(tb[:, 3]), np.median(tb[:, 2]), np.median(tb[:, 4])))
 ff = s[:, 50:54]
 print("  final stage (thread 0): list + bitmap + prefix %d, scatter %d, own work %d, wait for the others %d" % tuple(np.median(ff[:, k]) for k in range(4)))
