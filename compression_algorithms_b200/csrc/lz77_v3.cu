@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v3_kernel(const uint8_t* __r
             const uint32_t hi = cend < len ? cend : len;
             for (uint32_t p = hi; p-- > lo;) {
                 const uint32_t nx = p + adv[PADX(p)];
-                exitof[PADX(p)] = (uint8_t)(nx >= cend ? nx - cend : exitof[PADX(nx)]);
+                exitof[PADX(p)] = (uint8_t)(nx >= cend ? nx - cend : nx >= hi ? 0u : exitof[PADX(nx)]);   // (a ragged block's last chunk ends at len: nothing behind it was written)
             }
         }
         __syncthreads();
@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v3_kernel(const uint8_t* __r
         __syncthreads();
         if (tid == 0) {
             uint32_t e = 0;
-            for (uint32_t s = 0; s < 32; ++s) { ms->sentry[s] = (uint8_t)e; e = ms->sexit[s][e]; }
+            for (uint32_t s = 0; s < 32; ++s) { ms->sentry[s] = (uint8_t)e; e = ms->sexit[s][e & 31u]; }
         }
         __syncthreads();
         uint8_t* centry = reinterpret_cast<uint8_t*>(pre) + 8192;   // u8[1024] chunk entry offsets (clear of the V0 staging spill)

@@ -257,6 +257,8 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                             const uint8_t* data, uint16_t* fres, uint32_t* scr, uint32_t* tdbg = nullptr) {
     const uint32_t tt = T.tt;
     long long t_m = tdbg ? clock64() : 0;
+    const long long t_in = t_m;
+#define BC_MARK(k, who) do { if (tdbg && tt == (who)) atomicAdd(&tdbg[k], (uint32_t)((clock64() - t_in) >> 6)); } while (0)
 #define BC_STAMP(k) do { if (tdbg && tt == 0) { const long long t_n = clock64(); atomicAdd(&tdbg[k], (uint32_t)((t_n - t_m) >> 6)); t_m = t_n; } } while (0)
     for (uint32_t i = tt; i < m; i += TEAM) { const uint32_t e = Sx[i]; Sx[i] = (e & 0xFFFFu) | (((e >> 16) - cstart) << 16); }
     T.sync();
@@ -442,20 +444,25 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                         E1x[k + a] = (uint16_t)i;
                     }
                 }
+                if (tt == 0) { T.scr[10] = 0u; T.scr[11] = 0u; }     // (p1info has been read by everyone: the helpers' progress words)
                 T.sync();
                 if (tt == 0) { __threadfence_block(); *prog = m; }
             }
         }
-        if (TEAM != 32 && (tt >> 5) == 2u && m - n1 > 0u) {
-            // warp 2: for every slot phase 1 has finished, how many phase-2 entries arrive before the slot is dead (lower bound
-            // of its release time in the time-ordered phase-2 entries); parked in E2x[j] until phase 2 reaches the slot
+        if (TEAM != 32 && m - n1 > 0u && (p1_closed ? (tt >> 5) != 1u : (tt >> 5) == 2u)) {
+            // release ranks: for every slot phase 1 has finished, how many phase-2 entries arrive before the slot is dead (lower
+            // bound of its release time in the time-ordered phase-2 entries); parked in E2x[j] until phase 2 reaches the slot.
+            // Chunks of 32 slots; behind the closed form warps 0, 2 and 3 take them in turn (each publishes the start of its next
+            // chunk), behind a sweeping warp 0 it is warp 2 alone.
             const uint32_t cnt2 = m - n1;
-            uint32_t donej = 0;
-            while (donej < m) {
-                uint32_t lim;
-                while ((lim = *prog) <= donej) { __nanosleep(40); }
+            const uint32_t nh = p1_closed ? 3u : 1u, hidx = p1_closed ? ((tt >> 5) == 0u ? 0u : (tt >> 5) - 1u) : 0u;
+            volatile uint32_t* mine = reinterpret_cast<volatile uint32_t*>(T.scr + 9 + hidx);
+            for (uint32_t j0 = hidx * 32u; j0 < m; j0 += nh * 32u) {
+                const uint32_t need = j0 + 32u < m ? j0 + 32u : m;
+                while (*prog < need) { __nanosleep(40); }
                 __threadfence_block();
-                for (uint32_t j = donej + lane; j < lim; j += 32) {
+                const uint32_t j = j0 + lane;
+                if (j < m) {
                     const uint32_t y1 = E1x[j];
                     uint32_t a = 0;
                     if (y1 != NONE16) {
@@ -466,9 +473,10 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                     E2x[j] = (uint16_t)a;
                 }
                 __syncwarp();
-                donej = lim;
-                if (lane == 0) { __threadfence_block(); *progg = donej; }
+                if (lane == 0) { __threadfence_block(); *mine = j0 + nh * 32u; }
             }
+            if (lane == 0) { __threadfence_block(); *mine = 0xFFFFFFFFu; }
+            BC_MARK(5, 64u);
         }
         auto next_home_w = [&](uint32_t x) -> uint32_t {
             for (uint32_t base = x + 1; base < m; base += 32) {
@@ -490,25 +498,51 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                 if (!ph && TEAM != 32 && lane == 0) { __threadfence_block(); *prog = m; }
                 continue;
             }
-            uint32_t elig = 0, pend = 0;
-            for (uint32_t b0 = 0; b0 < 32; ++b0) {
-                const uint32_t bq = (b0 + lane) & 31u, g = 32u * lane + bq;     // rotated: no bank conflicts
-                if (g < cntp) { if (((Sx[ebase + g] >> 16) & 0x3FFFu) == 0u) elig |= 1u << bq; else pend |= 1u << bq; }
+            uint32_t elig = 0, pend = 0, pmin = 0xFFFFFFFFu;              // pmin: the earliest home among my pending entries
+            for (uint32_t r = 0; r * 32u < cntp; ++r) {                   // a row of 32 entries per step, lane r keeps the row's masks
+                const uint32_t g = r * 32u + lane;
+                const uint32_t hm = g < cntp ? (Sx[ebase + g] >> 16) & 0x3FFFu : 0xFFFFFFFFu;
+                const uint32_t be = __ballot_sync(0xffffffffu, hm == 0u), bp = __ballot_sync(0xffffffffu, hm != 0u && hm != 0xFFFFFFFFu);
+                const uint32_t rmin = __reduce_min_sync(0xffffffffu, hm == 0u ? 0xFFFFFFFFu : hm);
+                if (lane == r) { elig = be; pend = bp; pmin = rmin; }
             }
+            if (ph && TEAM != 32) BC_MARK(6, 32u);
             uint32_t x = 0;
             while (x < m) {
                 const uint32_t xe = next_home_w(x);
-                if (x > 0 && __any_sync(0xffffffffu, pend != 0u)) {       // entries whose home the sweep has reached join the pool
-                    uint32_t pb = pend;
-                    while (pb) {
-                        const uint32_t bq = (uint32_t)(__ffs(pb) - 1);
-                        pb &= pb - 1;
-                        if (((Sx[ebase + 32u * lane + bq] >> 16) & 0x3FFFu) <= x) { elig |= 1u << bq; pend &= ~(1u << bq); }
+                if (x > 0 && __any_sync(0xffffffffu, pmin <= x)) {        // entries whose home the sweep has reached join the pool
+                    if (pmin <= x) {
+                        uint32_t pb = pend, nmin = 0xFFFFFFFFu;
+                        while (pb) {
+                            const uint32_t bq = (uint32_t)(__ffs(pb) - 1);
+                            pb &= pb - 1;
+                            const uint32_t hm = (Sx[ebase + 32u * lane + bq] >> 16) & 0x3FFFu;
+                            if (hm <= x) { elig |= 1u << bq; pend &= ~(1u << bq); } else nmin = min(nmin, hm);
+                        }
+                        pmin = nmin;
                     }
                 }
-                if (ph && TEAM != 32) { while (*progg < xe) { __nanosleep(40); } __threadfence_block(); }   // phase 1 and the release ranks are past this segment
+                if (ph && TEAM != 32) {                                   // phase 1 and the release ranks are past this segment
+                    volatile uint32_t* pw = reinterpret_cast<volatile uint32_t*>(T.scr + 9);
+                    for (;;) {
+                        uint32_t f = pw[0];
+                        if (p1_closed) f = min(f, min(pw[1], pw[2]));
+                        if (f >= xe) break;
+                        __nanosleep(20);
+                    }
+                    __threadfence_block();
+                }
                 uint32_t used = xe;
-                if (ph) { uint32_t a = x, b = xe; while (a < b) { const uint32_t mid = (a + b) >> 1; if (E1x[mid] != NONE16) a = mid + 1; else b = mid; } used = a; }
+                if (ph) {                                                 // the phase-1 slots of a segment are a prefix of it
+                    if (xe - x <= 96u) {
+                        used = x;
+                        for (uint32_t b0 = x; b0 < xe; b0 += 32) {
+                            const uint32_t fm = __ballot_sync(0xffffffffu, b0 + lane < xe && E1x[b0 + lane] != NONE16);
+                            used = b0 + (uint32_t)__popc(fm);
+                            if (fm != 0xFFFFFFFFu) break;
+                        }
+                    } else { uint32_t a = x, b = xe; while (a < b) { const uint32_t mid = (a + b) >> 1; if (E1x[mid] != NONE16) a = mid + 1; else b = mid; } used = a; }
+                }
                 for (uint32_t part = 0; part < (ph ? 2u : 1u); ++part) {
                     const uint32_t lo = ph ? (part ? used : x) : x, hi = ph ? (part ? xe : used) : xe;
                     if (lo >= hi) continue;
@@ -575,6 +609,7 @@ __device__ void big_cluster(Team<TEAM>& T, uint32_t* Sx, uint16_t* E1x, uint16_t
                 if (!ph && TEAM != 32) { __syncwarp(); if (lane == 0) { __threadfence_block(); *prog = xe; } }
                 x = xe;
             }
+            if (ph && TEAM != 32) BC_MARK(7, 32u);
         }
         BC_STAMP(3);
         // post-pass (whole team): the finds, slot by slot (every occupant of [home, own slot) is final now; an e1 that had
@@ -1161,6 +1196,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                         const uint32_t cs0 = bigl[qi] & 0xFFFFu, m = bigl[qi] >> 16, kl = brank(cs0);
                         big_cluster<32>(TW, S + kl, E1 + kl, E2 + kl, m, cs0, data, fres, wscr + warp * 32);
                     }
+                    if (DBG && dbg_stats && lane == 0) dbg_stats[(uint64_t)b * 136 + 60 + warp] = (uint32_t)((clock64() - t_mark) >> 6);
                     for (;;) {                                   // LMAX+1 .. L2MAX entries: 32 listed clusters per warp, the warp sorts, a lane simulates
                         uint32_t g = 0;
                         if (lane == 0) g = atomicAdd(&ms->next_w, 32u);
@@ -1180,6 +1216,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                         if (mine) lane_cluster<false>(S + kl, E1 + kl, E2 + kl, m, 0u, data, fres);
                     }
                 }
+                if (DBG && dbg_stats && lane == 0) dbg_stats[(uint64_t)b * 136 + 92 + warp] = (uint32_t)((clock64() - t_mark) >> 6);
                 SUBSTAMP(dt_f[2]);
                 __syncthreads();
                 SUBSTAMP(dt_f[3]);
@@ -1224,7 +1261,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
             const uint32_t hi = cend < len ? cend : len;
             for (uint32_t p = hi; p-- > lo;) {
                 const uint32_t nx = p + adv[PADX(p)];
-                exitof[PADX(p)] = (uint8_t)(nx >= cend ? nx - cend : exitof[PADX(nx)]);
+                exitof[PADX(p)] = (uint8_t)(nx >= cend ? nx - cend : nx >= hi ? 0u : exitof[PADX(nx)]);   // (a ragged block's last chunk ends at len: nothing behind it was written)
             }
         }
         __syncthreads();
@@ -1240,7 +1277,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
         __syncthreads();
         if (tid == 0) {
             uint32_t e = 0;
-            for (uint32_t s = 0; s < 32; ++s) { ms->sentry[s] = (uint8_t)e; e = ms->sexit[s][e]; }
+            for (uint32_t s = 0; s < 32; ++s) { ms->sentry[s] = (uint8_t)e; e = ms->sexit[s][e & 31u]; }
         }
         __syncthreads();
         uint8_t* centry = reinterpret_cast<uint8_t*>(pre) + 8192;
@@ -1376,6 +1413,12 @@ int lz77_v4_launch(b200_ctx* ctx, const uint8_t* d_in, uint64_t n, uint64_t bs, 
     else lz77_v4_kernel<false><<<(unsigned)grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_in, n, (uint32_t)bs, (uint32_t)nblocks, fres, tok, scratch, stride, d_block_sizes, block_bytes, fb_list, fb_cnt, use_flag, dbg_tok);
     CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
+    if (getenv("B200_LZ_V4_SYNC")) {           // diagnostic: separate a fault of this kernel from one of the hand-back launch
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        uint32_t hcnt = 0;
+        CUDA_TRY(cudaMemcpy(&hcnt, fb_cnt, 4, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "lz77_v4_kernel done: %u of %llu blocks handed back\n", hcnt, (unsigned long long)nblocks);
+    }
     // the blocks handed back (empty list: the kernel's CTAs return at once)
     return lz77_v2_launch(ctx, 1, d_in, n, bs, nblocks, scratch, stride, d_block_sizes, block_bytes, dbg_tok, fb_list, fb_cnt);
 }

@@ -121,3 +121,14 @@ def test_small_special_clusters_inside_v4(ctx, ob, copies):
         for p in rng.integers(b * 65536, (b + 1) * 65536 - 8, size=copies):
             data[p:p + 4] = pat
     _encode_check(ctx, ob, data, 1, 65536)
+
+
+@pytest.mark.parametrize("kind", [0, 3])
+@pytest.mark.parametrize("last", [58395, 60470, 65535, 65473, 64001])
+def test_ragged_last_block_in_the_top_chunks(ctx, ob, kind, last):
+    """a last block whose length is no multiple of 64 and lies in the parse's last super-chunks: the exit of its final 64-byte
+    chunk must not come from shared memory nobody wrote (found by tools/v4_stress_random.py: it indexed the super-chunk table out
+    of range, an illegal address in 1 of ~3 encodes of such a block; same code in lz77_v2_kernel). Repeated: the stale bytes varied."""
+    data = _corpus(2 * 65536 + last, kind, 1000 + last)
+    for _ in range(6):
+        _encode_check(ctx, ob, data, 1, 65536)

@@ -19,10 +19,18 @@ for r in range(rounds):
             data[a:a + L] = np.resize(data[a:a + per].copy(), min(L, n - a))
     d = torch.from_numpy(data).to(ctx.device)
     os.environ["B200_LZ_V4"] = "0"
-    a = dv.lz77_encode(ctx, d, 1, block)
+    try:
+        a = dv.lz77_encode(ctx, d, 1, block)
+    except Exception:
+        print("FAILED (lz77_v2_kernel call) round %d kind %d n %d block %d seed %d" % (r, kind, n, block, seed), flush=True)
+        raise
     out_a = a.out[: a.total_bytes].clone(); sz_a = a.block_sizes.clone()
     os.environ["B200_LZ_V4"] = "1"
-    b = dv.lz77_encode(ctx, d, 1, block)
+    try:
+        b = dv.lz77_encode(ctx, d, 1, block)
+    except Exception:
+        print("FAILED round %d kind %d n %d block %d seed %d" % (r, kind, n, block, seed), flush=True)
+        raise
     ok = a.total_bytes == b.total_bytes and bool(torch.equal(sz_a, b.block_sizes)) and bool(torch.equal(out_a, b.out[: b.total_bytes]))
     tot += n; bad += 0 if ok else 1
     if not ok: print("MISMATCH kind %d n %d block %d seed %d" % (kind, n, block, seed))
