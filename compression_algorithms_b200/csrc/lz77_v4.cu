@@ -913,27 +913,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                 uint32_t tv[8];
 #pragma unroll
                 for (uint32_t k = 0; k < 8; ++k) { const uint32_t i = i0 + k * NTHREADS; tv[k] = i < len ? tokb[i] : 0u; }
+                // (branch-free per entry, so that the eight entries' shared-memory reads overlap)
+                uint32_t hv[8], rk[8];
+                bool ln[8];
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) {
+                    const uint32_t i = i0 + k * NTHREADS;
+                    const uint32_t cl = tv[k] & 0xFFFFFu, dd = tv[k] >> 20;
+                    uint32_t h = cl - dd;
+                    if (dd >= 4095u) h = lz_hash(sm_word(data, i < len ? i : 0u));
+                    hv[k] = h;
+                    const uint32_t hb = h ? h - 1u : 0u, ha = h + 1u;
+                    const uint32_t below = h ? (bm[hb >> 5] >> (hb & 31u)) & 1u : 0u;
+                    const uint32_t above = (bm[ha >> 5] >> (ha & 31u)) & 1u;
+                    ln[k] = cl == h && !below && !above;
+                    rk[k] = bm_rank(bm, pre16, cl) | ((cl - h) << 16);
+                }
 #pragma unroll
                 for (uint32_t k = 0; k < 8; ++k) {
                     const uint32_t i = i0 + k * NTHREADS;
                     if (i >= len) break;
-                    const uint32_t cl = tv[k] & 0xFFFFFu, dd = tv[k] >> 20;
-                    const uint32_t h = dd < 4095u ? cl - dd : lz_hash(sm_word(data, i));
-                    const uint32_t d = cl - h;
+                    const uint32_t h = hv[k];
                     if (h < sp_cut0 || h >= sp_top) {                     // entry of a special cluster: listed, kept out of everything else
                         const uint32_t si = atomicAdd(&ms->nsp, 1u);
                         if (si < 60u) spl[si] = (uint16_t)i; else ms->fallback = 1u;
                         tokb[i] = LONER; fres[i] = (uint16_t)NONE16;
                         continue;
                     }
-                    bool loner = false;
-                    if (d == 0) {
-                        const uint32_t wi = h >> 5, bi = h & 31u, wv = bm[wi];
-                        const uint32_t below = bi ? (wv >> (bi - 1u)) & 1u : (wi ? bm[wi - 1] >> 31 : 0u);
-                        const uint32_t above = bi != 31u ? (wv >> (bi + 1u)) & 1u : (bm[wi + 1] & 1u);
-                        loner = !below && !above;
-                    }
-                    tokb[i] = loner ? LONER : (bm_rank(bm, pre16, cl) | (d << 16));
+                    tokb[i] = ln[k] ? LONER : rk[k];
                     fres[i] = (uint16_t)NONE16;
                 }
             }
@@ -1196,7 +1203,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                         const uint32_t cs0 = bigl[qi] & 0xFFFFu, m = bigl[qi] >> 16, kl = brank(cs0);
                         big_cluster<32>(TW, S + kl, E1 + kl, E2 + kl, m, cs0, data, fres, wscr + warp * 32);
                     }
-                    if (DBG && dbg_stats && lane == 0) dbg_stats[(uint64_t)b * 136 + 60 + warp] = (uint32_t)((clock64() - t_mark) >> 6);
                     for (;;) {                                   // LMAX+1 .. L2MAX entries: 32 listed clusters per warp, the warp sorts, a lane simulates
                         uint32_t g = 0;
                         if (lane == 0) g = atomicAdd(&ms->next_w, 32u);
@@ -1216,7 +1222,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                         if (mine) lane_cluster<false>(S + kl, E1 + kl, E2 + kl, m, 0u, data, fres);
                     }
                 }
-                if (DBG && dbg_stats && lane == 0) dbg_stats[(uint64_t)b * 136 + 92 + warp] = (uint32_t)((clock64() - t_mark) >> 6);
                 SUBSTAMP(dt_f[2]);
                 __syncthreads();
                 SUBSTAMP(dt_f[3]);

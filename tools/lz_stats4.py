@@ -31,7 +31,3 @@ ff = s[:, 50:54]
 print("  final stage (thread 0): list + bitmap + prefix %d, scatter %d, own work %d, wait for the others %d" % tuple(np.median(ff[:, k]) for k in range(4)))
 tw = s[:, 45:48] * 64
 print("  team clusters, cycles after entry summed over the block's clusters (median): release ranks done (warp 2) %d, phase-2 sweep starts (warp 1) %d, ends %d" % tuple(np.median(tw[:, k]) for k in range(3)))
-t2 = s[:, 60:92] * 64; t3 = s[:, 92:124] * 64
-print("  final stage, per warp, cycles after the scatter (median over blocks of: min / median / max over warps): one-warp tier done %d / %d / %d, lane batches done %d / %d / %d" % (
-    np.median(t2.min(1)), np.median(np.median(t2, 1)), np.median(t2.max(1)), np.median(t3.min(1)), np.median(np.median(t3, 1)), np.median(t3.max(1))))
-print("   block 0 tier ends per warp:", list(t2[0] // 1000), list(t3[0] // 1000))
