@@ -483,6 +483,113 @@ __global__ void __launch_bounds__(128) lz77_decode_units_kernel(const uint8_t* _
     }
 }
 
+// The byte-per-lane decoder of literal-heavy blocks at 64 units per step (a lane holds unit l of two rows of 32): the per-step
+// work that does not depend on the output (token look-ahead, classification, ONE packed scan of both rows' output lengths) is
+// paid once per 64 units, the bytes then go out 64 per round exactly as in lz77_decode_units_kernel<0>.
+__global__ void __launch_bounds__(128) lz77_decode_units64_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ block_off,
+                                                                 const uint64_t* __restrict__ block_sizes, uint64_t n, uint64_t bs,
+                                                                 uint64_t nblocks, uint8_t* __restrict__ out) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t b = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= nblocks) return;
+    const uint32_t len = (uint32_t)(n - b * bs < bs ? n - b * bs : bs);
+    if (block_sizes[b] * 10ull < (uint64_t)len * 11ull) return;          // match-heavy block: lz77_decode_units_kernel<1>
+    const uint16_t* tk = reinterpret_cast<const uint16_t*>(stream + block_off[b]);
+    const uint32_t nunits = (uint32_t)(block_sizes[b] >> 1);
+    uint8_t* gout = out + b * bs;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t o = 0, s0 = 0;
+    auto ld = [&](uint32_t u) -> uint32_t { return u < nunits ? (uint32_t)__ldg(tk + u) : 0u; };
+    uint32_t a0 = ld(lane), a1 = ld(lane + 32), b0 = ld(lane + 64), b1 = ld(lane + 96), c0 = ld(lane + 128), c1 = ld(lane + 160);
+    for (uint32_t base = 0; base < nunits; base += 64) {
+        const uint32_t cur0 = a0, cur1 = a1;
+        a0 = b0; a1 = b1; b0 = c0; b1 = c1;
+        c0 = ld(base + 192 + lane); c1 = ld(base + 224 + lane);
+        uint32_t nx0 = __shfl_down_sync(0xffffffffu, cur0, 1), nx1 = __shfl_down_sync(0xffffffffu, cur1, 1);
+        const uint32_t f1 = __shfl_sync(0xffffffffu, cur1, 0), f2 = __shfl_sync(0xffffffffu, a0, 0);
+        if (lane == 31) { nx0 = f1; nx1 = f2; }
+        const bool v0 = base + lane < nunits, v1 = base + 32 + lane < nunits;
+        const bool h0 = v0 && (cur0 & 0xFFu) != 0u, h1 = v1 && (cur1 & 0xFFu) != 0u;
+        const uint32_t m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+        if ((m0 | m1) == 0u && s0 == 0u) {                                   // 64 literals
+            if (v0 && o + lane < len) gout[o + lane] = (uint8_t)(cur0 >> 8);
+            if (v1 && o + 32 + lane < len) gout[o + 32 + lane] = (uint8_t)(cur1 >> 8);
+            o += nunits - base < 64u ? nunits - base : 64u;
+            __syncwarp();
+            continue;
+        }
+        // a unit is a match tail iff the run of "first byte non-zero" units that ends just before it is odd
+        const uint32_t zb0 = ~m0 & lt_mask, zb1 = ~m1 & lt_mask;
+        const uint32_t sA = ~m0 ? ((uint32_t)__clz((int)~m0) & 1u) : s0;     // state behind row 0
+        const uint32_t tail0 = zb0 ? ((lane - 32u + (uint32_t)__clz((int)zb0)) & 1u) : (s0 ^ (lane & 1u));
+        const uint32_t tail1 = zb1 ? ((lane - 32u + (uint32_t)__clz((int)zb1)) & 1u) : (sA ^ (lane & 1u));
+        s0 = ~m1 ? ((uint32_t)__clz((int)~m1) & 1u) : sA;
+        const bool lit0 = v0 && !tail0 && !h0, head0 = v0 && !tail0 && h0;
+        const bool lit1 = v1 && !tail1 && !h1, head1 = v1 && !tail1 && h1;
+        const uint32_t ml0 = head0 ? (nx0 >> 8) & 0xFFu : 0u, ml1 = head1 ? (nx1 >> 8) & 0xFFu : 0u;
+        const uint32_t off0 = head0 ? ((cur0 >> 8) | ((nx0 & 0xFFu) << 8)) : 0u, off1 = head1 ? ((cur1 >> 8) | ((nx1 & 0xFFu) << 8)) : 0u;
+        const uint32_t ol0 = lit0 ? 1u : ml0, ol1 = lit1 ? 1u : ml1;
+        const uint32_t incl = warp_incl_scan_u32(ol0 | (ol1 << 16));         // both rows at once (a row's sum is below 32 * 255)
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t total0 = tot & 0xFFFFu, total = total0 + (tot >> 16);
+        const uint32_t myo0 = o + (incl & 0xFFFFu) - ol0, myo1 = o + total0 + (incl >> 16) - ol1;
+        const bool copy0 = head0 && ml0 != 0u && off0 != 0u && off0 <= myo0, copy1 = head1 && ml1 != 0u && off1 != 0u && off1 <= myo1;
+        const uint32_t pk0 = off0 | (lit0 ? 0x10000u : 0u) | (copy0 ? 0x20000u : 0u) | ((cur0 >> 8) << 24);
+        const uint32_t pk1 = off1 | (lit1 ? 0x10000u : 0u) | (copy1 ? 0x20000u : 0u) | ((cur1 >> 8) << 24);
+        for (uint32_t r0 = 0; r0 < total; r0 += 64) {
+            uint32_t xs[2], sv[2], fl[2];
+#pragma unroll
+            for (uint32_t q = 0; q < 2; ++q) {
+                const uint32_t xr = r0 + 32u * q + lane;
+                const bool row = xr >= total0;
+                const uint32_t key = row ? xr - total0 : xr;
+                uint32_t j = 0;
+#pragma unroll
+                for (uint32_t st = 16; st > 0; st >>= 1) {
+                    const uint32_t ic = __shfl_sync(0xffffffffu, incl, (j + st - 1u) & 31u);
+                    if ((row ? ic >> 16 : ic & 0xFFFFu) <= key) j += st;
+                }
+                const uint32_t p0 = __shfl_sync(0xffffffffu, pk0, j & 31u), p1 = __shfl_sync(0xffffffffu, pk1, j & 31u);
+                const uint32_t pj = row ? p1 : p0;
+                const uint32_t x = o + xr;
+                const bool inb = xr < total && x < len;
+                xs[q] = x;
+                if (pj & 0x10000u) { sv[q] = pj >> 24; fl[q] = inb ? 1u : 0u; }
+                else { sv[q] = x - (pj & 0xFFFFu); fl[q] = (inb && (pj & 0x20000u)) ? 3u : (inb ? 4u : 0u); }
+            }
+            const bool dep = ((fl[0] & 2u) && sv[0] >= o) || ((fl[1] & 2u) && sv[1] >= o);
+            if (!__any_sync(0xffffffffu, dep)) {
+                uint32_t w0 = sv[0], w1 = sv[1];
+                if (fl[0] & 2u) w0 = __ldcg(gout + sv[0]);
+                if (fl[1] & 2u) w1 = __ldcg(gout + sv[1]);
+                if (fl[0] & 1u) gout[xs[0]] = (uint8_t)w0;
+                if (fl[1] & 1u) gout[xs[1]] = (uint8_t)w1;
+            } else {
+#pragma unroll 1
+                for (uint32_t q = 0; q < 2; ++q) {
+                    __syncwarp();
+                    const uint32_t sub = o + r0 + 32u * q;
+                    uint32_t val = sv[q], ptr = lane;
+                    bool done = true;
+                    if (fl[q] & 2u) {
+                        if (sv[q] < sub) val = __ldcg(gout + sv[q]);
+                        else { ptr = sv[q] - sub; done = false; }
+                    } else if (fl[q] & 4u) val = __ldcg(gout + xs[q]);
+                    while (__any_sync(0xffffffffu, !done)) {
+                        const uint32_t v2 = __shfl_sync(0xffffffffu, val, ptr);
+                        const uint32_t p2 = __shfl_sync(0xffffffffu, ptr, ptr);
+                        const bool d2 = __shfl_sync(0xffffffffu, done ? 1u : 0u, ptr) != 0u;
+                        if (!done) { if (d2) { val = v2; done = true; } else ptr = p2; }
+                    }
+                    if (fl[q] & 1u) gout[xs[q]] = (uint8_t)val;
+                }
+            }
+        }
+        o += total;
+        __syncwarp();
+    }
+}
+
 inline uint64_t round16(uint64_t x) { return (x + 15) & ~(uint64_t)15; }
 
 }  // namespace
@@ -653,7 +760,8 @@ extern "C" int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d
     }
     if (variant == 1 && !(seq && seq[0] == '1')) {
         B200_TIMED_BEGIN(ctx, B200_K_LZ_DECODE);
-        lz77_decode_units_kernel<0><<<(unsigned)((nblocks + 3) / 4), 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
+        if (getenv("B200_LZ_DEC_U32")) lz77_decode_units_kernel<0><<<(unsigned)((nblocks + 3) / 4), 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
+        else lz77_decode_units64_kernel<<<(unsigned)((nblocks + 3) / 4), 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
         lz77_decode_units_kernel<1><<<(unsigned)((nblocks + 3) / 4), 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
         B200_TIMED_END(ctx);
         ctx->launches += 2;
