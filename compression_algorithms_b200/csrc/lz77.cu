@@ -338,9 +338,13 @@ __global__ void __launch_bounds__(128) lz77_decode_units_kernel(const uint8_t* _
     const uint64_t b = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= nblocks) return;
     const uint32_t len = (uint32_t)(n - b * bs < bs ? n - b * bs : bs);
-    // two instantiations share the blocks: MODE 0 (bytes spread over the lanes) takes the literal-heavy ones, stream >= 1.1 x
-    // block; MODE 1 (a lane copies its own match) the others (measured on B200, 1 GB: text 5.8 against 6.8 ms, acgt 6.1 against 4.5)
-    if ((block_sizes[b] * 10ull >= (uint64_t)len * 11ull) != (MODE == 0)) return;
+    // three kernels share the blocks: MODE 0 (bytes spread over the lanes) takes the literal-heavy ones, stream >= 1.1 x
+    // block (from 1.9 x on: lz77_decode_units64_kernel); MODE 1 (a lane copies its own match) the others (measured on B200, 1 GB: text 5.8 against 6.8 ms, acgt 6.1 against 4.5)
+    {
+        const uint64_t s10 = block_sizes[b] * 10ull, l = (uint64_t)len;
+        if (s10 >= l * 19ull) return;                                     // nearly incompressible: lz77_decode_units64_kernel
+        if ((s10 >= l * 11ull) != (MODE == 0)) return;
+    }
     const uint16_t* tk = reinterpret_cast<const uint16_t*>(stream + block_off[b]);   // block offsets are even (tokens are 2 or 4 bytes)
     const uint32_t nunits = (uint32_t)(block_sizes[b] >> 1);
     uint8_t* gout = out + b * bs;
@@ -483,9 +487,10 @@ __global__ void __launch_bounds__(128) lz77_decode_units_kernel(const uint8_t* _
     }
 }
 
-// The byte-per-lane decoder of literal-heavy blocks at 64 units per step (a lane holds unit l of two rows of 32): the per-step
-// work that does not depend on the output (token look-ahead, classification, ONE packed scan of both rows' output lengths) is
-// paid once per 64 units, the bytes then go out 64 per round exactly as in lz77_decode_units_kernel<0>.
+// The byte-per-lane decoder at 64 units per step (a lane holds unit l of two rows of 32) for nearly incompressible blocks: a step
+// of 64 literals is two stores; the rest as lz77_decode_units_kernel<0> with ONE packed scan of both rows' output lengths.
+// (Measured on B200, 1 GB: near-random input 2.09 -> 1.58 ms; text is SLOWER this way, 6.3 against 5.8 ms - the longer step is a
+// longer chain of dependent shuffles and loads per warp - so text stays with 32 units per step.)
 __global__ void __launch_bounds__(128) lz77_decode_units64_kernel(const uint8_t* __restrict__ stream, const uint64_t* __restrict__ block_off,
                                                                  const uint64_t* __restrict__ block_sizes, uint64_t n, uint64_t bs,
                                                                  uint64_t nblocks, uint8_t* __restrict__ out) {
@@ -493,7 +498,7 @@ __global__ void __launch_bounds__(128) lz77_decode_units64_kernel(const uint8_t*
     const uint64_t b = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= nblocks) return;
     const uint32_t len = (uint32_t)(n - b * bs < bs ? n - b * bs : bs);
-    if (block_sizes[b] * 10ull < (uint64_t)len * 11ull) return;          // match-heavy block: lz77_decode_units_kernel<1>
+    if (block_sizes[b] * 10ull < (uint64_t)len * 19ull) return;          // only nearly incompressible blocks (stream >= 1.9 x block)
     const uint16_t* tk = reinterpret_cast<const uint16_t*>(stream + block_off[b]);
     const uint32_t nunits = (uint32_t)(block_sizes[b] >> 1);
     uint8_t* gout = out + b * bs;
@@ -760,11 +765,11 @@ extern "C" int b200_lz77_decode_dev(b200_ctx* ctx, int variant, const uint8_t* d
     }
     if (variant == 1 && !(seq && seq[0] == '1')) {
         B200_TIMED_BEGIN(ctx, B200_K_LZ_DECODE);
-        if (getenv("B200_LZ_DEC_U32")) lz77_decode_units_kernel<0><<<(unsigned)((nblocks + 3) / 4), 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
-        else lz77_decode_units64_kernel<<<(unsigned)((nblocks + 3) / 4), 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
+        lz77_decode_units_kernel<0><<<(unsigned)((nblocks + 3) / 4), 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
+        lz77_decode_units64_kernel<<<(unsigned)((nblocks + 3) / 4), 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
         lz77_decode_units_kernel<1><<<(unsigned)((nblocks + 3) / 4), 128, 0, ctx->stream>>>(d_stream, d_block_off, d_block_sizes, n, bs, nblocks, d_out);
         B200_TIMED_END(ctx);
-        ctx->launches += 2;
+        ctx->launches += 3;
         CUDA_TRY(cudaGetLastError());
         return B200_OK;
     }
