@@ -257,10 +257,11 @@ def _random_token_block(rng, out_len, style):
     o = 0
     while o < out_len:
         r = rng.random()
-        if o == 0 or r < (0.15 if style == "matches" else 0.93 if style == "sparse" else 0.6):
+        if o == 0 or r < (0.15 if style == "matches" else 0.93 if style == "sparse" else 0.995 if style == "nearlit" else 0.6):
             tok += bytes((0, int(rng.integers(0, 256)))); o += 1
             continue
-        if style == "sparse":
+        if style in ("sparse", "nearlit"):
+            # ("nearlit": stream above 1.9 x block, the 64-units-per-step kernel)
             # literal-heavy (stream above 1.1 x block: the decoder's byte-per-lane instantiation) with short matches that
             # read what the same 32-unit step has just produced: offsets 1 .. 40, overlapping copies included
             off = int(rng.integers(1, min(o, 40) + 1))
@@ -279,12 +280,12 @@ def _random_token_block(rng, out_len, style):
     return bytes(tok)
 
 
-@pytest.mark.parametrize("style", ["mixed", "matches", "rle", "far", "sparse"])
+@pytest.mark.parametrize("style", ["mixed", "matches", "rle", "far", "sparse", "nearlit"])
 def test_decoder_on_handmade_streams(ctx, ob, style, monkeypatch):
     """both deflate-variant decoders (token-parallel units, token-serial) against the oracle's byte-serial decoder"""
     import torch
     from compression_algorithms_b200 import device as dv
-    rng = np.random.default_rng({"mixed": 1, "matches": 2, "rle": 3, "far": 4, "sparse": 5}[style])
+    rng = np.random.default_rng({"mixed": 1, "matches": 2, "rle": 3, "far": 4, "sparse": 5, "nearlit": 6}[style])
     block = 4096
     lens = [block] * 6 + [1, 2, 33, 777]
     n = sum(lens)
