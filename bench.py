@@ -605,7 +605,7 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "kernel": "deflate-variant match finder of the encode call: lz77_v4_kernel for text-like input (a byte-entropy sample decides), lz77_v2_kernel for the blocks it hands back and for other input; + greedy parse + token emission; rank 0's shard",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "static: dram__bytes of one ncu --set full capture at 100 MB (profiles/roofline_traffic.json), scaled to this launch's input; not re-measured per run",
+                "traffic_source": "static: dram__bytes per input byte of one ncu --set full capture of this kernel (profiles/roofline_traffic.json: lz77_v4_kernel over 296 blocks, lz77_v2_kernel over 100 MB), scaled to this launch's input; not re-measured per run",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": n + T, "avg_launch_ms": parse_avg,
                 "launches_timed": len(parse_ms), "share_of_step": parse_avg / ms_per_step,
                 "decode_kernel_avg_ms": float(np.mean(dec_ms)) if dec_ms else None,
