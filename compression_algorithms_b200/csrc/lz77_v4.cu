@@ -164,13 +164,12 @@ __device__ __forceinline__ void lane_cluster(const ST* S, uint16_t* E1x, uint16_
     }
 }
 
-// insertion sort of bare positions (m <= 16); returns the smallest hash = the raw slot the cluster starts on (the first
-// slot of a cluster is the home of the entry that sits in it, and no entry of the cluster has its home before it)
+// insertion sort of bare positions (m <= 16); returns the raw slot the cluster starts on = the hash of the entry that sits in
+// its first slot (nothing is occupied below it, so that entry cannot have probed its way there), read before the sort
 __device__ __forceinline__ uint32_t lane_sort16(uint16_t* S, uint32_t m, const uint8_t* data) {
-    uint32_t hmin = lz_hash(sm_word(data, S[0]));
+    const uint32_t hmin = lz_hash(sm_word(data, S[0]));
     for (uint32_t i = 1; i < m; ++i) {
         const uint32_t e = S[i];
-        hmin = min(hmin, lz_hash(sm_word(data, e)));
         uint32_t j = i;
         while (j > 0) { const uint32_t f = S[j - 1]; if (f <= e) break; S[j] = (uint16_t)f; --j; }
         S[j] = (uint16_t)e;
@@ -989,7 +988,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
 #define SUBSTAMP(acc) do { if (DBG) { const long long t_now = clk_ordered(); acc += t_now - t_mark; t_mark = t_now; } } while (0)
         if (!fb0 && !ms->fallback) {
             // ---- lane stage: every entry's bare position at S16[compact slot] (131072 bytes: the whole block at once; the home
-            // offsets come back from the hashes, lane_sort16), clusters of 2 .. LMAX entries one lane each
+            // offsets come back from the hashes, lane_cluster), clusters of 2 .. LMAX entries one lane each
             uint16_t* S16 = reinterpret_cast<uint16_t*>(big);
             if (tid == 0) { for (int c = 0; c < 7; ++c) { ms->ccnt[c] = 0; ms->cfill[c] = 0; } }
             for (uint32_t i0 = tid; i0 < len; i0 += 8 * NTHREADS) {
@@ -1071,8 +1070,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                     const uint32_t it = g + lane;
                     if (it < total) {
                         const uint32_t kl = wl_get(it), m = csize(kl);
-                        const uint32_t hmin = lane_sort16(S16 + kl, m, data);
-                        lane_cluster<true>(S16 + kl, nullptr, nullptr, m, hmin, data, fres);
+                        if (m == 2u) {
+                            // two entries (half of all listed clusters): the later one finds the earlier one iff that is still live
+                            // and has its 4-gram (equal 4-grams share the home; with different homes the later entry's own home
+                            // is dead or never taken, and find scans nothing)
+                            const uint32_t a = S16[kl], c = S16[kl + 1];
+                            const uint32_t p0 = min(a, c), p1 = max(a, c);
+                            fres[p0] = (uint16_t)NONE16;
+                            fres[p1] = (uint16_t)((p0 + W >= p1 && sm_word(data, p0) == sm_word(data, p1)) ? p0 : NONE16);
+                        } else {
+                            const uint32_t hmin = lane_sort16(S16 + kl, m, data);
+                            lane_cluster<true>(S16 + kl, nullptr, nullptr, m, hmin, data, fres);
+                        }
                     }
                 }
                 if (DBG) SUBSTAMP(dt_w);
