@@ -1015,6 +1015,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
             auto wl_get = [&](uint32_t i) -> uint32_t { return i < WL_CAP ? wl[i] : wlg[i - WL_CAP]; };
             const uint32_t sp_hi = len - (SLOTS - sp_top);
             uint32_t nlb[2] = {0, 0};                         // starts of clusters of 2 .. LMAX entries among my slots
+            uint32_t cA = 0, cB = 0;                          // my clusters per size class: 9..16 | 5..8 << 16, 3..4 | 2 << 16
 #pragma unroll
             for (uint32_t h = 0; h < 2; ++h) {
                 const uint32_t a = (2 * tid + h) * 32;
@@ -1035,10 +1036,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                             if (bi < NBIG) bigl[bi] = start | (m << 16); else ms->fallback = 1u;
                             continue;
                         }
-                        atomicAdd(&ms->ccnt[cls_of(m)], 1u);
+                        const uint32_t c = cls_of(m);
+                        if (c < 5u) cA += c == 3u ? 1u : 0x10000u; else cB += c == 5u ? 1u : 0x10000u;
                     }
                 }
             }
+            // places inside the list without an atomic per cluster (four counters shared by 9 000 clusters serialise): a warp scan of
+            // the per-thread counts, one atomicAdd per class and warp
+            const uint32_t iA = warp_incl_scan_u32(cA), iB = warp_incl_scan_u32(cB);
+            uint32_t wA = 0, wB = 0;                          // the warp's first place inside each class
+            if (lane == 31) {
+                wA = atomicAdd(&ms->ccnt[3], iA & 0xFFFFu) | (atomicAdd(&ms->ccnt[4], iA >> 16) << 16);
+                wB = atomicAdd(&ms->ccnt[5], iB & 0xFFFFu) | (atomicAdd(&ms->ccnt[6], iB >> 16) << 16);
+            }
+            wA = __shfl_sync(0xffffffffu, wA, 31); wB = __shfl_sync(0xffffffffu, wB, 31);
+            uint32_t myA = wA + iA - cA, myB = wB + iB - cB;  // my first place inside each class (16-bit halves; a class holds < 32 768 clusters)
             __syncthreads();
             if (tid == 0) {
                 uint32_t run = 0;
@@ -1054,7 +1066,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                     const uint32_t k = (uint32_t)(__ffs(nlbits) - 1);
                     nlbits &= nlbits - 1;
                     const uint32_t c = cls_of(csize(a + k));
-                    wl_put(ms->cbase[c] + atomicAdd(&ms->cfill[c], 1u), a + k);
+                    uint32_t place;
+                    if (c == 3u) { place = myA & 0xFFFFu; myA += 1u; } else if (c == 4u) { place = myA >> 16; myA += 0x10000u; }
+                    else if (c == 5u) { place = myB & 0xFFFFu; myB += 1u; } else { place = myB >> 16; myB += 0x10000u; }
+                    wl_put(ms->cbase[c] + place, a + k);
                 }
             }
             __syncthreads();
