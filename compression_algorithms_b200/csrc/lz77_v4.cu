@@ -1015,6 +1015,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
             auto wl_get = [&](uint32_t i) -> uint32_t { return i < WL_CAP ? wl[i] : wlg[i - WL_CAP]; };
             const uint32_t sp_hi = len - (SLOTS - sp_top);
             uint32_t nlb[2] = {0, 0};                         // starts of clusters of 2 .. LMAX entries among my slots
+            unsigned long long ccl[2] = {0, 0};               // ... and their size classes, two bits per slot (for the second pass)
             uint32_t cA = 0, cB = 0;                          // my clusters per size class: 9..16 | 5..8 << 16, 3..4 | 2 << 16
 #pragma unroll
             for (uint32_t h = 0; h < 2; ++h) {
@@ -1037,6 +1038,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                             continue;
                         }
                         const uint32_t c = cls_of(m);
+                        ccl[h] |= (unsigned long long)(c - 3u) << (2u * k);
                         if (c < 5u) cA += c == 3u ? 1u : 0x10000u; else cB += c == 5u ? 1u : 0x10000u;
                     }
                 }
@@ -1065,7 +1067,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
                 while (nlbits && !ms->fallback) {
                     const uint32_t k = (uint32_t)(__ffs(nlbits) - 1);
                     nlbits &= nlbits - 1;
-                    const uint32_t c = cls_of(csize(a + k));
+                    const uint32_t c = 3u + ((uint32_t)(ccl[h] >> (2u * k)) & 3u);
                     uint32_t place;
                     if (c == 3u) { place = myA & 0xFFFFu; myA += 1u; } else if (c == 4u) { place = myA >> 16; myA += 0x10000u; }
                     else if (c == 5u) { place = myB & 0xFFFFu; myB += 1u; } else { place = myB >> 16; myB += 0x10000u; }
