@@ -871,34 +871,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
             }
             __syncthreads();
             uint32_t run = ms->scan[warp] + incl - mine;
-            uint32_t fw = 0xFFFFFFFFu, fbits = 0;
-#pragma unroll 1
+#pragma unroll
             for (int k = 0; k < 5; ++k) {
                 const uint32_t ch = c0 + k;
-                if (ch >= PRE_N) break;
-                pre16[2 * ch] = (uint16_t)run; pre16[2 * ch + 1] = (uint16_t)(run + half[k]);
-                if (part[k]) {
-                    uint32_t rw = run;
-                    for (uint32_t wq_ = 0; wq_ < PRE_CHUNK; ++wq_) {
-                        const uint32_t widx = ch * PRE_CHUNK + wq_;
-                        const uint32_t xw = bm[widx];
-                        if (xw) {
-                            const uint32_t prev = widx ? bm[widx - 1] >> 31 : 0u;
-                            uint32_t st = xw & ~((xw << 1) | prev);
-                            while (st) {
-                                const uint32_t bp = (uint32_t)(__ffs(st) - 1);
-                                st &= st - 1;
-                                const uint32_t u = rw + __popc(xw & ((1u << bp) - 1u));
-                                if ((u >> 5) != fw) { if (fbits) atomicOr(&flags[fw], fbits); fw = u >> 5; fbits = 0; }
-                                fbits |= 1u << (u & 31);
-                            }
-                            rw += __popc(xw);
-                        }
-                    }
-                }
+                if (ch < PRE_N) { pre16[2 * ch] = (uint16_t)run; pre16[2 * ch + 1] = (uint16_t)(run + half[k]); }
                 run += part[k];
             }
-            if (fbits) atomicOr(&flags[fw], fbits);
+            __syncthreads();
+            // cluster-start flags, four bitmap words per thread and step, consecutive threads on consecutive groups (a walk along a
+            // thread's own 40 words has eight lanes of a warp on every bank): the rank before a group comes from the prefix, the bit
+            // before it from the neighbouring lane
+            for (uint32_t g0 = 0; g0 < BM_WORDS / 4; g0 += NTHREADS) {
+                const uint32_t g = g0 + tid;
+                const bool in = g < BM_WORDS / 4;
+                const uint4 q = in ? *reinterpret_cast<const uint4*>(bm + 4 * g) : make_uint4(0u, 0u, 0u, 0u);
+                uint32_t prev = __shfl_up_sync(0xffffffffu, q.w, 1);
+                if (lane == 0) prev = (in && g) ? bm[4 * g - 1] : 0u;
+                prev >>= 31;
+                if (q.x | q.y | q.z | q.w) {
+                    const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+                    uint32_t rw = pre16[g], fw = 0xFFFFFFFFu, fbits = 0;
+#pragma unroll
+                    for (uint32_t wq_ = 0; wq_ < 4; ++wq_) {
+                        const uint32_t xw = wd[wq_];
+                        uint32_t st = xw & ~((xw << 1) | prev);
+                        while (st) {
+                            const uint32_t bp = (uint32_t)(__ffs(st) - 1);
+                            st &= st - 1;
+                            const uint32_t u = rw + __popc(xw & ((1u << bp) - 1u));
+                            if ((u >> 5) != fw) { if (fbits) atomicOr(&flags[fw], fbits); fw = u >> 5; fbits = 0; }
+                            fbits |= 1u << (u & 31);
+                        }
+                        rw += __popc(xw);
+                        prev = xw >> 31;
+                    }
+                    if (fbits) atomicOr(&flags[fw], fbits);
+                }
+            }
             if (tid == 0) atomicOr(&flags[len >> 5], 1u << (len & 31));   // sentinel behind the last compact slot
         }
         __syncthreads();
