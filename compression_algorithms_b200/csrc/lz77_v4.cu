@@ -1088,11 +1088,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lz77_v4_kernel(const uint8_t* __r
             if (!ms->fallback) {
                 const uint32_t total = ms->cbase[7];
                 if (DBG) { ++n_chunks; n_wq += total; }
-                for (;;) {                                   // 32 clusters of similar size per warp, one lane each
-                    uint32_t g = 0;
-                    if (lane == 0) g = atomicAdd(&ms->next_l, 32u);
-                    g = __shfl_sync(0xffffffffu, g, 0);
-                    if (g >= total) break;
+                for (uint32_t rr = 0; rr * 1024u < total; ++rr) {             // 32 clusters of similar size per warp, one lane each; batches dealt
+                    const uint32_t g = rr * 1024u + ((rr & 1u) ? 31u - warp : warp) * 32u;   // in snake order (the list runs from the costly to the cheap)
+                    if (g >= total) continue;
                     const uint32_t it = g + lane;
                     if (it < total) {
                         const uint32_t kl = wl_get(it), m = csize(kl);
