@@ -94,7 +94,7 @@ def test_match_finder_candidates(ctx, ob):
             assert int(tok[b, p]) == want, "block %d position %d" % (b, p)
 
 
-@pytest.mark.parametrize("kind,expect_v4", [(0, True), (1, True), (2, False), (3, False)])
+@pytest.mark.parametrize("kind,expect_v4", [(0, True), (1, True), (2, False), (3, True)])
 def test_default_choice_by_sample(ctx, ob, monkeypatch, kind, expect_v4):
     """no override: a byte-entropy sample of the input picks the kernel (text-like -> v4); the stream is the oracle's either way.
     The debug statistics tell which kernel ran: lz77_v4_kernel leaves its cluster counters behind stamp 8."""
