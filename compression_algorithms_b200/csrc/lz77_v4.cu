@@ -17,17 +17,21 @@
 //    run of phase-1 slots because those were filled in time order).
 //  * find(p) only ever looks at the slots [home(p), slot(p)): all live at time p by construction, so the find is a
 //    bounded scan for the first occupant (e1 if still live, else e2) with p's pattern. No liveness test, no table.
-//  * Clusters of up to 8 entries (80 % of the non-trivial ones) are simulated by ONE thread in registers
-//    (liveness mask + FIFO expiry pointer); 9..64 by a warp, larger ones by a team of four warps, with the sweeps
-//    above; a cluster of one entry (a third of text positions) is a literal candidate and costs nothing.
-//  * Blocks this kernel does not take (a cluster touching slot 0 or the table end: the reference's early slot-0
-//    clear and the wrapping insert; a cluster above 16383 entries) are listed and run through lz77_v2_kernel.
+//  * Clusters of up to 16 entries (95 % of the non-trivial ones) are simulated by ONE lane in registers (liveness mask + FIFO
+//    expiry pointer; two entries in closed form), 17..64 by a lane after a warp sort, 65..256 by a warp and larger ones by a
+//    team of four warps with the sweeps above; a cluster of one entry (a third of text positions) is a literal candidate
+//    and costs nothing.
+//  * The clusters on slot 0 and on the table's last slot (the reference's early slot-0 clear, U10, and its wrapping insert) are
+//    simulated by one thread with the reference's own rules when they have at most 60 slots together. Blocks this kernel does
+//    not take (larger special clusters, a cluster above 16383 entries, more than 512 clusters above 16 entries) are listed and
+//    run through lz77_v2_kernel.
 //
 // Phases per block (one persistent CTA of 1024 threads per SM):
 //   P0 load | P1 occupancy bitmap, claimed slot per position | P2 rank prefix, cluster-start flags
-//   P3 rank of the claimed slot -> (compact slot, displacement) per position; loners marked
-//   per chunk of <= 17408 compact slots: scatter entries into shared memory by compact slot, small clusters by
-//   threads, larger ones by warps / four-warp teams -> F(p) (u16, global, L2 resident)
+//   P3 rank of the claimed slot -> (compact slot, displacement) per position; loners marked; the special clusters
+//   lane stage: every entry's position (u16) to its compact slot in shared memory, work list by size class, clusters of up to
+//   16 entries one lane each | final stage: the larger clusters, all at once (lane batches, warps, four-warp teams)
+//   -> F(p) (u16, global, L2 resident)
 //   P5 token candidates (match extension) + greedy parse | P6 token emission   (as v2)
 #include "common.cuh"
 #include "../../include/b200comp.h"
