@@ -603,7 +603,7 @@ def main():
             traffic = int(per_byte * n) if per_byte else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "deflate-variant match finder of the encode call: lz77_v4_kernel for text-like input (a byte-entropy sample decides), lz77_v2_kernel for the blocks it hands back and for other input; + greedy parse + token emission; rank 0's shard",
+    roofline = {"bound": "hbm", "kernel": "deflate-variant match finder of the encode call: lz77_v4_kernel for input of at least 1.5 bits per byte (a byte-entropy sample decides), lz77_v2_kernel for the blocks it hands back and for few-symbol input; + greedy parse + token emission; rank 0's shard",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "static: dram__bytes per input byte of one ncu --set full capture of this kernel (profiles/roofline_traffic.json: lz77_v4_kernel over 296 blocks, lz77_v2_kernel over 100 MB), scaled to this launch's input; not re-measured per run",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": n + T, "avg_launch_ms": parse_avg,
